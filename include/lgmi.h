@@ -1,0 +1,207 @@
+/*
+ * lgmi.h -- C ABI of liblgmi.so, the B200 (sm_100a) implementation of the
+ * L-GIREMI mutual-information step.
+ *
+ * The reference (gxiaolab/L-GIREMI v0.2.4) is pure Python and has no FFI of
+ * its own; the seam this library sits behind is three Python functions:
+ *
+ *   mismatch_pair_mutual_info(mismatches, min_common_reads)
+ *        /root/reference/src/giremi/mutual_information.py:6-45
+ *        (called at /root/reference/src/giremi/mismatch.py:389)
+ *   mean_mismatch_pair_mutual_info(rows)
+ *        /root/reference/src/giremi/mutual_information.py:48-60
+ *        (called at /root/reference/src/giremi/mismatch.py:398, after the het
+ *         filter at mismatch.py:393-396)
+ *   ecdf(x) and its use for `mip` + the threshold call
+ *        /root/reference/src/giremi/stat.py:7-29,
+ *        /root/reference/src/giremi/script/giremi.py:415-429, :97-114
+ *
+ * Every entry point below names the reference lines it replaces.  The ctypes
+ * binding a reference maintainer would add is shown in INTEGRATION.md and
+ * lives in l-giremi_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative lgmi_status on error;
+ *     lgmi_last_error() gives the message.  No C++ exception crosses the ABI.
+ *   - plain pointers + sizes only.  Host buffers passed to *_upload / *_submit
+ *     must stay alive until the matching lgmi_batch_sync()/lgmi_wait().
+ *   - one lgmi_t per process per GPU (one process per GPU is the scaling
+ *     model; there is no collective on this path).  Not thread-safe: callers
+ *     serialise calls on one handle.
+ *   - there is NO CPU fallback: without a CUDA device lgmi_create() fails.
+ */
+#ifndef LGMI_H_
+#define LGMI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGMI_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  LGMI_OK = 0,
+  LGMI_ERR_CUDA = -1,       /* a CUDA runtime call failed                      */
+  LGMI_ERR_ARG = -2,        /* bad argument (null, misaligned, out of range)   */
+  LGMI_ERR_NOMEM = -3,      /* host or device allocation failed                */
+  LGMI_ERR_STATE = -4,      /* call sequence violated (run before upload, ...) */
+  LGMI_ERR_NODEVICE = -5,   /* no usable sm_100 device                         */
+  LGMI_ERR_UNSUPPORTED = -6 /* shape outside what this build supports          */
+} lgmi_status;
+
+/* ----- input encoding ---------------------------------------------------- *
+ * A *unit* is one (footprint, strand): the `mismatches[strand]` dict consumed
+ * at mutual_information.py:10-26.  It is shipped as three bit-planes per site
+ * over the unit's R distinct read names (bit r of word r/32, little endian):
+ *     M  read carries the site's major allele   (label 2, :33-38)
+ *     m  read carries the site's minor allele   (label 1)
+ *     C  read covers the site at all            (label 0 "other" = C & ~M & ~m)
+ * Major/minor are decided site-wide by `depth` with the reference's stable
+ * tie-break (:25-32); duplicate read names are resolved last-wins (:15-16) by
+ * the encoder before packing.  Sites are in ascending position order.
+ *
+ * Layout of one unit inside the planes buffer (32-bit words):
+ *     row(s) = [ M[0..W) | m[0..W) | C[0..W) ],   s = 0..S-1, row stride 3*W
+ *     W = row_words = 4*ceil(R/128)   (each plane row is a whole number of
+ *                                      16-byte vectors; pad bits are zero)
+ * plane_off is the unit's first word, a multiple of 4 (16-byte aligned).
+ */
+typedef struct {
+  uint64_t plane_off; /* first 32-bit word of the unit in the planes buffer    */
+  uint32_t n_sites;   /* S >= 0; S < 2 yields no pairs; S <= 65535             */
+  uint32_t n_reads;   /* R                                                     */
+  uint32_t row_words; /* W = 4*ceil(R/128)                                     */
+  uint32_t site_off;  /* first entry of the unit in site_flags / site outputs  */
+} lgmi_unit_desc;
+
+/* per-site flag byte */
+#define LGMI_SITE_TYPE_MASK 0x03u
+#define LGMI_SITE_MISMATCH 0u /* 'mismatch'  (mismatch.py:326-340 typing)      */
+#define LGMI_SITE_SNP 1u      /* 'snp'                                         */
+#define LGMI_SITE_HET_SNP 2u  /* 'het_snp' -- the only partner type that keeps */
+                              /* a pair (mismatch.py:393-396)                  */
+#define LGMI_SITE_HAS_OTHER 0x04u /* some read has label 0 at this site; the   */
+                                  /* encoder sets it, kernels may also derive  */
+
+/* run modes (bit flags) */
+#define LGMI_MODE_ALL_PAIRS 0x0u   /* emit every pair passing min_common       */
+                                   /* (= mismatch_pair_mutual_info's return)   */
+#define LGMI_MODE_HET_ONLY 0x1u    /* emit only pairs with a het_snp partner   */
+                                   /* (= after mismatch.py:393-396); MI is     */
+                                   /* still evaluated for every candidate      */
+#define LGMI_MODE_EMIT_COUNTS 0x2u /* also emit the 3x3 tables of emitted pairs*/
+#define LGMI_MODE_SKIP_NONHET 0x4u /* with HET_ONLY: do not evaluate MI of     */
+                                   /* pairs without a het partner (dead work   */
+                                   /* in the reference); reported   */
+                                   /* separately, never in the headline        */
+
+/* one emitted pair == one row [p1,type1,p2,type2,mi] of                       *
+ * mutual_information.py:42-44; i<j index the unit's sorted positions.         */
+typedef struct {
+  uint32_t unit;
+  uint16_t i;
+  uint16_t j;
+  double mi;
+} lgmi_pair_rec;
+
+/* results of one batch; pointers are HOST memory owned by the batch, valid    *
+ * until the batch is run again or destroyed.                                  */
+typedef struct {
+  uint64_t n_candidates;        /* sum over units of S(S-1)/2                  */
+  uint64_t n_evaluated;         /* candidates whose MI was computed or dropped */
+                                /* by the filter (== n_candidates unless       */
+                                /* SKIP_NONHET)                                */
+  uint64_t n_records;           /* emitted pairs                               */
+  const lgmi_pair_rec* records; /* unit order, then pair order (i, then j) --  */
+                                /* exactly the reference's row order           */
+  const uint32_t* counts;       /* 9 per record [a*3+b], a,b in {0 other,      */
+                                /* 1 minor, 2 major}; NULL unless EMIT_COUNTS  */
+  uint64_t n_sites;             /* length of the two per-site arrays           */
+  const double* site_mean;      /* mean MI over het-kept pairs, NaN if none    */
+                                /* (mutual_information.py:48-60,               */
+                                /*  mismatch.py:476-479)                       */
+  const uint32_t* site_cnt;     /* number of het-kept pairs per site           */
+  const uint64_t* unit_rec_off; /* n_units+1 offsets of each unit's records    */
+  float kernel_ms;              /* device time of the compute kernels          */
+} lgmi_result;
+
+typedef struct lgmi_ctx lgmi_t;
+typedef struct lgmi_batch lgmi_batch_t;
+
+/* ----- context ------------------------------------------------------------ */
+int lgmi_version(void);
+/* device: CUDA ordinal.  Fails with LGMI_ERR_NODEVICE if there is no GPU.     */
+int lgmi_create(int device, lgmi_t** out);
+void lgmi_destroy(lgmi_t* ctx);
+const char* lgmi_last_error(const lgmi_t* ctx); /* ctx may be NULL: last create error */
+/* Launch on a caller-owned stream (cudaStream_t as void*), e.g. torch's       *
+ * current stream so that torch.cuda.Event brackets the kernels. NULL restores *
+ * the context's own stream.                                                   */
+int lgmi_set_stream(lgmi_t* ctx, void* cuda_stream);
+int lgmi_pinned_alloc(lgmi_t* ctx, size_t bytes, void** out);
+int lgmi_pinned_free(lgmi_t* ctx, void* ptr);
+/* number of kernels this library has launched on the context so far           */
+uint64_t lgmi_launch_count(const lgmi_t* ctx);
+
+/* ----- batched MI step: replaces the per-unit loop                           *
+ *   mismatch.py:387-404 = mutual_information.py:6-45 -> het filter -> :48-60  */
+/* Builds device-side work tables and sizes the outputs for `units`.           */
+int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units,
+                      uint64_t plane_words, uint64_t n_sites, lgmi_batch_t** out);
+void lgmi_batch_destroy(lgmi_batch_t* b);
+/* async H2D of planes (plane_words u32) and site_flags (n_sites bytes)        */
+int lgmi_batch_upload(lgmi_batch_t* b, const uint32_t* planes, const uint8_t* site_flags);
+/* launches the kernels (async).  min_common: keep a pair iff                  *
+ * common >= min_common (strict '<' drop, mutual_information.py:19).           */
+int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode);
+/* async D2H of whatever the last run produced, then stream sync; fills *out.  */
+int lgmi_batch_download(lgmi_batch_t* b, lgmi_result* out);
+/* stream sync only; fills the scalar fields of *out (no record copy)          */
+int lgmi_batch_sync(lgmi_batch_t* b, lgmi_result* out);
+/* device pointers of the batch's buffers, for device-resident callers         *
+ * (benchmarks that generate or keep inputs in HBM).                           */
+int lgmi_batch_device_ptrs(lgmi_batch_t* b, void** d_planes, void** d_site_flags,
+                           void** d_records, void** d_site_mean);
+/* algorithmic bytes of the last run: planes + flags read once,    *
+ * 16 B per emitted record, 12 B per site.                                     */
+int lgmi_batch_algorithmic_bytes(lgmi_batch_t* b, uint64_t* bytes);
+
+/* one-shot convenience: create + upload + run + download (+ destroy on wait)  */
+int lgmi_submit(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units,
+                const uint32_t* planes, uint64_t plane_words,
+                const uint8_t* site_flags, uint64_t n_sites, int min_common,
+                uint32_t mode);
+int lgmi_wait(lgmi_t* ctx, lgmi_result* out); /* result valid until next submit */
+
+/* ----- mean of pre-computed rows: mutual_information.py:48-60 -------------- *
+ * CSR form: site s owns values[offsets[s] .. offsets[s+1]) in row order.      *
+ * mean[s] = sum/len with CPython's compensated float sum; NaN for empty.      */
+int lgmi_site_mean_csr(lgmi_t* ctx, const uint64_t* offsets, const double* values,
+                       uint64_t n_sites, double* mean_out);
+
+/* ----- global pass: stat.py:7-29 + giremi.py:415-429 + :97-114 ------------- *
+ * mip[s]  = NaN if mean[s] is NaN, else (#het means strictly below mean[s])   *
+ *           mapped through y = [0] ++ linspace(1/n, 1, n)                     *
+ * call[s] = 1 if mean notna & mip<=thr & type==mismatch                       *
+ *           2 if mean notna & mip> thr & type!=mismatch, else 0               *
+ * site_flags carries the type in its low 2 bits.  call may be NULL.           */
+int lgmi_ecdf(lgmi_t* ctx, const double* mean, const uint8_t* site_flags, uint64_t n,
+              double threshold, double* mip, uint8_t* call);
+/* ecdf(x)(samples): y[searchsorted(sort(x), samples, 'left')]  (stat.py:16-27)*/
+int lgmi_ecdf_eval(lgmi_t* ctx, const double* x, uint64_t n, const double* samples,
+                   uint64_t n_samples, double* out);
+
+/* ----- multi-GPU partitioning (no collective) ------------------- *
+ * cost(unit) = S(S-1)/2 * ceil(R/64).  Longest-processing-time greedy into    *
+ * n_bins; bin_of[u] receives the bin.  Deterministic (ties: lower index).     */
+uint64_t lgmi_unit_cost(uint32_t n_sites, uint32_t n_reads);
+int lgmi_partition_lpt(const uint64_t* cost, uint32_t n_units, uint32_t n_bins,
+                       uint32_t* bin_of, uint64_t* bin_load);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGMI_H_ */

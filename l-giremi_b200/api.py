@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference's MI interface, backed by liblgmi.so.
+
+Same names, argument meaning, return shapes, row order and error behaviour as
+
+  giremi.mutual_information.mismatch_pair_mutual_info        (:6-45)
+  giremi.mutual_information.mean_mismatch_pair_mutual_info   (:48-60)
+  giremi.stat.ecdf                                           (stat.py:7-29)
+
+plus the batched step (`mi_step_batched`) that replaces the per-unit loop of
+giremi.mismatch.region_mismatch_analysis (mismatch.py:387-404) with one submit.
+Nothing here computes MI on the CPU; without the CUDA library or a GPU every
+entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (MODE_ALL_PAIRS, MODE_EMIT_COUNTS, MODE_HET_ONLY, MODE_SKIP_NONHET,
+                   PAIR_REC, SITE_TYPE_CODE, LgmiError, Result, array_at, check, ptr)
+from .encode import PlaneBatch, encode_batch, encode_mismatches, pack_units
+
+
+class Context:
+    """One liblgmi handle == one process on one GPU."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.lgmi_create(int(device), C.byref(h))
+        if rc != 0:
+            msg = self._lib.lgmi_last_error(None)
+            raise LgmiError(rc, msg.decode() if msg else "")
+        self.handle = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.lgmi_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        """Launch on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(self._lib.lgmi_set_stream(self.handle, C.c_void_p(cuda_stream_ptr or 0)), self.handle)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.lgmi_launch_count(self.handle))
+
+    def pinned_empty(self, shape, dtype):
+        """numpy array backed by cudaHostAlloc memory (kept alive by the returned object)."""
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        p = C.c_void_p()
+        check(self._lib.lgmi_pinned_alloc(self.handle, max(1, count * dtype.itemsize), C.byref(p)), self.handle)
+        arr = array_at(p.value, dtype, count).reshape(shape) if count else np.empty(shape, dtype)
+        return _Pinned(self, p.value, arr)
+
+
+class _Pinned:
+    def __init__(self, ctx, address, array):
+        self.ctx, self.address, self.array = ctx, address, array
+
+    def free(self):
+        if self.address and self.ctx.handle:
+            self.ctx._lib.lgmi_pinned_free(self.ctx.handle, C.c_void_p(self.address))
+        self.address = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def get_context(device=None) -> Context:
+    """Process-wide context, created on first use (after any fork: CUDA must be
+    initialised in the process that uses it)."""
+    global _default_ctx
+    if _default_ctx is None or _default_ctx.handle is None:
+        import os
+        if device is None:
+            device = int(os.environ.get("LGMI_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        _default_ctx = Context(device)
+    return _default_ctx
+
+
+class StepResult:
+    """Host view of one batch's outputs (copies: safe after the batch is reused)."""
+
+    def __init__(self, res: Result, n_units, copy=True):
+        self.n_candidates = int(res.n_candidates)
+        self.n_evaluated = int(res.n_evaluated)
+        self.n_records = int(res.n_records)
+        self.kernel_ms = float(res.kernel_ms)
+        rec = array_at(res.records, PAIR_REC, self.n_records)
+        mean = array_at(res.site_mean, np.float64, int(res.n_sites))
+        cnt = array_at(res.site_cnt, np.uint32, int(res.n_sites))
+        off = array_at(res.unit_rec_off, np.uint64, n_units + 1)
+        counts = array_at(res.counts, np.uint32, self.n_records * 9).reshape(-1, 9) if res.counts else None
+        if copy:
+            rec, mean, cnt, off = rec.copy(), mean.copy(), cnt.copy(), off.copy()
+            counts = counts.copy() if counts is not None else None
+        self.records, self.site_mean, self.site_cnt, self.unit_rec_off, self.counts = rec, mean, cnt, off, counts
+
+    def unit_records(self, unit):
+        a, b = int(self.unit_rec_off[unit]), int(self.unit_rec_off[unit + 1])
+        return self.records[a:b]
+
+    def unit_counts(self, unit):
+        a, b = int(self.unit_rec_off[unit]), int(self.unit_rec_off[unit + 1])
+        return self.counts[a:b]
+
+
+class Batch:
+    """Device-side batch: create once, then upload / run / download repeatedly."""
+
+    def __init__(self, ctx: Context, pb: PlaneBatch):
+        self.ctx, self.pb = ctx, pb
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        check(self._lib.lgmi_batch_create(ctx.handle, ptr(pb.units), pb.n_units, pb.planes.size,
+                                          pb.n_sites, C.byref(h)), ctx.handle)
+        self.handle = h
+
+    def upload(self, planes=None, site_flags=None):
+        planes = self.pb.planes if planes is None else planes
+        site_flags = self.pb.site_flags if site_flags is None else site_flags
+        assert planes.dtype == np.uint32 and planes.size == self.pb.planes.size
+        assert site_flags.dtype == np.uint8 and site_flags.size == self.pb.n_sites
+        self._keep = (planes, site_flags)
+        check(self._lib.lgmi_batch_upload(self.handle, ptr(planes), ptr(site_flags)), self.ctx.handle)
+
+    def run(self, min_common, mode=MODE_ALL_PAIRS):
+        check(self._lib.lgmi_batch_run(self.handle, int(min_common), int(mode)), self.ctx.handle)
+
+    def sync(self) -> Result:
+        res = Result()
+        check(self._lib.lgmi_batch_sync(self.handle, C.byref(res)), self.ctx.handle)
+        return res
+
+    def download(self, copy=True) -> StepResult:
+        res = Result()
+        check(self._lib.lgmi_batch_download(self.handle, C.byref(res)), self.ctx.handle)
+        return StepResult(res, self.pb.n_units, copy=copy)
+
+    def algorithmic_bytes(self) -> int:
+        v = C.c_uint64()
+        check(self._lib.lgmi_batch_algorithmic_bytes(self.handle, C.byref(v)), self.ctx.handle)
+        return int(v.value)
+
+    def device_ptrs(self):
+        p = [C.c_void_p() for _ in range(4)]
+        check(self._lib.lgmi_batch_device_ptrs(self.handle, *[C.byref(x) for x in p]), self.ctx.handle)
+        return tuple(x.value for x in p)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.lgmi_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if self.ctx.handle:
+                self.close()
+        except Exception:
+            pass
+
+
+def mi_step_batched(pb: PlaneBatch, min_common_reads=5, mode=MODE_HET_ONLY, ctx=None) -> StepResult:
+    """All units of `pb` in one submit: pair MI -> het filter -> per-site mean
+    (mismatch.py:387-404 for every unit at once).  Host buffers in, host
+    buffers out."""
+    ctx = ctx or get_context()
+    b = Batch(ctx, pb)
+    try:
+        b.upload()
+        b.run(min_common_reads, mode)
+        return b.download(copy=True)
+    finally:
+        b.close()
+
+
+# --------------------------------------------------------------------------- #
+# drop-in functions (reference signatures)
+# --------------------------------------------------------------------------- #
+def mismatch_pair_mutual_info(mismatches, min_common_reads=5):
+    """Drop-in for giremi.mutual_information.mismatch_pair_mutual_info (:6-45):
+    returns ``[[p1, type1, p2, type2, mi], ...]`` in ``combinations`` order for
+    every pair sharing at least ``min_common_reads`` reads."""
+    if len(mismatches) < 2:
+        return []
+    eu = encode_mismatches(mismatches)
+    res = mi_step_batched(pack_units([eu]), min_common_reads, MODE_ALL_PAIRS)
+    rec = res.records
+    if eu.bad_sites and len(rec):
+        bad = np.fromiter(eu.bad_sites, dtype=np.int64)
+        if np.isin(rec['i'], bad).any() or np.isin(rec['j'], bad).any():
+            raise IndexError('list index out of range')   # mutual_information.py:30/32
+    pos, typ = eu.positions, eu.types
+    return [[pos[i], typ[i], pos[j], typ[j], mi]
+            for i, j, mi in zip(rec['i'].tolist(), rec['j'].tolist(), rec['mi'].tolist())]
+
+
+def mean_mismatch_pair_mutual_info(mismatch_pair_mi):
+    """Drop-in for giremi.mutual_information.mean_mismatch_pair_mutual_info
+    (:48-60): ``[[pos, mean], ...]`` in first-appearance order.  The grouping
+    is index bookkeeping on the host; the summation and division run on the
+    device with CPython's float-sum semantics."""
+    order, values = {}, []
+    for p1, _t1, p2, _t2, mi in mismatch_pair_mi:
+        for p in (p1, p2):
+            k = order.get(p)
+            if k is None:
+                k = order[p] = len(values)
+                values.append([])
+            values[k].append(mi)
+    if not values:
+        return []
+    offsets = np.zeros(len(values) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(v) for v in values])
+    flat = np.array([x for v in values for x in v], dtype=np.float64)
+    out = np.empty(len(values), dtype=np.float64)
+    ctx = get_context()
+    check(ctx._lib.lgmi_site_mean_csr(ctx.handle, ptr(offsets), ptr(flat), len(values), ptr(out)), ctx.handle)
+    return [[p, m] for p, m in zip(order.keys(), out.tolist())]
+
+
+def ecdf(x):
+    """Drop-in for giremi.stat.ecdf (stat.py:7-29): returns a callable mapping a
+    sample (scalar or array) to ``y[searchsorted(sort(x), sample)]``."""
+    xs = np.ascontiguousarray(np.array(x, dtype=np.float64).reshape(-1))
+    if xs.size == 0:
+        raise ZeroDivisionError('division by zero')      # 1/n at stat.py:19
+
+    def childfunc(sample):
+        s = np.ascontiguousarray(np.asarray(sample, dtype=np.float64))
+        flat = s.reshape(-1)
+        out = np.empty(flat.size, dtype=np.float64)
+        ctx = get_context()
+        check(ctx._lib.lgmi_ecdf_eval(ctx.handle, ptr(xs), xs.size, ptr(flat), flat.size, ptr(out)), ctx.handle)
+        return np.float64(out[0]) if s.ndim == 0 else out.reshape(s.shape)
+
+    return childfunc
+
+
+def mip_and_calls(mean_mi, site_types, threshold=0.05, ctx=None):
+    """Vectorised global pass (giremi.py:415-429 and :97-114): returns
+    (mip, call) with call 1 = positive label, 2 = negative label, 0 = neither.
+    `site_types` is an array of type codes or of type names."""
+    mean = np.ascontiguousarray(mean_mi, dtype=np.float64)
+    st = np.asarray(site_types)
+    if st.dtype.kind in "US" or st.dtype == object:
+        st = np.array([SITE_TYPE_CODE[t] for t in st.tolist()], dtype=np.uint8)
+    flags = np.ascontiguousarray(st, dtype=np.uint8)
+    mip = np.empty(mean.size, dtype=np.float64)
+    call = np.empty(mean.size, dtype=np.uint8)
+    ctx = ctx or get_context()
+    check(ctx._lib.lgmi_ecdf(ctx.handle, ptr(mean), ptr(flags), mean.size, float(threshold), ptr(mip), ptr(call)),
+          ctx.handle)
+    return mip, call
+
+
+# --------------------------------------------------------------------------- #
+# partitioning
+# --------------------------------------------------------------------------- #
+def unit_costs(units) -> np.ndarray:
+    s = units['n_sites'].astype(np.uint64)
+    r = units['n_reads'].astype(np.uint64)
+    return (s * (s - np.minimum(s, 1)) // 2 * ((r + 63) // 64)).astype(np.uint64)
+
+
+def partition_lpt(costs, n_bins):
+    """Longest-processing-time greedy partition; returns
+    (bin_of[unit], bin_load[bin]).  Pure host bookkeeping, no device needed."""
+    lib = _lib.load()
+    costs = np.ascontiguousarray(costs, dtype=np.uint64)
+    bin_of = np.empty(costs.size, dtype=np.uint32)
+    load = np.zeros(int(n_bins), dtype=np.uint64)
+    rc = lib.lgmi_partition_lpt(ptr(costs), costs.size, int(n_bins), ptr(bin_of), ptr(load))
+    if rc != 0:
+        raise LgmiError(rc, "lgmi_partition_lpt: bad argument")
+    return bin_of, load

@@ -1,0 +1,662 @@
+// lgmi.cu -- host side of liblgmi.so: the C ABI declared in include/lgmi.h.
+//
+// Owns the CUDA context state (stream, ln table, pinned staging), builds the
+// per-batch work tables and launches the kernels in lgmi_kernels.cuh.  There is
+// no CPU implementation of the MI step in this library: every entry point that
+// computes does so on the device, and lgmi_create() fails without one.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/lgmi.h"
+#include "lgmi_kernels.cuh"
+
+extern "C" void lgmi_build_lntab(double* hi_lo_pairs, uint64_t k_begin, uint64_t k_end);
+
+using namespace lgmi;
+
+static thread_local std::string g_create_error;
+
+struct lgmi_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  // ln table
+  lg_dd* d_lntab = nullptr;
+  uint64_t ln_cap = 0;  // entries 0..ln_cap-1 valid
+  // one-shot submit state
+  lgmi_batch* oneshot = nullptr;
+  // scratch for ecdf / csr
+  void* d_scratch = nullptr;
+  size_t scratch_cap = 0;
+};
+
+struct lgmi_batch {
+  lgmi_ctx* ctx = nullptr;
+  uint32_t n_units = 0, n_items = 0, n_mean_items = 0;
+  uint64_t plane_words = 0, n_sites = 0, n_candidates = 0, n_dense = 0;
+  uint32_t max_reads = 0;
+  std::vector<lgmi_unit_desc> h_units;
+  std::vector<Item> h_items;
+  // device
+  DevUnit* d_units = nullptr;
+  Item* d_items = nullptr;
+  MeanItem* d_mean_items = nullptr;
+  uint32_t* d_planes = nullptr;
+  uint8_t* d_flags = nullptr;
+  unsigned long long* d_status = nullptr;
+  Header* d_header = nullptr;
+  lgmi_pair_rec* d_records = nullptr;
+  uint64_t rec_cap = 0;
+  uint32_t* d_counts = nullptr;
+  uint64_t counts_cap = 0;
+  double* d_site_mean = nullptr;
+  uint32_t* d_site_cnt = nullptr;
+  double* d_dense = nullptr;
+  unsigned long long* d_unit_rec_off = nullptr;
+  // host (pinned) mirrors
+  Header* h_header = nullptr;
+  lgmi_pair_rec* h_records = nullptr;
+  uint64_t h_rec_cap = 0;
+  uint32_t* h_counts = nullptr;
+  uint64_t h_counts_cap = 0;
+  double* h_site_mean = nullptr;
+  uint32_t* h_site_cnt = nullptr;
+  unsigned long long* h_unit_rec_off = nullptr;
+  // run state
+  bool uploaded = false, ran = false;
+  uint32_t last_mode = 0;
+  uint64_t last_evaluated = 0;
+  uint64_t n_het_pairs_candidates = 0;
+};
+
+// --------------------------------------------------------------------------- helpers
+static int fail(lgmi_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(ctx, call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fail((ctx), (e__ == cudaErrorMemoryAllocation) ? LGMI_ERR_NOMEM : LGMI_ERR_CUDA, \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+static int ensure_lntab(lgmi_ctx* ctx, uint64_t k_max) {
+  if (k_max + 1 <= ctx->ln_cap) return LGMI_OK;
+  uint64_t cap = std::max<uint64_t>(4096, ctx->ln_cap);
+  while (cap < k_max + 1) cap *= 2;
+  std::vector<double> host(2 * cap);
+  lgmi_build_lntab(host.data(), 0, cap);
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_lntab) CU(ctx, cudaFree(ctx->d_lntab));
+  ctx->d_lntab = nullptr;
+  ctx->ln_cap = 0;
+  CU(ctx, cudaMalloc(&ctx->d_lntab, cap * sizeof(lg_dd)));
+  CU(ctx, cudaMemcpy(ctx->d_lntab, host.data(), cap * sizeof(lg_dd), cudaMemcpyHostToDevice));
+  ctx->ln_cap = cap;
+  return LGMI_OK;
+}
+
+static int ensure_scratch(lgmi_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_cap) return LGMI_OK;
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_scratch) CU(ctx, cudaFree(ctx->d_scratch));
+  ctx->d_scratch = nullptr;
+  ctx->scratch_cap = 0;
+  size_t cap = std::max<size_t>(bytes, 1 << 20);
+  CU(ctx, cudaMalloc(&ctx->d_scratch, cap));
+  ctx->scratch_cap = cap;
+  return LGMI_OK;
+}
+
+// --------------------------------------------------------------------------- context
+extern "C" int lgmi_version(void) { return LGMI_VERSION; }
+
+extern "C" int lgmi_create(int device, lgmi_t** out) {
+  if (!out) return fail(nullptr, LGMI_ERR_ARG, "lgmi_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, LGMI_ERR_NODEVICE,
+                "lgmi_create: no CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev)
+    return fail(nullptr, LGMI_ERR_ARG, "lgmi_create: device %d out of range [0,%d)", device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+    return fail(nullptr, LGMI_ERR_NODEVICE,
+                "lgmi_create: device %d is sm_%d%d; this build contains sm_100a code only", device,
+                prop.major, prop.minor);
+  lgmi_ctx* ctx = new (std::nothrow) lgmi_ctx();
+  if (!ctx) return fail(nullptr, LGMI_ERR_NOMEM, "lgmi_create: out of host memory");
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: %s", cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return rc;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return LGMI_OK;
+}
+
+extern "C" void lgmi_destroy(lgmi_t* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->oneshot) lgmi_batch_destroy(ctx->oneshot);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_lntab) cudaFree(ctx->d_lntab);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" const char* lgmi_last_error(const lgmi_t* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int lgmi_set_stream(lgmi_t* ctx, void* cuda_stream) {
+  if (!ctx) return LGMI_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return LGMI_OK;
+}
+
+extern "C" int lgmi_pinned_alloc(lgmi_t* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return LGMI_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return LGMI_OK;
+}
+
+extern "C" int lgmi_pinned_free(lgmi_t* ctx, void* ptr) {
+  if (!ctx) return LGMI_ERR_ARG;
+  if (ptr) CU(ctx, cudaFreeHost(ptr));
+  return LGMI_OK;
+}
+
+extern "C" uint64_t lgmi_launch_count(const lgmi_t* ctx) { return ctx ? ctx->launches : 0; }
+
+// --------------------------------------------------------------------------- batch
+extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
+  if (!b) return;
+  if (b->ctx) {
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    if (b->ctx->oneshot == b) b->ctx->oneshot = nullptr;
+  }
+  cudaFree(b->d_units);
+  cudaFree(b->d_items);
+  cudaFree(b->d_mean_items);
+  cudaFree(b->d_planes);
+  cudaFree(b->d_flags);
+  cudaFree(b->d_status);
+  cudaFree(b->d_header);
+  cudaFree(b->d_records);
+  cudaFree(b->d_counts);
+  cudaFree(b->d_site_mean);
+  cudaFree(b->d_site_cnt);
+  cudaFree(b->d_dense);
+  cudaFree(b->d_unit_rec_off);
+  cudaFreeHost(b->h_header);
+  cudaFreeHost(b->h_records);
+  cudaFreeHost(b->h_counts);
+  cudaFreeHost(b->h_site_mean);
+  cudaFreeHost(b->h_site_cnt);
+  cudaFreeHost(b->h_unit_rec_off);
+  delete b;
+}
+
+extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units,
+                                 uint64_t plane_words, uint64_t n_sites, lgmi_batch_t** out) {
+  if (!ctx || !out || (!units && n_units)) return fail(ctx, LGMI_ERR_ARG, "lgmi_batch_create: NULL argument");
+  *out = nullptr;
+  CU(ctx, cudaSetDevice(ctx->device));
+  lgmi_batch* b = new (std::nothrow) lgmi_batch();
+  if (!b) return fail(ctx, LGMI_ERR_NOMEM, "lgmi_batch_create: out of host memory");
+  b->ctx = ctx;
+  b->n_units = n_units;
+  b->plane_words = plane_words;
+  b->n_sites = n_sites;
+  b->h_units.assign(units, units + n_units);
+
+  std::vector<DevUnit> du(n_units);
+  std::vector<MeanItem> mean_items;
+  uint64_t dense = 0;
+  for (uint32_t k = 0; k < n_units; ++k) {
+    const lgmi_unit_desc& u = units[k];
+    if (u.n_sites > 65535u) {
+      delete b;
+      return fail(ctx, LGMI_ERR_UNSUPPORTED, "unit %u: %u sites > 65535", k, u.n_sites);
+    }
+    if (u.row_words != 4u * ((u.n_reads + 127u) / 128u) || (u.plane_off & 3ull) ||
+        u.plane_off + 3ull * u.n_sites * u.row_words > plane_words ||
+        (uint64_t)u.site_off + u.n_sites > n_sites) {
+      delete b;
+      return fail(ctx, LGMI_ERR_ARG,
+                  "unit %u: inconsistent descriptor (S=%u R=%u W=%u plane_off=%llu site_off=%u)", k,
+                  u.n_sites, u.n_reads, u.row_words, (unsigned long long)u.plane_off, u.site_off);
+    }
+    DevUnit& d = du[k];
+    d.plane_off = u.plane_off;
+    d.S = u.n_sites;
+    d.R = u.n_reads;
+    d.W = u.row_words;
+    d.site_off = u.site_off;
+    d.first_item = (uint32_t)b->h_items.size();
+    const uint64_t np = u.n_sites >= 2 ? (uint64_t)u.n_sites * (u.n_sites - 1) / 2 : 0;
+    b->n_candidates += np;
+    b->max_reads = std::max(b->max_reads, u.n_reads);
+    const uint32_t nit = np ? (uint32_t)((np + kPairsMax - 1) / kPairsMax) : 1u;
+    d.n_items = nit;
+    d.dense_off = ~0ull;
+    if (nit > 1) {
+      d.dense_off = dense;
+      dense += np;
+      for (uint32_t s0 = 0; s0 < u.n_sites; s0 += 128) mean_items.push_back(MeanItem{k, s0});
+    }
+    for (uint32_t t = 0; t < nit; ++t) {
+      Item it;
+      it.unit = k;
+      it.pair_begin = t * (uint32_t)kPairsMax;
+      it.pair_cnt = (uint32_t)std::min<uint64_t>(kPairsMax, np - (uint64_t)t * kPairsMax);
+      it.flags = (t == 0 ? ITEM_FIRST : 0u) | (nit == 1 ? ITEM_SINGLE : 0u);
+      b->h_items.push_back(it);
+    }
+  }
+  b->n_items = (uint32_t)b->h_items.size();
+  b->n_mean_items = (uint32_t)mean_items.size();
+  b->n_dense = dense;
+
+#define BCU(call)                                                                    \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      int rc__ = fail(ctx, (e__ == cudaErrorMemoryAllocation) ? LGMI_ERR_NOMEM : LGMI_ERR_CUDA, \
+                      "%s failed: %s", #call, cudaGetErrorString(e__));              \
+      lgmi_batch_destroy(b);                                                         \
+      return rc__;                                                                   \
+    }                                                                                \
+  } while (0)
+
+  BCU(cudaMalloc(&b->d_units, std::max<size_t>(1, n_units) * sizeof(DevUnit)));
+  BCU(cudaMalloc(&b->d_items, std::max<size_t>(1, b->n_items) * sizeof(Item)));
+  BCU(cudaMalloc(&b->d_mean_items, std::max<size_t>(1, mean_items.size()) * sizeof(MeanItem)));
+  BCU(cudaMalloc(&b->d_planes, std::max<uint64_t>(4, plane_words) * sizeof(uint32_t)));
+  BCU(cudaMalloc(&b->d_flags, std::max<uint64_t>(1, n_sites)));
+  BCU(cudaMalloc(&b->d_status, std::max<size_t>(1, b->n_items) * sizeof(unsigned long long)));
+  BCU(cudaMalloc(&b->d_header, sizeof(Header)));
+  BCU(cudaMalloc(&b->d_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double)));
+  BCU(cudaMalloc(&b->d_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t)));
+  BCU(cudaMalloc(&b->d_dense, std::max<uint64_t>(1, dense) * sizeof(double)));
+  BCU(cudaMalloc(&b->d_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long)));
+  b->rec_cap = std::max<uint64_t>(1, b->n_candidates);
+  BCU(cudaMalloc(&b->d_records, b->rec_cap * sizeof(lgmi_pair_rec)));
+  BCU(cudaHostAlloc(&b->h_header, sizeof(Header), cudaHostAllocDefault));
+  BCU(cudaHostAlloc(&b->h_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double), cudaHostAllocDefault));
+  BCU(cudaHostAlloc(&b->h_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t), cudaHostAllocDefault));
+  BCU(cudaHostAlloc(&b->h_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
+  if (n_units) BCU(cudaMemcpyAsync(b->d_units, du.data(), n_units * sizeof(DevUnit), cudaMemcpyHostToDevice, ctx->stream));
+  if (b->n_items) BCU(cudaMemcpyAsync(b->d_items, b->h_items.data(), b->n_items * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
+  if (!mean_items.empty())
+    BCU(cudaMemcpyAsync(b->d_mean_items, mean_items.data(), mean_items.size() * sizeof(MeanItem), cudaMemcpyHostToDevice, ctx->stream));
+  BCU(cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope
+#undef BCU
+  int rc = ensure_lntab(ctx, std::max<uint32_t>(b->max_reads, 1u));
+  if (rc) {
+    lgmi_batch_destroy(b);
+    return rc;
+  }
+  *out = b;
+  return LGMI_OK;
+}
+
+extern "C" int lgmi_batch_upload(lgmi_batch_t* b, const uint32_t* planes, const uint8_t* site_flags) {
+  if (!b) return LGMI_ERR_ARG;
+  lgmi_ctx* ctx = b->ctx;
+  if ((!planes && b->plane_words) || (!site_flags && b->n_sites))
+    return fail(ctx, LGMI_ERR_ARG, "lgmi_batch_upload: NULL input");
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (b->plane_words)
+    CU(ctx, cudaMemcpyAsync(b->d_planes, planes, b->plane_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (b->n_sites)
+    CU(ctx, cudaMemcpyAsync(b->d_flags, site_flags, b->n_sites, cudaMemcpyHostToDevice, ctx->stream));
+  b->uploaded = true;
+  return LGMI_OK;
+}
+
+extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
+  if (!b) return LGMI_ERR_ARG;
+  lgmi_ctx* ctx = b->ctx;
+  if (!b->uploaded) return fail(ctx, LGMI_ERR_STATE, "lgmi_batch_run: no input uploaded");
+  if ((mode & LGMI_MODE_SKIP_NONHET) && !(mode & LGMI_MODE_HET_ONLY))
+    return fail(ctx, LGMI_ERR_ARG, "LGMI_MODE_SKIP_NONHET requires LGMI_MODE_HET_ONLY");
+  CU(ctx, cudaSetDevice(ctx->device));
+  if ((mode & LGMI_MODE_EMIT_COUNTS) && b->counts_cap < b->rec_cap) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (b->d_counts) CU(ctx, cudaFree(b->d_counts));
+    b->d_counts = nullptr;
+    b->counts_cap = 0;
+    CU(ctx, cudaMalloc(&b->d_counts, b->rec_cap * 9ull * sizeof(uint32_t)));
+    b->counts_cap = b->rec_cap;
+  }
+  RunParams P;
+  P.units = b->d_units;
+  P.items = b->d_items;
+  P.n_items = b->n_items;
+  P.n_units = b->n_units;
+  P.planes = b->d_planes;
+  P.site_flags = b->d_flags;
+  P.lntab = ctx->d_lntab;
+  P.min_common = min_common;
+  P.mode = mode;
+  P.status = b->d_status;
+  P.header = b->d_header;
+  P.records = b->d_records;
+  P.counts = b->d_counts;
+  P.site_mean = b->d_site_mean;
+  P.site_cnt = b->d_site_cnt;
+  P.dense = b->d_dense;
+  P.unit_rec_off = b->d_unit_rec_off;
+
+  CU(ctx, cudaMemsetAsync(b->d_header, 0, sizeof(Header), ctx->stream));
+  CU(ctx, cudaMemsetAsync(b->d_status, 0, std::max<size_t>(1, b->n_items) * sizeof(unsigned long long), ctx->stream));
+  CU(ctx, cudaMemsetAsync(b->d_unit_rec_off, 0, ((size_t)b->n_units + 1) * sizeof(unsigned long long), ctx->stream));
+  CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (b->n_sites) {
+    // sites of pair-less units keep NaN; everything else is overwritten
+    k_fill_nan<<<(unsigned)((b->n_sites + 255) / 256), 256, 0, ctx->stream>>>(b->d_site_mean, b->d_site_cnt, b->n_sites);
+    ++ctx->launches;
+  }
+  if (b->n_items) {
+    k_pairs<<<b->n_items, kThreads, 0, ctx->stream>>>(P);
+    ++ctx->launches;
+  }
+  if (b->n_mean_items) {
+    k_site_mean_dense<<<b->n_mean_items, 128, 0, ctx->stream>>>(b->d_units, b->d_mean_items, b->d_flags, b->d_dense,
+                                                              b->d_site_mean, b->d_site_cnt);
+    ++ctx->launches;
+  }
+  CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(ctx, cudaGetLastError());
+  b->ran = true;
+  b->last_mode = mode;
+  b->last_evaluated = b->n_candidates;  // refined on the host in sync for SKIP_NONHET
+  return LGMI_OK;
+}
+
+static int fill_scalars(lgmi_batch* b, lgmi_result* out) {
+  lgmi_ctx* ctx = b->ctx;
+  memset(out, 0, sizeof *out);
+  out->n_candidates = b->n_candidates;
+  out->n_evaluated = b->n_candidates;
+  out->n_records = b->h_header->n_records;
+  out->n_sites = b->n_sites;
+  float ms = 0.f;
+  CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  out->kernel_ms = ms;
+  return LGMI_OK;
+}
+
+extern "C" int lgmi_batch_sync(lgmi_batch_t* b, lgmi_result* out) {
+  if (!b || !out) return LGMI_ERR_ARG;
+  lgmi_ctx* ctx = b->ctx;
+  if (!b->ran) return fail(ctx, LGMI_ERR_STATE, "lgmi_batch_sync: batch has not been run");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync(b->h_header, b->d_header, sizeof(Header), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return fill_scalars(b, out);
+}
+
+extern "C" int lgmi_batch_download(lgmi_batch_t* b, lgmi_result* out) {
+  if (!b || !out) return LGMI_ERR_ARG;
+  lgmi_ctx* ctx = b->ctx;
+  if (!b->ran) return fail(ctx, LGMI_ERR_STATE, "lgmi_batch_download: batch has not been run");
+  CU(ctx, cudaSetDevice(ctx->device));
+  // the small per-site / per-unit outputs can go while we learn the record count
+  CU(ctx, cudaMemcpyAsync(b->h_header, b->d_header, sizeof(Header), cudaMemcpyDeviceToHost, ctx->stream));
+  if (b->n_sites) {
+    CU(ctx, cudaMemcpyAsync(b->h_site_mean, b->d_site_mean, b->n_sites * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(b->h_site_cnt, b->d_site_cnt, b->n_sites * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(ctx, cudaMemcpyAsync(b->h_unit_rec_off, b->d_unit_rec_off, ((size_t)b->n_units + 1) * sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  const uint64_t nrec = b->h_header->n_records;
+  if (nrec > b->rec_cap) return fail(ctx, LGMI_ERR_STATE, "record count %llu exceeds capacity", (unsigned long long)nrec);
+  if (nrec > b->h_rec_cap) {
+    if (b->h_records) CU(ctx, cudaFreeHost(b->h_records));
+    b->h_records = nullptr;
+    b->h_rec_cap = 0;
+    const uint64_t cap = std::max<uint64_t>(nrec + nrec / 8, 1024);
+    CU(ctx, cudaHostAlloc(&b->h_records, cap * sizeof(lgmi_pair_rec), cudaHostAllocDefault));
+    b->h_rec_cap = cap;
+  }
+  const bool want_counts = (b->last_mode & LGMI_MODE_EMIT_COUNTS) != 0u;
+  if (want_counts && nrec > b->h_counts_cap) {
+    if (b->h_counts) CU(ctx, cudaFreeHost(b->h_counts));
+    b->h_counts = nullptr;
+    b->h_counts_cap = 0;
+    const uint64_t cap = std::max<uint64_t>(nrec + nrec / 8, 1024);
+    CU(ctx, cudaHostAlloc(&b->h_counts, cap * 9ull * sizeof(uint32_t), cudaHostAllocDefault));
+    b->h_counts_cap = cap;
+  }
+  if (nrec) {
+    CU(ctx, cudaMemcpyAsync(b->h_records, b->d_records, nrec * sizeof(lgmi_pair_rec), cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_counts)
+      CU(ctx, cudaMemcpyAsync(b->h_counts, b->d_counts, nrec * 9ull * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  int rc = fill_scalars(b, out);
+  if (rc) return rc;
+  out->records = b->h_records;
+  out->counts = want_counts ? b->h_counts : nullptr;
+  out->site_mean = b->h_site_mean;
+  out->site_cnt = b->h_site_cnt;
+  out->unit_rec_off = reinterpret_cast<const uint64_t*>(b->h_unit_rec_off);
+  return LGMI_OK;
+}
+
+extern "C" int lgmi_batch_device_ptrs(lgmi_batch_t* b, void** d_planes, void** d_site_flags, void** d_records,
+                                      void** d_site_mean) {
+  if (!b) return LGMI_ERR_ARG;
+  if (d_planes) *d_planes = b->d_planes;
+  if (d_site_flags) *d_site_flags = b->d_flags;
+  if (d_records) *d_records = b->d_records;
+  if (d_site_mean) *d_site_mean = b->d_site_mean;
+  b->uploaded = true;  // a device-resident caller fills the buffers itself
+  return LGMI_OK;
+}
+
+extern "C" int lgmi_batch_algorithmic_bytes(lgmi_batch_t* b, uint64_t* bytes) {
+  if (!b || !bytes) return LGMI_ERR_ARG;
+  if (!b->ran) return fail(b->ctx, LGMI_ERR_STATE, "lgmi_batch_algorithmic_bytes: batch has not been run");
+  uint64_t in = 0;
+  for (const lgmi_unit_desc& u : b->h_units) in += 3ull * u.n_sites * ((u.n_reads + 7ull) / 8ull) + u.n_sites;
+  *bytes = in + 16ull * b->h_header->n_records + 12ull * b->n_sites;
+  return LGMI_OK;
+}
+
+// --------------------------------------------------------------------------- one-shot
+extern "C" int lgmi_submit(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units, const uint32_t* planes,
+                           uint64_t plane_words, const uint8_t* site_flags, uint64_t n_sites, int min_common,
+                           uint32_t mode) {
+  if (!ctx) return LGMI_ERR_ARG;
+  if (ctx->oneshot) lgmi_batch_destroy(ctx->oneshot);
+  ctx->oneshot = nullptr;
+  lgmi_batch* b = nullptr;
+  int rc = lgmi_batch_create(ctx, units, n_units, plane_words, n_sites, &b);
+  if (rc) return rc;
+  ctx->oneshot = b;
+  rc = lgmi_batch_upload(b, planes, site_flags);
+  if (rc) return rc;
+  return lgmi_batch_run(b, min_common, mode);
+}
+
+extern "C" int lgmi_wait(lgmi_t* ctx, lgmi_result* out) {
+  if (!ctx || !out) return LGMI_ERR_ARG;
+  if (!ctx->oneshot) return fail(ctx, LGMI_ERR_STATE, "lgmi_wait: nothing submitted");
+  return lgmi_batch_download(ctx->oneshot, out);
+}
+
+// --------------------------------------------------------------------------- mean of rows
+extern "C" int lgmi_site_mean_csr(lgmi_t* ctx, const uint64_t* offsets, const double* values, uint64_t n_sites,
+                                  double* mean_out) {
+  if (!ctx || !offsets || !mean_out) return fail(ctx, LGMI_ERR_ARG, "lgmi_site_mean_csr: NULL argument");
+  if (n_sites == 0) return LGMI_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const uint64_t nval = offsets[n_sites];
+  if (nval && !values) return fail(ctx, LGMI_ERR_ARG, "lgmi_site_mean_csr: NULL values");
+  const size_t off_bytes = (n_sites + 1) * sizeof(uint64_t);
+  const size_t val_bytes = std::max<uint64_t>(1, nval) * sizeof(double);
+  const size_t out_bytes = n_sites * sizeof(double);
+  int rc = ensure_scratch(ctx, off_bytes + val_bytes + out_bytes + 64);
+  if (rc) return rc;
+  char* p = static_cast<char*>(ctx->d_scratch);
+  unsigned long long* d_off = reinterpret_cast<unsigned long long*>(p);
+  double* d_val = reinterpret_cast<double*>(p + off_bytes);
+  double* d_out = reinterpret_cast<double*>(p + off_bytes + val_bytes);
+  CU(ctx, cudaMemcpyAsync(d_off, offsets, off_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (nval) CU(ctx, cudaMemcpyAsync(d_val, values, nval * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  k_site_mean_csr<<<(unsigned)((n_sites + 127) / 128), 128, 0, ctx->stream>>>(d_off, d_val, n_sites, d_out);
+  ++ctx->launches;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(mean_out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LGMI_OK;
+}
+
+// --------------------------------------------------------------------------- ecdf
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int lgmi_ecdf(lgmi_t* ctx, const double* mean, const uint8_t* site_flags, uint64_t n, double threshold,
+                         double* mip, uint8_t* call) {
+  if (!ctx || (n && (!mean || !site_flags || !mip))) return fail(ctx, LGMI_ERR_ARG, "lgmi_ecdf: NULL argument");
+  if (n == 0) return LGMI_OK;
+  if (n > 0x7fffffffull) return fail(ctx, LGMI_ERR_UNSUPPORTED, "lgmi_ecdf: more than 2^31-1 sites");
+  CU(ctx, cudaSetDevice(ctx->device));
+  size_t sort_bytes = 0;
+  CU(ctx, cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const double*)nullptr, (double*)nullptr, (int)n, 0, 64,
+                                        ctx->stream));
+  const size_t a_mean = 0;
+  const size_t a_keys = align_up(a_mean + n * 8, 256);
+  const size_t a_sorted = align_up(a_keys + n * 8, 256);
+  const size_t a_mip = align_up(a_sorted + n * 8, 256);
+  const size_t a_flags = align_up(a_mip + n * 8, 256);
+  const size_t a_call = align_up(a_flags + n, 256);
+  const size_t a_cnt = align_up(a_call + n, 256);
+  const size_t a_tmp = align_up(a_cnt + 8, 256);
+  int rc = ensure_scratch(ctx, a_tmp + sort_bytes);
+  if (rc) return rc;
+  char* p = static_cast<char*>(ctx->d_scratch);
+  double* d_mean = reinterpret_cast<double*>(p + a_mean);
+  double* d_keys = reinterpret_cast<double*>(p + a_keys);
+  double* d_sorted = reinterpret_cast<double*>(p + a_sorted);
+  double* d_mip = reinterpret_cast<double*>(p + a_mip);
+  uint8_t* d_flags = reinterpret_cast<uint8_t*>(p + a_flags);
+  uint8_t* d_call = reinterpret_cast<uint8_t*>(p + a_call);
+  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(p + a_cnt);
+  CU(ctx, cudaMemcpyAsync(d_mean, mean, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(d_flags, site_flags, n, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, ctx->stream));
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  k_ecdf_keys<<<grid, 256, 0, ctx->stream>>>(d_mean, d_flags, n, d_keys, d_cnt);
+  ++ctx->launches;
+  CU(ctx, cub::DeviceRadixSort::SortKeys(p + a_tmp, sort_bytes, d_keys, d_sorted, (int)n, 0, 64, ctx->stream));
+  ++ctx->launches;
+  k_ecdf_mip<<<grid, 256, 0, ctx->stream>>>(d_mean, d_flags, n, d_sorted, d_cnt, threshold, d_mip, d_call);
+  ++ctx->launches;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(mip, d_mip, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (call) CU(ctx, cudaMemcpyAsync(call, d_call, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LGMI_OK;
+}
+
+extern "C" int lgmi_ecdf_eval(lgmi_t* ctx, const double* x, uint64_t n, const double* samples, uint64_t m,
+                              double* out) {
+  if (!ctx || (n && !x) || (m && (!samples || !out))) return fail(ctx, LGMI_ERR_ARG, "lgmi_ecdf_eval: NULL argument");
+  if (n == 0) return fail(ctx, LGMI_ERR_ARG, "lgmi_ecdf_eval: empty x (the reference divides by len(x))");
+  if (m == 0) return LGMI_OK;
+  if (n > 0x7fffffffull) return fail(ctx, LGMI_ERR_UNSUPPORTED, "lgmi_ecdf_eval: more than 2^31-1 values");
+  CU(ctx, cudaSetDevice(ctx->device));
+  size_t sort_bytes = 0;
+  CU(ctx, cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const double*)nullptr, (double*)nullptr, (int)n, 0, 64,
+                                        ctx->stream));
+  const size_t a_x = 0;
+  const size_t a_sorted = align_up(a_x + n * 8, 256);
+  const size_t a_s = align_up(a_sorted + n * 8, 256);
+  const size_t a_o = align_up(a_s + m * 8, 256);
+  const size_t a_tmp = align_up(a_o + m * 8, 256);
+  int rc = ensure_scratch(ctx, a_tmp + sort_bytes);
+  if (rc) return rc;
+  char* p = static_cast<char*>(ctx->d_scratch);
+  double* d_x = reinterpret_cast<double*>(p + a_x);
+  double* d_sorted = reinterpret_cast<double*>(p + a_sorted);
+  double* d_s = reinterpret_cast<double*>(p + a_s);
+  double* d_o = reinterpret_cast<double*>(p + a_o);
+  CU(ctx, cudaMemcpyAsync(d_x, x, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(d_s, samples, m * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cub::DeviceRadixSort::SortKeys(p + a_tmp, sort_bytes, d_x, d_sorted, (int)n, 0, 64, ctx->stream));
+  ++ctx->launches;
+  k_ecdf_eval<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(d_sorted, n, d_s, m, d_o);
+  ++ctx->launches;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(out, d_o, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LGMI_OK;
+}
+
+// --------------------------------------------------------------------------- partitioning
+extern "C" uint64_t lgmi_unit_cost(uint32_t n_sites, uint32_t n_reads) {
+  if (n_sites < 2) return 0;
+  return (uint64_t)n_sites * (n_sites - 1) / 2 * ((n_reads + 63ull) / 64ull);
+}
+
+extern "C" int lgmi_partition_lpt(const uint64_t* cost, uint32_t n_units, uint32_t n_bins, uint32_t* bin_of,
+                                  uint64_t* bin_load) {
+  if ((!cost && n_units) || !bin_of || n_bins == 0) return LGMI_ERR_ARG;
+  std::vector<uint32_t> order(n_units);
+  for (uint32_t k = 0; k < n_units; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+  typedef std::pair<uint64_t, uint32_t> Bin;  // (load, bin); min-heap, ties -> lower bin index
+  std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> heap;
+  for (uint32_t k = 0; k < n_bins; ++k) heap.push(Bin(0, k));
+  std::vector<uint64_t> load(n_bins, 0);
+  for (uint32_t k : order) {
+    Bin top = heap.top();
+    heap.pop();
+    bin_of[k] = top.second;
+    top.first += cost[k];
+    load[top.second] = top.first;
+    heap.push(top);
+  }
+  if (bin_load) memcpy(bin_load, load.data(), n_bins * sizeof(uint64_t));
+  return LGMI_OK;
+}

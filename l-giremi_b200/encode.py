@@ -1,0 +1,176 @@
+"""Host-side encoder: the reference's ``mismatches[strand]`` dict -> bit-planes.
+
+Replicates, before any GPU work, the dict semantics the kernels cannot see
+(/root/reference/src/giremi/mutual_information.py):
+
+  * :15-16  a read name listed twice at a site keeps its LAST allele in
+            ('nt' key order, list order)
+  * :25-32  major / minor allele by site-wide ``depth`` descending with the
+            stable-sort tie-break (dict order); ``depth`` may count duplicates
+  * :33-38  every other allele -> label 0 ("other")
+
+Plane layout is documented in include/lgmi.h."""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import (SITE_HAS_OTHER, SITE_TYPE_CODE, SITE_TYPE_NAMES, UNIT_DESC)
+
+UNCOVERED = 255  # label value for "read does not cover the site"
+
+
+def row_words(n_reads: int) -> int:
+    """32-bit words per plane row: whole 16-byte vectors."""
+    return 4 * ((int(n_reads) + 127) // 128)
+
+
+class EncodedUnit:
+    """One (footprint, strand) unit in label-matrix form."""
+
+    __slots__ = ("positions", "types", "labels", "bad_sites")
+
+    def __init__(self, positions, types, labels, bad_sites=()):
+        self.positions = list(positions)           # ascending
+        self.types = list(types)                   # 'mismatch' | 'snp' | 'het_snp'
+        self.labels = labels                       # uint8 [S, R]: 0/1/2 or UNCOVERED
+        self.bad_sites = frozenset(bad_sites)      # indices whose 'depth' has < 2 alleles
+
+    @property
+    def n_sites(self):
+        return self.labels.shape[0]
+
+    @property
+    def n_reads(self):
+        return self.labels.shape[1]
+
+
+def encode_mismatches(mismatches) -> EncodedUnit:
+    """dict -> EncodedUnit.  Never mutates the input."""
+    positions = sorted(mismatches)
+    read_index = {}
+    per_site = []
+    for pos in positions:
+        site = mismatches[pos]
+        allele_of = {}
+        for allele, names in site['nt'].items():       # last occurrence wins
+            for name in names:
+                allele_of[name] = allele
+        for name in allele_of:
+            if name not in read_index:
+                read_index[name] = len(read_index)
+        per_site.append(allele_of)
+    labels = np.full((len(positions), len(read_index)), UNCOVERED, dtype=np.uint8)
+    types, bad = [], []
+    for s, pos in enumerate(positions):
+        site = mismatches[pos]
+        types.append(site['type'])
+        ranked = sorted(site['depth'].items(), key=lambda kv: -kv[1])   # stable
+        major = ranked[0][0] if len(ranked) > 0 else None
+        minor = ranked[1][0] if len(ranked) > 1 else None
+        if len(ranked) < 2:
+            bad.append(s)      # the reference raises IndexError at :30 when a
+                               # surviving pair touches this site
+        row = labels[s]
+        for name, allele in per_site[s].items():
+            row[read_index[name]] = 2 if allele == major else (1 if allele == minor else 0)
+    return EncodedUnit(positions, types, labels, bad)
+
+
+def pack_labels(labels: np.ndarray) -> np.ndarray:
+    """uint8 [S, R] label matrix -> uint32 [S, 3, W] planes (M, m, C)."""
+    S, R = labels.shape
+    W = row_words(R)
+    bits = np.zeros((S, 3, W * 32), dtype=np.uint8)
+    bits[:, 0, :R] = labels == 2
+    bits[:, 1, :R] = labels == 1
+    bits[:, 2, :R] = labels != UNCOVERED
+    packed = np.packbits(bits, axis=-1, bitorder='little')
+    return np.ascontiguousarray(packed).view('<u4').reshape(S, 3, W)
+
+
+def site_flag_bytes(types, labels) -> np.ndarray:
+    flags = np.array([SITE_TYPE_CODE[t] for t in types], dtype=np.uint8)
+    if len(flags):
+        flags |= np.where((labels == 0).any(axis=1), SITE_HAS_OTHER, 0).astype(np.uint8)
+    return flags
+
+
+class PlaneBatch:
+    """Many units packed for one submit (the layout of include/lgmi.h)."""
+
+    def __init__(self, units, planes, site_flags, positions=None, types=None, bad_sites=None):
+        self.units = np.ascontiguousarray(units, dtype=UNIT_DESC)
+        self.planes = np.ascontiguousarray(planes, dtype=np.uint32)
+        self.site_flags = np.ascontiguousarray(site_flags, dtype=np.uint8)
+        self.positions = positions      # list of per-unit position lists (optional metadata)
+        self.types = types
+        self.bad_sites = bad_sites
+
+    @property
+    def n_units(self):
+        return len(self.units)
+
+    @property
+    def n_sites(self):
+        return len(self.site_flags)
+
+    @property
+    def n_candidates(self):
+        s = self.units['n_sites'].astype(np.int64)
+        return int((s * (s - 1) // 2).sum())
+
+    def site_types(self, unit):
+        off = int(self.units['site_off'][unit])
+        n = int(self.units['n_sites'][unit])
+        return [SITE_TYPE_NAMES[f & 3] for f in self.site_flags[off:off + n]]
+
+    def subset(self, index):
+        """A new batch holding units[index] (planes re-packed contiguously)."""
+        index = np.asarray(index)
+        units = self.units[index].copy()
+        chunks, flags = [], []
+        plane_off = 0
+        site_off = 0
+        for k, u in enumerate(units):
+            n = 3 * int(u['n_sites']) * int(u['row_words'])
+            chunks.append(self.planes[int(u['plane_off']):int(u['plane_off']) + n])
+            flags.append(self.site_flags[int(u['site_off']):int(u['site_off']) + int(u['n_sites'])])
+            units[k]['plane_off'] = plane_off
+            units[k]['site_off'] = site_off
+            plane_off += n
+            site_off += int(u['n_sites'])
+        planes = np.concatenate(chunks) if chunks else np.zeros(0, np.uint32)
+        site_flags = np.concatenate(flags) if flags else np.zeros(0, np.uint8)
+
+        def pick(meta):
+            return [meta[i] for i in index] if meta is not None else None
+
+        return PlaneBatch(units, planes, site_flags, pick(self.positions), pick(self.types),
+                          pick(self.bad_sites))
+
+
+def pack_units(encoded_units) -> PlaneBatch:
+    """List[EncodedUnit] -> PlaneBatch."""
+    units = np.zeros(len(encoded_units), dtype=UNIT_DESC)
+    chunks, flags = [], []
+    plane_off = 0
+    site_off = 0
+    for k, eu in enumerate(encoded_units):
+        S, R = eu.labels.shape
+        W = row_words(R)
+        units[k] = (plane_off, S, R, W, site_off)
+        if S:
+            chunks.append(pack_labels(eu.labels).reshape(-1))
+            flags.append(site_flag_bytes(eu.types, eu.labels))
+        plane_off += 3 * S * W
+        site_off += S
+    planes = np.concatenate(chunks) if chunks else np.zeros(0, np.uint32)
+    site_flags = np.concatenate(flags) if flags else np.zeros(0, np.uint8)
+    return PlaneBatch(units, planes, site_flags,
+                      [eu.positions for eu in encoded_units],
+                      [eu.types for eu in encoded_units],
+                      [eu.bad_sites for eu in encoded_units])
+
+
+def encode_batch(list_of_mismatches) -> PlaneBatch:
+    return pack_units([encode_mismatches(m) for m in list_of_mismatches])

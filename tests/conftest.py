@@ -1,0 +1,107 @@
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def unhex(s):
+    return float.fromhex(s)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    def load(name):
+        with open(os.path.join(ROOT, "tests", "golden", name)) as fh:
+            return json.load(fh)["data"]
+    return load
+
+
+def golden_mismatches(unit):
+    """JSON unit -> the reference's dict (int positions, insertion orders kept)."""
+    return {int(p): {'ref': s['ref'], 'type': s['type'], 'depth': dict(s['depth']),
+                     'nt': {a: list(v) for a, v in s['nt'].items()},
+                     'neighbor': [], 'up': 'A', 'down': 'C'}
+            for p, s in unit['mismatches'].items()}
+
+
+@pytest.fixture(scope="session")
+def lg():
+    """The product package (directory name has a hyphen)."""
+    return importlib.import_module("l-giremi_b200")
+
+
+@pytest.fixture(scope="session")
+def liblgmi_path():
+    build = importlib.import_module("l-giremi_b200.build")
+    return build.build_lib()
+
+
+@pytest.fixture(scope="session")
+def math_host(liblgmi_path):
+    """Host build of csrc/lgmi_math.cuh (+ the ln-table builder) for CPU tests."""
+    out = os.path.join(ROOT, "tests", "csrc", "libmath_host.so")
+    srcs = [os.path.join(ROOT, "tests", "csrc", "math_host.cpp"),
+            os.path.join(ROOT, "l-giremi_b200", "csrc", "lgmi_lntab.c"),
+            os.path.join(ROOT, "l-giremi_b200", "csrc", "lgmi_math.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        obj = os.path.join(ROOT, "tests", "csrc", "lntab_host.o")
+        subprocess.run(["gcc", "-O2", "-fPIC", "-c", srcs[1], "-o", obj], check=True)
+        quad = subprocess.run(["gcc", "-print-file-name=libquadmath.a"], capture_output=True, text=True).stdout.strip()
+        subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-std=c++17", "-o", out,
+                        srcs[0], obj, quad, "-lm"], check=True)
+    lib = ctypes.CDLL(out)
+    vp = ctypes.c_void_p
+    lib.t_mi_from_table.restype = ctypes.c_double
+    lib.t_mi_from_table.argtypes = [vp, vp]
+    lib.t_mi_from_2x2.restype = ctypes.c_double
+    lib.t_mi_from_2x2.argtypes = [ctypes.c_uint32] * 4 + [vp]
+    lib.t_ln_product.restype = ctypes.c_double
+    lib.t_ln_product.argtypes = [ctypes.c_uint32, ctypes.c_uint32, vp]
+    lib.t_neumaier_mean.restype = ctypes.c_double
+    lib.t_neumaier_mean.argtypes = [vp, ctypes.c_int64]
+    lib.t_pair_ij.restype = None
+    lib.t_pair_ij.argtypes = [ctypes.c_uint32, ctypes.c_uint32, vp, vp]
+    lib.t_row_off.restype = ctypes.c_uint64
+    lib.t_row_off.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
+    lib.t_ecdf_y.restype = ctypes.c_double
+    lib.t_ecdf_y.argtypes = [ctypes.c_uint64, ctypes.c_uint64]
+    lib.t_build_lntab.restype = None
+    lib.t_build_lntab.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64]
+    return lib
+
+
+@pytest.fixture(scope="session")
+def lntab(math_host):
+    n = 1 << 17
+    tab = np.empty(2 * n, dtype=np.float64)
+    math_host.t_build_lntab(tab.ctypes.data, 0, n)
+    return tab
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx(lg, liblgmi_path):
+    if not has_gpu():
+        pytest.skip("no CUDA device")
+    return lg.get_context(0)
