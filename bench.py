@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- site-pairs MI/s of the MI step on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU MI step
+
+Workload (N=1): BASELINE.json configs[1] -- 20 000 units (footprint x strand),
+50 candidate sites x 200 reads each, coverage 0.5, mi_min_common_read 6:
+24.5 M candidate site pairs per step.  One step = one pass of the whole MI
+step (pair MI for every candidate, min-common filter, het filter, per-site
+mean) over that batch.  For N>1 each rank owns its own 20 000-unit shard of an
+N-times larger transcriptome (units are independent: no collective on the data
+path; torch.distributed is used only for the barrier and the max-over-ranks
+time), so scaling is "weak".
+
+Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM;
+`e2e` goes through the C-ABI calls with pinned HOST buffers, H2D and D2H inside
+the timed region.  `roofline` is for the dominant kernel (k_pairs), timed live
+with CUDA events on the launching stream.  `cpu_baseline` times the oracle's
+port of the reference step on the host cores on a bounded sample of the same
+units.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "site-pairs MI/sec"
+UNIT = "site-pairs/s"
+CFG = dict(units=20000, sites=50, reads=200, cov=0.5, min_common=6, seed=20261020)
+CHUNK = 500
+L2_FLUSH_BYTES = 512 << 20
+
+
+def workload_name():
+    return ("cfg2: %(units)d units x %(sites)d sites x %(reads)d reads, cov %(cov)g, "
+            "mi_min_common_read %(min_common)d" % CFG)
+
+
+# --------------------------------------------------------------------------- host cores / CPU arm
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def sample_units(n_units):
+    """The first `n_units` units of rank 0's workload, in the reference's dict form."""
+    synth = importlib.import_module("l-giremi_b200.synth")
+    sb = synth.make_uniform(CFG["seed"], CHUNK, CFG["sites"], CFG["reads"], CFG["cov"], chunk=CHUNK)
+    return [sb.mismatches(g) for g in range(min(n_units, CHUNK))]
+
+
+def cpu_step(pool, cores, units, min_common):
+    """The reference's MI step over `units` on `cores` processes, chunked the way
+    giremi.py:367-370 chunks footprints.  Returns (pairs, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_port
+    n = max(1, len(units) // cores // 2)
+    chunks = [(units[k:k + n], min_common) for k in range(0, len(units), n)]
+    t0 = time.perf_counter()
+    out = pool.map(ref_port.port_chunk, chunks)
+    dt = time.perf_counter() - t0
+    return sum(p for p, _ in out), dt
+
+
+def make_pool(cores):
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_port  # noqa: F401  (imported before the fork so that workers have sklearn loaded)
+    return mp.get_context("fork").Pool(cores)
+
+
+def cpu_baseline(target_seconds=15.0):
+    cores = host_cores()
+    units = sample_units(CHUNK)
+    with make_pool(cores) as pool:
+        pairs, dt = cpu_step(pool, cores, units[:2 * cores], CFG["min_common"])       # calibration + warm-up
+        rate = pairs / dt
+        n = int(max(2 * cores, min(CHUNK, target_seconds * rate / 1225)))
+        pairs, dt = cpu_step(pool, cores, units[:n], CFG["min_common"])
+    return {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "first %d of %d units of the workload (%d candidate pairs, %.1f s wall, mp.Pool(%d)); "
+                      "oracle/ref_port.py = the reference's per-pair dict rebuild + sklearn mutual_info_score"
+                      % (n, CFG["units"], pairs, dt, cores)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU MI step on the host cores, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    cores = host_cores()
+    units = sample_units(CHUNK)
+    budget = 150.0                                           # seconds for the whole run
+    with make_pool(cores) as pool:
+        pairs, dt = cpu_step(pool, cores, units[:2 * cores], CFG["min_common"])
+        rate = pairs / dt
+        per_step = budget / max(1, args.steps + args.warmup)
+        n = int(max(cores, min(CHUNK, per_step * rate / 1225)))
+        for _ in range(args.warmup):
+            cpu_step(pool, cores, units[:n], CFG["min_common"])
+        tot_pairs, tot_dt = 0, 0.0
+        for _ in range(args.steps):
+            p, d = cpu_step(pool, cores, units[:n], CFG["min_common"])
+            tot_pairs += p
+            tot_dt += d
+    value = tot_pairs / tot_dt
+    sample = ("each step = first %d of %d units of the workload (%d candidate pairs) through mp.Pool(%d); "
+              "throughput in pairs/s is size-independent for equal-shape units" % (n, CFG["units"], n * 1225, cores))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_dt / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (numpy/sklearn)",
+        "data": "synthetic", "config": {"workload": workload_name(), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        inside = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, smax, reasons = [], [], set()
+        for row in inside:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the MI step has no CPU path (use --impl reference for the CPU arm)")
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lg = importlib.import_module("l-giremi_b200")
+    synth = importlib.import_module("l-giremi_b200.synth")
+    ctx = lg.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)                       # torch.cuda.Event sees the library's launches
+
+    # this rank's shard: LPT over the global unit list (equal costs -> equal bins); its data by seed
+    G = CFG["units"]
+    costs = np.full(G * world, lg.unit_costs(np.array([(0, CFG["sites"], CFG["reads"], 8, 0)],
+                                                      dtype=lg.UNIT_DESC))[0], dtype=np.uint64)
+    bin_of, load = lg.partition_lpt(costs, world)
+    assert int((bin_of == rank).sum()) == G and load.max() == load.min()
+    pb = synth.make_uniform_planes(CFG["seed"] + rank, G, CFG["sites"], CFG["reads"], CFG["cov"], chunk=CHUNK)
+    pairs_per_step = pb.n_candidates
+
+    # pinned host staging (the public API's input buffers)
+    pin_planes = ctx.pinned_empty(pb.planes.shape, np.uint32)
+    pin_flags = ctx.pinned_empty(pb.site_flags.shape, np.uint8)
+    pin_planes.array[...] = pb.planes
+    pin_flags.array[...] = pb.site_flags
+    batch = lg.Batch(ctx, pb)
+    batch.upload(pin_planes.array, pin_flags.array)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    mode_dev = lg.MODE_ALL_PAIRS
+    mc = CFG["min_common"]
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for _ in range(args.warmup):
+        batch.run(mc, mode_dev)
+    res = batch.sync()
+    n_records = int(res.n_records)
+    algo_bytes = batch.algorithmic_bytes()
+    launches0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    pairs_ms = []
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                                        # L2 flush between timed iterations (untimed)
+        ev[k][0].record(stream)
+        batch.run(mc, mode_dev)
+        ev[k][1].record(stream)
+        r = batch.sync()
+        pairs_ms.append(float(r.pairs_kernel_ms))
+    barrier()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    launches = ctx.launch_count - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = pairs_per_step * world * args.steps / (dev_ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------
+    mode_e2e = lg.MODE_HET_ONLY                              # what mismatch.py:393-404 hands on
+    def e2e_step():
+        batch.upload(pin_planes.array, pin_flags.array)      # H2D from pinned host memory
+        batch.run(mc, mode_e2e)
+        return batch.download(copy=False)                    # D2H of records + per-site means, stream sync
+    for _ in range(args.warmup):
+        out = e2e_step()
+    h2d = pb.planes.nbytes + pb.site_flags.nbytes
+    d2h = out.n_records * 16 + pb.n_sites * 12 + (pb.n_units + 1) * 8 + 16
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    barrier()
+    e2e_value = pairs_per_step * world * args.steps / float(t.item())
+    e2e_records = int(out.n_records)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    peak_src = "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k_ms = sum(pairs_ms) / len(pairs_ms)
+    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_pairs_dram_bytes_per_launch")
+        except (OSError, ValueError):
+            traffic = None
+
+    cpu = None if args.no_cpu_baseline else cpu_baseline()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 popcount + f64 MI", "data": "synthetic",
+        "config": {"workload": workload_name(), "units_per_gpu": G, "pairs_per_step_per_gpu": pairs_per_step,
+                   "surviving_pairs_per_step_per_gpu": n_records, "mode": "ALL_PAIRS (every candidate evaluated and "
+                   "every survivor written)", "l2": "512 MiB buffer written between timed iterations",
+                   "partition": "LPT over %d units -> %d bins, loads equal" % (G * world, world)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "k_pairs", "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes,
+                     "peak_source": peak_src,
+                     "kernel_share_of_step": k_ms * args.steps / dev_ms if dev_ms else None},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "mode": "HET_ONLY: all candidates evaluated, het-kept rows (%d) + per-site mean MI returned"
+                        % e2e_records, "ms_per_step": 1e3 * float(t.item()) / args.steps},
+        "gpu_launches": launches * world,
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["graft", "reference"], default="graft")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

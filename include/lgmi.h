@@ -42,6 +42,13 @@ extern "C" {
 
 #define LGMI_VERSION 100 /* 0.1.0 */
 
+/* the library is built with -fvisibility=hidden; only these are exported */
+#if defined(__GNUC__)
+#define LGMI_API __attribute__((visibility("default")))
+#else
+#define LGMI_API
+#endif
+
 typedef enum {
   LGMI_OK = 0,
   LGMI_ERR_CUDA = -1,       /* a CUDA runtime call failed                      */
@@ -125,61 +132,63 @@ typedef struct {
                                 /*  mismatch.py:476-479)                       */
   const uint32_t* site_cnt;     /* number of het-kept pairs per site           */
   const uint64_t* unit_rec_off; /* n_units+1 offsets of each unit's records    */
-  float kernel_ms;              /* device time of the compute kernels          */
+  float kernel_ms;              /* device time of all compute kernels of the   */
+                                /* run (CUDA events on the launching stream)   */
+  float pairs_kernel_ms;        /* device time of the pair kernel alone        */
 } lgmi_result;
 
 typedef struct lgmi_ctx lgmi_t;
 typedef struct lgmi_batch lgmi_batch_t;
 
 /* ----- context ------------------------------------------------------------ */
-int lgmi_version(void);
+LGMI_API int lgmi_version(void);
 /* device: CUDA ordinal.  Fails with LGMI_ERR_NODEVICE if there is no GPU.     */
-int lgmi_create(int device, lgmi_t** out);
-void lgmi_destroy(lgmi_t* ctx);
-const char* lgmi_last_error(const lgmi_t* ctx); /* ctx may be NULL: last create error */
+LGMI_API int lgmi_create(int device, lgmi_t** out);
+LGMI_API void lgmi_destroy(lgmi_t* ctx);
+LGMI_API const char* lgmi_last_error(const lgmi_t* ctx); /* ctx may be NULL: last create error */
 /* Launch on a caller-owned stream (cudaStream_t as void*), e.g. torch's       *
  * current stream so that torch.cuda.Event brackets the kernels. NULL restores *
  * the context's own stream.                                                   */
-int lgmi_set_stream(lgmi_t* ctx, void* cuda_stream);
-int lgmi_pinned_alloc(lgmi_t* ctx, size_t bytes, void** out);
-int lgmi_pinned_free(lgmi_t* ctx, void* ptr);
+LGMI_API int lgmi_set_stream(lgmi_t* ctx, void* cuda_stream);
+LGMI_API int lgmi_pinned_alloc(lgmi_t* ctx, size_t bytes, void** out);
+LGMI_API int lgmi_pinned_free(lgmi_t* ctx, void* ptr);
 /* number of kernels this library has launched on the context so far           */
-uint64_t lgmi_launch_count(const lgmi_t* ctx);
+LGMI_API uint64_t lgmi_launch_count(const lgmi_t* ctx);
 
 /* ----- batched MI step: replaces the per-unit loop                           *
  *   mismatch.py:387-404 = mutual_information.py:6-45 -> het filter -> :48-60  */
 /* Builds device-side work tables and sizes the outputs for `units`.           */
-int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units,
+LGMI_API int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units,
                       uint64_t plane_words, uint64_t n_sites, lgmi_batch_t** out);
-void lgmi_batch_destroy(lgmi_batch_t* b);
+LGMI_API void lgmi_batch_destroy(lgmi_batch_t* b);
 /* async H2D of planes (plane_words u32) and site_flags (n_sites bytes)        */
-int lgmi_batch_upload(lgmi_batch_t* b, const uint32_t* planes, const uint8_t* site_flags);
+LGMI_API int lgmi_batch_upload(lgmi_batch_t* b, const uint32_t* planes, const uint8_t* site_flags);
 /* launches the kernels (async).  min_common: keep a pair iff                  *
  * common >= min_common (strict '<' drop, mutual_information.py:19).           */
-int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode);
+LGMI_API int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode);
 /* async D2H of whatever the last run produced, then stream sync; fills *out.  */
-int lgmi_batch_download(lgmi_batch_t* b, lgmi_result* out);
+LGMI_API int lgmi_batch_download(lgmi_batch_t* b, lgmi_result* out);
 /* stream sync only; fills the scalar fields of *out (no record copy)          */
-int lgmi_batch_sync(lgmi_batch_t* b, lgmi_result* out);
+LGMI_API int lgmi_batch_sync(lgmi_batch_t* b, lgmi_result* out);
 /* device pointers of the batch's buffers, for device-resident callers         *
  * (benchmarks that generate or keep inputs in HBM).                           */
-int lgmi_batch_device_ptrs(lgmi_batch_t* b, void** d_planes, void** d_site_flags,
+LGMI_API int lgmi_batch_device_ptrs(lgmi_batch_t* b, void** d_planes, void** d_site_flags,
                            void** d_records, void** d_site_mean);
 /* algorithmic bytes of the last run: planes + flags read once,    *
  * 16 B per emitted record, 12 B per site.                                     */
-int lgmi_batch_algorithmic_bytes(lgmi_batch_t* b, uint64_t* bytes);
+LGMI_API int lgmi_batch_algorithmic_bytes(lgmi_batch_t* b, uint64_t* bytes);
 
 /* one-shot convenience: create + upload + run + download (+ destroy on wait)  */
-int lgmi_submit(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units,
+LGMI_API int lgmi_submit(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units,
                 const uint32_t* planes, uint64_t plane_words,
                 const uint8_t* site_flags, uint64_t n_sites, int min_common,
                 uint32_t mode);
-int lgmi_wait(lgmi_t* ctx, lgmi_result* out); /* result valid until next submit */
+LGMI_API int lgmi_wait(lgmi_t* ctx, lgmi_result* out); /* result valid until next submit */
 
 /* ----- mean of pre-computed rows: mutual_information.py:48-60 -------------- *
  * CSR form: site s owns values[offsets[s] .. offsets[s+1]) in row order.      *
  * mean[s] = sum/len with CPython's compensated float sum; NaN for empty.      */
-int lgmi_site_mean_csr(lgmi_t* ctx, const uint64_t* offsets, const double* values,
+LGMI_API int lgmi_site_mean_csr(lgmi_t* ctx, const uint64_t* offsets, const double* values,
                        uint64_t n_sites, double* mean_out);
 
 /* ----- global pass: stat.py:7-29 + giremi.py:415-429 + :97-114 ------------- *
@@ -188,17 +197,17 @@ int lgmi_site_mean_csr(lgmi_t* ctx, const uint64_t* offsets, const double* value
  * call[s] = 1 if mean notna & mip<=thr & type==mismatch                       *
  *           2 if mean notna & mip> thr & type!=mismatch, else 0               *
  * site_flags carries the type in its low 2 bits.  call may be NULL.           */
-int lgmi_ecdf(lgmi_t* ctx, const double* mean, const uint8_t* site_flags, uint64_t n,
+LGMI_API int lgmi_ecdf(lgmi_t* ctx, const double* mean, const uint8_t* site_flags, uint64_t n,
               double threshold, double* mip, uint8_t* call);
 /* ecdf(x)(samples): y[searchsorted(sort(x), samples, 'left')]  (stat.py:16-27)*/
-int lgmi_ecdf_eval(lgmi_t* ctx, const double* x, uint64_t n, const double* samples,
+LGMI_API int lgmi_ecdf_eval(lgmi_t* ctx, const double* x, uint64_t n, const double* samples,
                    uint64_t n_samples, double* out);
 
 /* ----- multi-GPU partitioning (no collective) ------------------- *
  * cost(unit) = S(S-1)/2 * ceil(R/64).  Longest-processing-time greedy into    *
  * n_bins; bin_of[u] receives the bin.  Deterministic (ties: lower index).     */
-uint64_t lgmi_unit_cost(uint32_t n_sites, uint32_t n_reads);
-int lgmi_partition_lpt(const uint64_t* cost, uint32_t n_units, uint32_t n_bins,
+LGMI_API uint64_t lgmi_unit_cost(uint32_t n_sites, uint32_t n_reads);
+LGMI_API int lgmi_partition_lpt(const uint64_t* cost, uint32_t n_units, uint32_t n_bins,
                        uint32_t* bin_of, uint64_t* bin_load);
 
 #ifdef __cplusplus

@@ -54,6 +54,7 @@ class Result(C.Structure):
         ("site_cnt", C.c_void_p),
         ("unit_rec_off", C.c_void_p),
         ("kernel_ms", C.c_float),
+        ("pairs_kernel_ms", C.c_float),
     ]
 
 

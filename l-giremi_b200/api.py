@@ -103,6 +103,7 @@ class StepResult:
         self.n_evaluated = int(res.n_evaluated)
         self.n_records = int(res.n_records)
         self.kernel_ms = float(res.kernel_ms)
+        self.pairs_kernel_ms = float(res.pairs_kernel_ms)
         rec = array_at(res.records, PAIR_REC, self.n_records)
         mean = array_at(res.site_mean, np.float64, int(res.n_sites))
         cnt = array_at(res.site_cnt, np.uint32, int(res.n_sites))

@@ -15,7 +15,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",                      # the fp64 epilogue must not contract a*b+c
-    "-Xcompiler", "-fPIC,-ffp-contract=off",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
     "-Xptxas", "-v",
 ]
 

@@ -30,7 +30,7 @@ struct lgmi_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   std::string err;
   uint64_t launches = 0;
   // ln table
@@ -153,7 +153,8 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess) {
     int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
     return rc;
@@ -172,6 +173,8 @@ extern "C" void lgmi_destroy(lgmi_t* ctx) {
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+  if (ctx->ev3) cudaEventDestroy(ctx->ev3);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -394,10 +397,12 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     k_fill_nan<<<(unsigned)((b->n_sites + 255) / 256), 256, 0, ctx->stream>>>(b->d_site_mean, b->d_site_cnt, b->n_sites);
     ++ctx->launches;
   }
+  CU(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
   if (b->n_items) {
     k_pairs<<<b->n_items, kThreads, 0, ctx->stream>>>(P);
     ++ctx->launches;
   }
+  CU(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
   if (b->n_mean_items) {
     k_site_mean_dense<<<b->n_mean_items, 128, 0, ctx->stream>>>(b->d_units, b->d_mean_items, b->d_flags, b->d_dense,
                                                               b->d_site_mean, b->d_site_cnt);
@@ -421,6 +426,8 @@ static int fill_scalars(lgmi_batch* b, lgmi_result* out) {
   float ms = 0.f;
   CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   out->kernel_ms = ms;
+  CU(ctx, cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
+  out->pairs_kernel_ms = ms;
   return LGMI_OK;
 }
 

@@ -1,0 +1,381 @@
+"""GPU parity tests: liblgmi.so (through its C ABI, via the ctypes binding)
+against the oracle and the golden fixtures generated from the real reference.
+
+  * pair sets, 3x3 counts, threshold calls, record order: bit-exact
+  * MI, mean MI, mip: 1e-10 relative (conftest.MI_RTOL / MI_ATOL), with a floor
+    on the fraction that must be bit-identical
+"""
+import importlib
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_mi_close, golden_mismatches, unhex
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import c_oracle  # noqa: E402
+from fuzz import random_mismatches  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+synth = importlib.import_module("l-giremi_b200.synth")
+enc = importlib.import_module("l-giremi_b200.encode")
+
+
+def signed(labels):
+    out = labels.astype(np.int16)
+    out[out == 255] = -1
+    return out.astype(np.int8)
+
+
+def oracle_unit(eu, min_common):
+    """Oracle on an EncodedUnit: (i, j, mi, tables, mean, cnt)."""
+    S = eu.n_sites
+    if S < 2:
+        z = np.zeros(0, np.int32)
+        return z, z, np.zeros(0), np.zeros((0, 9), np.int64), np.full(S, np.nan), np.zeros(S, np.int32)
+    i, j, mi, tab = c_oracle.unit_pairs_from_labels(signed(eu.labels), None, min_common)
+    is_het = np.array([t == 'het_snp' for t in eu.types], dtype=np.uint8)
+    mean, cnt = c_oracle.site_means(S, is_het, i, j, mi)
+    return i, j, mi, tab, mean, cnt
+
+
+def check_batch(lg, ctx, eus, min_common, min_exact=0.97):
+    """Runs one batch in ALL_PAIRS|EMIT_COUNTS and HET_ONLY modes and checks
+    every output against the oracle."""
+    pb = lg.pack_units(eus)
+    full = lg.mi_step_batched(pb, min_common, lg.MODE_ALL_PAIRS | lg.MODE_EMIT_COUNTS, ctx=ctx)
+    het = lg.mi_step_batched(pb, min_common, lg.MODE_HET_ONLY, ctx=ctx)
+    skip = lg.mi_step_batched(pb, min_common, lg.MODE_HET_ONLY | lg.MODE_SKIP_NONHET, ctx=ctx)
+    assert full.n_candidates == pb.n_candidates == het.n_candidates
+    assert full.unit_rec_off[0] == 0 and full.unit_rec_off[-1] == full.n_records
+    got_mi, want_mi, got_mean, want_mean = [], [], [], []
+    for u, eu in enumerate(eus):
+        i, j, mi, tab, mean, cnt = oracle_unit(eu, min_common)
+        rec = full.unit_records(u)
+        assert np.all(rec['unit'] == u)
+        assert rec['i'].tolist() == i.tolist() and rec['j'].tolist() == j.tolist(), "pair set of unit %d" % u
+        assert np.array_equal(full.unit_counts(u).astype(np.int64), tab), "3x3 counts of unit %d" % u
+        got_mi.append(rec['mi'])
+        want_mi.append(mi)
+        is_het = np.array([t == 'het_snp' for t in eu.types], dtype=bool)
+        keep = is_het[i] | is_het[j] if len(i) else np.zeros(0, bool)
+        for res in (het, skip):
+            hrec = res.unit_records(u)
+            assert hrec['i'].tolist() == i[keep].tolist() and hrec['j'].tolist() == j[keep].tolist()
+            assert np.array_equal(hrec['mi'], rec['mi'][keep])          # same bits in every mode
+        off = int(pb.units['site_off'][u])
+        for res in (full, het, skip):
+            assert res.site_cnt[off:off + eu.n_sites].tolist() == cnt.tolist()
+            assert np.array_equal(res.site_mean[off:off + eu.n_sites], full.site_mean[off:off + eu.n_sites],
+                                  equal_nan=True)
+        got_mean.append(full.site_mean[off:off + eu.n_sites])
+        want_mean.append(mean)
+    cat = lambda v: np.concatenate(v) if v else np.zeros(0)
+    assert_mi_close(cat(got_mi), cat(want_mi), min_exact, "pair MI")
+    assert_mi_close(cat(got_mean), cat(want_mean), min_exact, "mean MI")
+    return full
+
+
+# --------------------------------------------------------------------------- drop-in functions
+def rows_equal(got, want_hex):
+    want = [[r[0], r[1], r[2], r[3], unhex(r[4])] for r in want_hex]
+    assert [r[:4] for r in got] == [r[:4] for r in want]
+    assert all(isinstance(r[4], float) for r in got)
+    assert_mi_close([r[4] for r in got], [r[4] for r in want], 0.97)
+
+
+def test_kat_drop_in_functions(lg, gpu_ctx, golden):
+    kat = golden("kat.json")
+    for name in ("ab", "cb", "db", "ef_min6", "ef_min7", "abc"):
+        unit = kat[name]
+        m = golden_mismatches(unit)
+        rows = lg.mismatch_pair_mutual_info(m, unit["min_common"])
+        rows_equal(rows, unit["rows"])
+        kept = [r for r in rows if r[1] == 'het_snp' or r[3] == 'het_snp']
+        means = lg.mean_mismatch_pair_mutual_info(kept) if kept else []
+        assert [p for p, _ in means] == [p for p, _ in unit["means"]]
+        assert_mi_close([v for _, v in means], [unhex(v) for _, v in unit["means"]], 0.9)
+    # the survey's known answers, literally
+    m = golden_mismatches(kat["abc"])
+    got = {(r[0], r[2]): r[4] for r in lg.mismatch_pair_mutual_info(m, 6)}
+    assert got == {(10, 20): 0.6931471805599454, (10, 30): 0.4620981203732968, (20, 30): 0.4620981203732968}
+    assert lg.mismatch_pair_mutual_info(golden_mismatches(kat["ef_min6"]), 6)[0][4] == 0.0
+    assert lg.mismatch_pair_mutual_info({}, 6) == []
+    assert lg.mismatch_pair_mutual_info({10: m[10]}, 6) == []
+    assert lg.mean_mismatch_pair_mutual_info([]) == []
+
+
+def test_default_min_common_is_five(lg, gpu_ctx):
+    reads = ['r%d' % k for k in range(10)]
+    a = {'ref': 'A', 'type': 'het_snp', 'depth': {'A': 3, 'G': 2}, 'nt': {'A': reads[:3], 'G': reads[3:5]}}
+    b = {'ref': 'A', 'type': 'mismatch', 'depth': {'A': 2, 'G': 3}, 'nt': {'A': reads[:2], 'G': reads[2:5]}}
+    assert len(lg.mismatch_pair_mutual_info({1: a, 2: b})) == 1          # 5 common, default 5: kept
+    assert len(lg.mismatch_pair_mutual_info({1: a, 2: b}, 6)) == 0
+
+
+def test_index_error_like_reference(lg, gpu_ctx):
+    ok = {'ref': 'A', 'type': 'het_snp', 'depth': {'A': 6, 'C': 6},
+          'nt': {'A': ['r%d' % k for k in range(6)], 'C': ['r%d' % k for k in range(6, 12)]}}
+    bad = {'ref': 'A', 'type': 'mismatch', 'depth': {'G': 12}, 'nt': {'G': ['r%d' % k for k in range(12)]}}
+    with pytest.raises(IndexError):
+        lg.mismatch_pair_mutual_info({10: bad, 20: ok}, 6)
+    assert lg.mismatch_pair_mutual_info({10: bad, 20: ok}, 13) == []
+
+
+@pytest.mark.parametrize("fixture", ["units_fuzz.json", "units_synth.json"])
+def test_golden_units_drop_in(lg, gpu_ctx, golden, fixture):
+    for unit in golden(fixture):
+        m = golden_mismatches(unit)
+        rows = lg.mismatch_pair_mutual_info(m, unit["min_common"])
+        rows_equal(rows, unit["rows"])
+        kept = [r for r in rows if r[1] == 'het_snp' or r[3] == 'het_snp']
+        means = lg.mean_mismatch_pair_mutual_info(kept) if kept else []
+        assert [p for p, _ in means] == [p for p, _ in unit["means"]]
+        assert_mi_close([v for _, v in means], [unhex(v) for _, v in unit["means"]])
+
+
+def test_golden_units_batched(lg, gpu_ctx, golden):
+    """All golden units with the same min_common in ONE submit."""
+    units = golden("units_fuzz.json") + golden("units_synth.json")
+    for mc in sorted(set(u["min_common"] for u in units)):
+        group = [u for u in units if u["min_common"] == mc]
+        eus = [lg.encode_mismatches(golden_mismatches(u)) for u in group]
+        ok = [k for k, eu in enumerate(eus) if not eu.bad_sites]
+        full = check_batch(lg, gpu_ctx, [eus[k] for k in ok], mc)
+        for n, k in enumerate(ok):
+            rec = full.unit_records(n)
+            pos, typ = eus[k].positions, eus[k].types
+            rows = [[pos[i], typ[i], pos[j], typ[j], mi] for i, j, mi in
+                    zip(rec['i'].tolist(), rec['j'].tolist(), rec['mi'].tolist())]
+            rows_equal(rows, group[k]["rows"])
+            # mean MI against the reference's own output
+            off = int(np.sum([eus[q].n_sites for q in ok[:n]]))
+            want = dict((p, unhex(v)) for p, v in group[k]["means"])
+            got = {p: v for p, v in zip(pos, full.site_mean[off:off + len(pos)].tolist()) if not math.isnan(v)}
+            assert list(got) == sorted(want)
+            assert_mi_close([got[p] for p in got], [want[p] for p in got])
+
+
+# --------------------------------------------------------------------------- batched kernel vs oracle
+def test_fuzz_batch_all_quirks(lg, gpu_ctx):
+    rng = np.random.default_rng(2026)
+    ms = [random_mismatches(rng) for _ in range(300)]
+    eus = [lg.encode_mismatches(m) for m in ms]
+    eus = [e for e in eus if not e.bad_sites]
+    for mc in (1, 3, 6):
+        check_batch(lg, gpu_ctx, eus, mc)
+
+
+def test_ragged_and_degenerate_units(lg, gpu_ctx):
+    """Empty units, single-site units, R not a multiple of 32/128, exactly
+    2048 / 2049 pairs per unit (work-item boundary), units spanning many items."""
+    rng = np.random.default_rng(77)
+    shapes = [(0, 0), (1, 9), (2, 1), (2, 6), (3, 31), (5, 32), (7, 33), (9, 127), (11, 128), (4, 129),
+              (64, 40), (65, 40), (66, 70), (130, 17), (50, 200), (23, 1000), (300, 90)]
+    eus = []
+    for S, R in shapes:
+        if S == 0:
+            eus.append(enc.EncodedUnit([], [], np.zeros((0, 0), np.uint8)))
+            continue
+        a, k = synth.draw_alleles(rng, 1, S, R, float(rng.uniform(0.2, 0.9))) if R >= 2 and S >= 1 else (None, None)
+        if a is None:
+            lab = np.full((S, R), 2, np.uint8)
+            eus.append(enc.EncodedUnit(list(range(S)), ['het_snp'] * S, lab))
+            continue
+        lab = synth.labels_from_alleles(a[0])
+        eus.append(enc.EncodedUnit([1000 + 37 * s for s in range(S)],
+                                   [("mismatch", "snp", "het_snp")[int(x)] for x in k[0]], lab))
+    for mc in (1, 6, 20):
+        check_batch(lg, gpu_ctx, eus, mc)
+
+
+def test_min_common_is_strict_less_than(lg, gpu_ctx):
+    """A pair with exactly min_common common reads is kept (mutual_information.py:19)."""
+    for n in (1, 5, 6, 7, 32, 33, 128, 129):
+        lab = np.full((2, n + 3), 255, np.uint8)
+        lab[0, :n] = [2 if k % 2 else 1 for k in range(n)]
+        lab[1, :n] = [2 if k % 3 else 1 for k in range(n)]
+        lab[0, n] = 2          # covered by one site only
+        lab[1, n + 1] = 1
+        eu = enc.EncodedUnit([10, 20], ['het_snp', 'mismatch'], lab)
+        pb = lg.pack_units([eu])
+        assert lg.mi_step_batched(pb, n, lg.MODE_ALL_PAIRS, ctx=gpu_ctx).n_records == 1
+        assert lg.mi_step_batched(pb, n + 1, lg.MODE_ALL_PAIRS, ctx=gpu_ctx).n_records == 0
+        res = lg.mi_step_batched(pb, n + 1, lg.MODE_HET_ONLY, ctx=gpu_ctx)
+        assert np.isnan(res.site_mean).all() and res.site_cnt.tolist() == [0, 0]
+
+
+def test_heavy_tail_batch(lg, gpu_ctx):
+    pb, raw = synth.make_heavy_tail(20261022, 120, keep_raw=True, s_max=400, r_max=5000)
+    eus = [enc.EncodedUnit([1000 + 37 * s for s in range(a.shape[0])],
+                           [("mismatch", "snp", "het_snp")[int(x)] for x in k], synth.labels_from_alleles(a))
+           for a, k in raw]
+    full = check_batch(lg, gpu_ctx, eus, 6)
+    # the generator's own packing is the same bytes as pack_units
+    again = lg.mi_step_batched(pb, 6, lg.MODE_ALL_PAIRS, ctx=gpu_ctx)
+    assert np.array_equal(again.records, full.records)
+
+
+def test_deep_unit_large_counts(lg, gpu_ctx):
+    """R = 30 000: counts beyond 2^14, ln table grown on demand."""
+    rng = np.random.default_rng(5)
+    a, k = synth.draw_alleles(rng, 1, 24, 30000, 0.7)
+    eu = enc.EncodedUnit(list(range(24)), [("mismatch", "snp", "het_snp")[int(x)] for x in k[0]],
+                         synth.labels_from_alleles(a[0]))
+    check_batch(lg, gpu_ctx, [eu], 6, min_exact=0.9)
+
+
+def test_many_sites_multi_item_unit(lg, gpu_ctx):
+    """S = 700 (244 650 pairs, ~120 work items): ordered compaction across CTAs
+    and the multi-item per-site mean path."""
+    rng = np.random.default_rng(6)
+    a, k = synth.draw_alleles(rng, 1, 700, 64, 0.3)
+    eu = enc.EncodedUnit(list(range(700)), [("mismatch", "snp", "het_snp")[int(x)] for x in k[0]],
+                         synth.labels_from_alleles(a[0]))
+    small = enc.EncodedUnit([1, 2, 3], ['het_snp', 'mismatch', 'snp'], synth.labels_from_alleles(a[0][:3]))
+    check_batch(lg, gpu_ctx, [small, eu, small], 6)
+
+
+# --------------------------------------------------------------------------- full-size properties (cfg2)
+@pytest.fixture(scope="module")
+def cfg2(lg):
+    return synth.make_uniform(20261020, 20000, 50, 200, 0.5, chunk=500)
+
+
+def test_cfg2_full_size_properties(lg, gpu_ctx, cfg2):
+    pb = cfg2.plane_batch()
+    assert pb.n_candidates == 24_500_000
+    b = lg.Batch(gpu_ctx, pb)
+    b.upload()
+    b.run(6, lg.MODE_ALL_PAIRS)
+    r1 = b.download()
+    b.run(6, lg.MODE_ALL_PAIRS)
+    r2 = b.download()
+    assert np.array_equal(r1.records, r2.records)                         # deterministic, bit for bit
+    assert np.array_equal(r1.site_mean, r2.site_mean, equal_nan=True)
+    rec = r1.records
+    # reference row order: unit, then i, then j
+    key = rec['unit'].astype(np.int64) * (1 << 32) + rec['i'].astype(np.int64) * (1 << 16) + rec['j']
+    assert np.all(np.diff(key) > 0)
+    assert np.all(rec['i'] < rec['j']) and rec['j'].max() < 50
+    assert np.array_equal(np.searchsorted(rec['unit'], np.arange(20001)), r1.unit_rec_off.astype(np.int64))
+    assert np.all(rec['mi'] >= 0.0) and np.all(rec['mi'] <= math.log(3) + 1e-12)
+    # per-site mean recomputed on the host from the emitted records (any order-insensitive check)
+    flags = pb.site_flags & 3
+    site = np.arange(20000 * 50).reshape(20000, 50)
+    gi, gj = site[rec['unit'], rec['i']], site[rec['unit'], rec['j']]
+    keep = (flags[gi] == 2) | (flags[gj] == 2)
+    tot = np.bincount(gi[keep], rec['mi'][keep], 20000 * 50) + np.bincount(gj[keep], rec['mi'][keep], 20000 * 50)
+    cnt = np.bincount(gi[keep], minlength=20000 * 50) + np.bincount(gj[keep], minlength=20000 * 50)
+    assert np.array_equal(cnt, r1.site_cnt)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        assert np.allclose(tot / cnt, r1.site_mean, rtol=1e-12, atol=1e-15, equal_nan=True)
+    # a random sample of units against the oracle
+    rng = np.random.default_rng(1)
+    for g in rng.choice(20000, 40, replace=False).tolist():
+        i, j, mi, tab, mean, cnt_o = oracle_unit(cfg2.encoded(g), 6)
+        u = r1.unit_records(g)
+        assert u['i'].tolist() == i.tolist() and u['j'].tolist() == j.tolist()
+        assert_mi_close(u['mi'], mi)
+        assert_mi_close(r1.site_mean[g * 50:(g + 1) * 50], mean)
+    b.close()
+
+
+def test_read_permutation_and_label_swap_invariance(lg, gpu_ctx):
+    """MI does not depend on read order, nor on which of two alleles is called
+    major when no third allele is present."""
+    rng = np.random.default_rng(12)
+    a, k = synth.draw_alleles(rng, 1, 40, 333, 0.6)
+    lab = synth.labels_from_alleles(a[0])
+    types = [("mismatch", "snp", "het_snp")[int(x)] for x in k[0]]
+    eu0 = enc.EncodedUnit(list(range(40)), types, lab)
+    eu1 = enc.EncodedUnit(list(range(40)), types, lab[:, rng.permutation(333)])
+    swapped = lab.copy()
+    bi = ~(lab == 0).any(axis=1)
+    swapped[bi] = np.where(lab[bi] == 2, 1, np.where(lab[bi] == 1, 2, lab[bi]))
+    eu2 = enc.EncodedUnit(list(range(40)), types, swapped)
+    res = lg.mi_step_batched(lg.pack_units([eu0, eu1, eu2]), 6, lg.MODE_ALL_PAIRS, ctx=gpu_ctx)
+    r0, r1, r2 = (res.unit_records(u) for u in range(3))
+    assert np.array_equal(r0['i'], r1['i']) and np.array_equal(r0['j'], r1['j'])
+    assert np.array_equal(r0['mi'], r1['mi'])                 # integer counts are identical -> same bits
+    assert np.array_equal(r0['i'], r2['i'])
+    assert_mi_close(r2['mi'], r0['mi'])
+
+
+# --------------------------------------------------------------------------- global pass
+def test_ecdf_drop_in_matches_reference(lg, gpu_ctx, golden):
+    for case in golden("ecdf.json")["functions"]:
+        fn = lg.ecdf([unhex(v) for v in case["x"]])
+        samples = np.array([unhex(v) for v in case["samples"]])
+        want = np.array([unhex(v) for v in case["y"]])
+        assert np.array_equal(fn(samples), want)              # bit-exact: same linspace arithmetic
+        assert fn(float(samples[0])) == want[0]
+    k = golden("kat.json")["ecdf"]
+    assert lg.ecdf(k["x"])(np.array(k["samples"])).tolist() == [0, 0, 0.25, 0.75, 0.75, 1.0]
+    with pytest.raises(ZeroDivisionError):
+        lg.ecdf([])
+
+
+def test_mip_and_threshold_calls_match_reference(lg, gpu_ctx, golden):
+    tab = golden("ecdf.json")["site_table"]
+    mean = np.array([unhex(v) for v in tab["mean"]])
+    mip, call = lg.mip_and_calls(mean, tab["type"], tab["threshold"], ctx=gpu_ctx)
+    want = np.array([unhex(v) for v in tab["mip"]])
+    assert np.array_equal(mip, want, equal_nan=True)
+    assert (call == 1).tolist() == tab["positive"]
+    assert (call == 2).tolist() == tab["negative"]
+
+
+def test_mip_large_random_vs_oracle(lg, gpu_ctx):
+    rng = np.random.default_rng(3)
+    n = 300_000
+    mean = rng.random(n).round(4)                             # plenty of ties
+    mean[rng.random(n) < 0.3] = np.nan
+    code = rng.choice(np.array([0, 1, 2], np.uint8), n, p=[0.85, 0.05, 0.10])
+    for thr in (0.05, 0.5):
+        mip, call = lg.mip_and_calls(mean, code, thr, ctx=gpu_ctx)
+        wmip, wcall = c_oracle.mip_calls(mean, code, thr)
+        assert np.array_equal(mip, wmip, equal_nan=True)
+        assert np.array_equal(call, wcall)
+    # no het SNP at all -> everything NaN / no call
+    mip, call = lg.mip_and_calls(mean, np.zeros(n, np.uint8), 0.05, ctx=gpu_ctx)
+    assert np.isnan(mip).all() and not call.any()
+
+
+def test_end_to_end_calls_identical(lg, gpu_ctx, cfg2):
+    """units -> MI -> mean -> mip -> call on the GPU vs the oracle chain, on 300
+    units: every site's call at mi_p_threshold must be identical."""
+    idx = list(range(300))
+    eus = [cfg2.encoded(g) for g in idx]
+    res = lg.mi_step_batched(lg.pack_units(eus), 6, lg.MODE_HET_ONLY, ctx=gpu_ctx)
+    want_mean = np.concatenate([oracle_unit(eu, 6)[4] for eu in eus])
+    assert_mi_close(res.site_mean, want_mean)
+    code = np.concatenate([[c_oracle.TYPE_CODE[t] for t in eu.types] for eu in eus]).astype(np.uint8)
+    mip, call = lg.mip_and_calls(res.site_mean, code, 0.05, ctx=gpu_ctx)
+    wmip, wcall = c_oracle.mip_calls(want_mean, code, 0.05)
+    assert np.array_equal(call, wcall)
+    assert_mi_close(mip, wmip)
+
+
+# --------------------------------------------------------------------------- errors
+def test_argument_errors(lg, gpu_ctx):
+    pb = synth.make_uniform_planes(1, 2, 5, 40, 0.5)
+    bad = lg.PlaneBatch(pb.units.copy(), pb.planes, pb.site_flags)
+    bad.units['row_words'][0] = 3
+    with pytest.raises(lg.LgmiError) as e:
+        lg.Batch(gpu_ctx, bad)
+    assert e.value.code == -2
+    b = lg.Batch(gpu_ctx, pb)
+    with pytest.raises(lg.LgmiError) as e:
+        b.run(6)                                               # nothing uploaded
+    assert e.value.code == -4
+    b.upload()
+    with pytest.raises(lg.LgmiError):
+        b.run(6, lg.MODE_SKIP_NONHET)                          # needs HET_ONLY
+    b.close()
+    assert gpu_ctx.launch_count > 0
