@@ -103,7 +103,7 @@ def run_reference(args):
         return 0
     cores = host_cores()
     units = sample_units(CHUNK)
-    budget = 150.0                                           # seconds for the whole run
+    budget = 100.0                                           # seconds for the whole run
     with make_pool(cores) as pool:
         pairs, dt = cpu_step(pool, cores, units[:2 * cores], CFG["min_common"])
         rate = pairs / dt
@@ -159,7 +159,9 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        inside = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        # the timed region is tens of milliseconds: widen the window to the warm-up just before it,
+        # which runs the same kernels, so that the median has several samples under load
+        inside = [r for t, r in self.rows if t0 - 1.0 <= t <= t1 + 0.05] or [r for _, r in self.rows[-3:]]
         sm, smax, reasons = [], [], set()
         for row in inside:
             f = [x.strip() for x in row.split(",")]
@@ -203,7 +205,9 @@ def run_gpu(args):
     lg = importlib.import_module("l-giremi_b200")
     synth = importlib.import_module("l-giremi_b200.synth")
     ctx = lg.Context(local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                             # a real (non-default) stream: handle 0 would mean
+    torch.cuda.set_stream(stream)                            # "library's own stream" to lgmi_set_stream
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)                       # torch.cuda.Event sees the library's launches
 
     # this rank's shard: LPT over the global unit list (equal costs -> equal bins); its data by seed
@@ -233,11 +237,15 @@ def run_gpu(args):
     res = batch.sync()
     n_records = int(res.n_records)
     algo_bytes = batch.algorithmic_bytes()
-    launches0 = ctx.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     pairs_ms = []
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 1.0:                # ~1 s of the same kernels under the clock sampler
+        batch.run(mc, mode_dev)
+        batch.sync()
+    launches0 = ctx.launch_count
+    barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                                        # L2 flush between timed iterations (untimed)
@@ -263,13 +271,14 @@ def run_gpu(args):
         batch.upload(pin_planes.array, pin_flags.array)      # H2D from pinned host memory
         batch.run(mc, mode_e2e)
         return batch.download(copy=False)                    # D2H of records + per-site means, stream sync
-    for _ in range(args.warmup):
+    e2e_steps = 0 if args.no_e2e else args.steps
+    for _ in range(args.warmup if e2e_steps else 1):
         out = e2e_step()
     h2d = pb.planes.nbytes + pb.site_flags.nbytes
     d2h = out.n_records * 16 + pb.n_sites * 12 + (pb.n_units + 1) * 8 + 16
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         out = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -277,7 +286,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     barrier()
-    e2e_value = pairs_per_step * world * args.steps / float(t.item())
+    e2e_value = pairs_per_step * world * e2e_steps / float(t.item()) if e2e_steps else None
     e2e_records = int(out.n_records)
 
     if rank != 0:
@@ -319,7 +328,7 @@ def run_gpu(args):
                      "kernel_share_of_step": k_ms * args.steps / dev_ms if dev_ms else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "mode": "HET_ONLY: all candidates evaluated, het-kept rows (%d) + per-site mean MI returned"
-                        % e2e_records, "ms_per_step": 1e3 * float(t.item()) / args.steps},
+                        % e2e_records, "ms_per_step": 1e3 * float(t.item()) / e2e_steps if e2e_steps else None},
         "gpu_launches": launches * world,
         "clocks": clocks,
     }
@@ -338,6 +347,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["graft", "reference"], default="graft")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
     if args.impl == "reference":
