@@ -16,6 +16,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "../../include/lgmi.h"
 #include "lgmi_kernels.cuh"
@@ -41,11 +42,14 @@ struct lgmi_ctx {
   // scratch for ecdf / csr
   void* d_scratch = nullptr;
   size_t scratch_cap = 0;
+  // persistent launch shape of k_pairs
+  int num_sms = 0;
+  int pairs_ctas_per_sm = 0;
 };
 
 struct lgmi_batch {
   lgmi_ctx* ctx = nullptr;
-  uint32_t n_units = 0, n_items = 0, n_mean_items = 0;
+  uint32_t n_units = 0, n_items = 0, n_mean_items = 0, n_fast = 0;
   uint64_t plane_words = 0, n_sites = 0, n_candidates = 0, n_dense = 0;
   uint32_t max_reads = 0;
   std::vector<lgmi_unit_desc> h_units;
@@ -53,10 +57,16 @@ struct lgmi_batch {
   // device
   DevUnit* d_units = nullptr;
   Item* d_items = nullptr;
+  FastItem* d_fast_items = nullptr;
+  uint8_t* d_item_dense = nullptr;
+  uint32_t* d_n_generic = nullptr;
   MeanItem* d_mean_items = nullptr;
   uint32_t* d_planes = nullptr;
   uint8_t* d_flags = nullptr;
-  unsigned long long* d_status = nullptr;
+  unsigned long long* d_item_cnt = nullptr;  // n_items + 1 (last stays 0)
+  unsigned long long* d_item_off = nullptr;  // n_items + 1
+  void* d_scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
   Header* d_header = nullptr;
   lgmi_pair_rec* d_records = nullptr;
   uint64_t rec_cap = 0;
@@ -160,6 +170,17 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
     return rc;
   }
   ctx->stream = ctx->own_stream;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaFuncSetAttribute(k_pairs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem)) !=
+          cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pairs_ctas_per_sm, k_pairs_fast, kFastThreads,
+                                                    sizeof(FastSmem)) != cudaSuccess ||
+      ctx->pairs_ctas_per_sm < 1) {
+    int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: k_pairs_fast cannot be resident (%s)",
+                  cudaGetErrorString(cudaGetLastError()));
+    lgmi_destroy(ctx);
+    return rc;
+  }
   *out = ctx;
   return LGMI_OK;
 }
@@ -216,10 +237,15 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   }
   cudaFree(b->d_units);
   cudaFree(b->d_items);
+  cudaFree(b->d_fast_items);
+  cudaFree(b->d_item_dense);
+  cudaFree(b->d_n_generic);
   cudaFree(b->d_mean_items);
   cudaFree(b->d_planes);
   cudaFree(b->d_flags);
-  cudaFree(b->d_status);
+  cudaFree(b->d_item_cnt);
+  cudaFree(b->d_item_off);
+  cudaFree(b->d_scan_tmp);
   cudaFree(b->d_header);
   cudaFree(b->d_records);
   cudaFree(b->d_counts);
@@ -250,6 +276,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   b->h_units.assign(units, units + n_units);
 
   std::vector<DevUnit> du(n_units);
+  std::vector<FastItem> fast_items;
   std::vector<MeanItem> mean_items;
   uint64_t dense = 0;
   for (uint32_t k = 0; k < n_units; ++k) {
@@ -290,10 +317,24 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       it.pair_begin = t * (uint32_t)kPairsMax;
       it.pair_cnt = (uint32_t)std::min<uint64_t>(kPairsMax, np - (uint64_t)t * kPairsMax);
       it.flags = (t == 0 ? ITEM_FIRST : 0u) | (nit == 1 ? ITEM_SINGLE : 0u);
+      if (nit == 1 && np >= 1 && u.n_sites <= (uint32_t)kFastMaxS && u.n_reads <= (uint32_t)kFastMaxR) {
+        it.flags |= ITEM_FAST;
+        FastItem f;
+        f.plane_off = u.plane_off;
+        f.site_off = u.site_off;
+        f.unit = k;
+        f.item = (uint32_t)b->h_items.size();
+        f.S = (uint16_t)u.n_sites;
+        f.R = (uint16_t)u.n_reads;
+        f.W = u.row_words;
+        f.pad = 0;
+        fast_items.push_back(f);
+      }
       b->h_items.push_back(it);
     }
   }
   b->n_items = (uint32_t)b->h_items.size();
+  b->n_fast = (uint32_t)fast_items.size();
   b->n_mean_items = (uint32_t)mean_items.size();
   b->n_dense = dense;
 
@@ -310,10 +351,18 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
 
   BCU(cudaMalloc(&b->d_units, std::max<size_t>(1, n_units) * sizeof(DevUnit)));
   BCU(cudaMalloc(&b->d_items, std::max<size_t>(1, b->n_items) * sizeof(Item)));
+  BCU(cudaMalloc(&b->d_fast_items, std::max<size_t>(1, fast_items.size()) * sizeof(FastItem)));
+  BCU(cudaMalloc(&b->d_item_dense, std::max<size_t>(1, b->n_items)));
+  BCU(cudaMalloc(&b->d_n_generic, sizeof(uint32_t)));
   BCU(cudaMalloc(&b->d_mean_items, std::max<size_t>(1, mean_items.size()) * sizeof(MeanItem)));
   BCU(cudaMalloc(&b->d_planes, std::max<uint64_t>(4, plane_words) * sizeof(uint32_t)));
   BCU(cudaMalloc(&b->d_flags, std::max<uint64_t>(1, n_sites)));
-  BCU(cudaMalloc(&b->d_status, std::max<size_t>(1, b->n_items) * sizeof(unsigned long long)));
+  BCU(cudaMalloc(&b->d_item_cnt, ((size_t)b->n_items + 1) * sizeof(unsigned long long)));
+  BCU(cudaMalloc(&b->d_item_off, ((size_t)b->n_items + 1) * sizeof(unsigned long long)));
+  BCU(cub::DeviceScan::ExclusiveSum(nullptr, b->scan_tmp_bytes, b->d_item_cnt, b->d_item_off, (int)b->n_items + 1,
+                                    ctx->stream));
+  BCU(cudaMalloc(&b->d_scan_tmp, std::max<size_t>(b->scan_tmp_bytes, 16)));
+  BCU(cudaMemsetAsync(b->d_item_cnt, 0, ((size_t)b->n_items + 1) * sizeof(unsigned long long), ctx->stream));
   BCU(cudaMalloc(&b->d_header, sizeof(Header)));
   BCU(cudaMalloc(&b->d_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double)));
   BCU(cudaMalloc(&b->d_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t)));
@@ -327,6 +376,9 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   BCU(cudaHostAlloc(&b->h_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
   if (n_units) BCU(cudaMemcpyAsync(b->d_units, du.data(), n_units * sizeof(DevUnit), cudaMemcpyHostToDevice, ctx->stream));
   if (b->n_items) BCU(cudaMemcpyAsync(b->d_items, b->h_items.data(), b->n_items * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
+  if (!fast_items.empty())
+    BCU(cudaMemcpyAsync(b->d_fast_items, fast_items.data(), fast_items.size() * sizeof(FastItem), cudaMemcpyHostToDevice,
+                        ctx->stream));
   if (!mean_items.empty())
     BCU(cudaMemcpyAsync(b->d_mean_items, mean_items.data(), mean_items.size() * sizeof(MeanItem), cudaMemcpyHostToDevice, ctx->stream));
   BCU(cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope
@@ -377,9 +429,13 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   P.planes = b->d_planes;
   P.site_flags = b->d_flags;
   P.lntab = ctx->d_lntab;
+  P.ln_cap = (uint32_t)std::min<uint64_t>(ctx->ln_cap, 0xffffffffull);
   P.min_common = min_common;
   P.mode = mode;
-  P.status = b->d_status;
+  P.item_cnt = b->d_item_cnt;
+  P.item_off = b->d_item_off;
+  P.item_dense = b->d_item_dense;
+  P.n_generic = b->d_n_generic;
   P.header = b->d_header;
   P.records = b->d_records;
   P.counts = b->d_counts;
@@ -389,20 +445,59 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   P.unit_rec_off = b->d_unit_rec_off;
 
   CU(ctx, cudaMemsetAsync(b->d_header, 0, sizeof(Header), ctx->stream));
-  CU(ctx, cudaMemsetAsync(b->d_status, 0, std::max<size_t>(1, b->n_items) * sizeof(unsigned long long), ctx->stream));
   CU(ctx, cudaMemsetAsync(b->d_unit_rec_off, 0, ((size_t)b->n_units + 1) * sizeof(unsigned long long), ctx->stream));
+  CU(ctx, cudaMemsetAsync(b->d_item_dense, 0, std::max<size_t>(1, b->n_items), ctx->stream));
+  const uint32_t n_generic0 = b->n_items - b->n_fast;  // k_count adds the dense small units
+  CU(ctx, cudaMemcpyAsync(b->d_n_generic, &n_generic0, sizeof n_generic0, cudaMemcpyHostToDevice, ctx->stream));
   CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (b->n_sites) {
     // sites of pair-less units keep NaN; everything else is overwritten
     k_fill_nan<<<(unsigned)((b->n_sites + 255) / 256), 256, 0, ctx->stream>>>(b->d_site_mean, b->d_site_cnt, b->n_sites);
     ++ctx->launches;
   }
-  CU(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
   if (b->n_items) {
-    k_pairs<<<b->n_items, kThreads, 0, ctx->stream>>>(P);
+    // K0 + scan: every item's place in the ordered output
+    const unsigned cgrid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 8u);
+    k_count<<<cgrid, kThreads, 0, ctx->stream>>>(P);
+    ++ctx->launches;
+    CU(ctx, cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, b->scan_tmp_bytes, b->d_item_cnt, b->d_item_off,
+                                          (int)b->n_items + 1, ctx->stream));
+    ++ctx->launches;
+    CU(ctx, cudaMemcpyAsync(&b->d_header->n_records, b->d_item_off + b->n_items, sizeof(unsigned long long),
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(b->d_unit_rec_off + b->n_units, b->d_item_off + b->n_items, sizeof(unsigned long long),
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  CU(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+  if (b->n_fast) {
+    FastParams F;
+    F.items = b->d_fast_items;
+    F.n_items = b->n_fast;
+    F.planes = b->d_planes;
+    F.site_flags = b->d_flags;
+    F.lntab = ctx->d_lntab;
+    F.ln_cap = P.ln_cap;
+    F.min_common = min_common;
+    F.mode = mode;
+    F.item_off = b->d_item_off;
+    F.item_dense = b->d_item_dense;
+    F.records = b->d_records;
+    F.counts = b->d_counts;
+    F.site_mean = b->d_site_mean;
+    F.site_cnt = b->d_site_cnt;
+    F.unit_rec_off = b->d_unit_rec_off;
+    // persistent CTAs: a whole number of CTAs per SM, never more than there are items
+    const unsigned grid = (unsigned)std::min<uint64_t>(b->n_fast, (uint64_t)ctx->num_sms * ctx->pairs_ctas_per_sm);
+    k_pairs_fast<<<grid, kFastThreads, sizeof(FastSmem), ctx->stream>>>(F);
     ++ctx->launches;
   }
   CU(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+  if (b->n_items) {
+    // everything the small-unit kernel does not take; exits at once when there is nothing
+    const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
+    k_pairs_generic<<<grid, kThreads, 0, ctx->stream>>>(P);
+    ++ctx->launches;
+  }
   if (b->n_mean_items) {
     k_site_mean_dense<<<b->n_mean_items, 128, 0, ctx->stream>>>(b->d_units, b->d_mean_items, b->d_flags, b->d_dense,
                                                               b->d_site_mean, b->d_site_cnt);

@@ -18,6 +18,7 @@
 
 #include "../../include/lgmi.h"
 #include "lgmi_math.cuh"
+#include "lgmi_fast_kernel.cuh"
 
 namespace lgmi {
 
@@ -31,7 +32,7 @@ struct DevUnit {
   uint32_t first_item, n_items;
 };
 
-enum : uint32_t { ITEM_FIRST = 1u, ITEM_SINGLE = 2u };
+enum : uint32_t { ITEM_FIRST = 1u, ITEM_SINGLE = 2u, ITEM_FAST = 4u };
 
 struct Item {
   uint32_t unit;
@@ -42,8 +43,7 @@ struct Item {
 
 struct Header {
   unsigned long long n_records;
-  unsigned int ticket;
-  unsigned int pad;
+  unsigned long long pad;
 };
 
 struct RunParams {
@@ -54,9 +54,13 @@ struct RunParams {
   const uint32_t* planes;
   const uint8_t* site_flags;
   const lg_dd* lntab;
+  uint32_t ln_cap;
   int min_common;
   uint32_t mode;
-  unsigned long long* status;  // per item: look-back word
+  unsigned long long* item_cnt;        // per item: emitted pairs (k_count)
+  const unsigned long long* item_off;  // exclusive scan of item_cnt, n_items + 1 entries
+  uint8_t* item_dense;                 // k_count: fast-eligible item with > kOthCap "other" reads at a site
+  uint32_t* n_generic;                 // items k_pairs_generic has to process (host count + dense ones)
   Header* header;
   lgmi_pair_rec* records;
   uint32_t* counts;
@@ -131,172 +135,95 @@ __device__ __forceinline__ bool pair_table(const uint4* __restrict__ ri, const u
 }
 
 // ---------------------------------------------------------------------------
-// look-back status word: [63:62] flag, [61:0] value
-constexpr unsigned long long kFlagAgg = 1ull << 62;
-constexpr unsigned long long kFlagPrefix = 2ull << 62;
-constexpr unsigned long long kValMask = (1ull << 62) - 1ull;
-
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Exclusive prefix of `count` over items in ticket order.  Called by warp 0.
-__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long* status,
-                                                                 uint32_t item,
-                                                                 unsigned long long count) {
-  const uint32_t lane = threadIdx.x & 31u;
-  if (item == 0) {
-    if (lane == 0) st_status(status, kFlagPrefix | count);
-    return 0ull;
-  }
-  if (lane == 0) st_status(status + item, kFlagAgg | count);
-  unsigned long long excl = 0ull;
-  int64_t base = (int64_t)item - 1;
-  while (true) {
-    const int64_t idx = base - (int64_t)lane;
-    unsigned long long st = kFlagPrefix;  // virtual zero prefix before item 0
-    if (idx >= 0) {
-      st = ld_status(status + idx);
-      while ((st >> 62) == 0ull) {
-        __nanosleep(20);
-        st = ld_status(status + idx);
-      }
-    }
-    const uint32_t pm = __ballot_sync(0xffffffffu, (st >> 62) == 2ull);
-    const uint32_t first = pm ? (uint32_t)(__ffs((int)pm) - 1) : 32u;
-    unsigned long long v = (lane <= first) ? (st & kValMask) : 0ull;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    excl += v;
-    if (pm) break;
-    base -= 32;
-  }
-  if (lane == 0) st_status(status + item, kFlagPrefix | (excl + count));
-  return excl;
-}
-
-// ---------------------------------------------------------------------------
-// K1 + K2.  One CTA per work item, items taken in ticket order.
-__global__ void __launch_bounds__(kThreads) k_pairs(const RunParams P) {
-  __shared__ double s_mi[kPairsMax];     // MI of each pair of the item, NaN = dropped
-  __shared__ uint32_t s_ij[kPairsMax];   // (i << 16) | j
+// K1 + K2, generic path: up to 2048 consecutive pairs of any unit per work item,
+// one thread per pair, planes read through L1/L2.  Handles everything the
+// small-unit kernel (lgmi_fast_kernel.cuh) does not: units with more than 64
+// sites or 256 reads, pair-less units, and small units with dense third alleles.
+// The output offset of every item is known before the kernel starts (k_count +
+// exclusive scan), so no CTA ever waits on another.
+__global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
+  __shared__ double s_mi[kPairsMax];    // MI of each pair of the item, NaN = no MI
+  __shared__ uint32_t s_ij[kPairsMax];  // (i << 16) | j
   __shared__ uint32_t s_warp[kThreads / 32];
-  __shared__ uint32_t s_item;
-  __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_total;
-
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  if (tid == 0) s_item = atomicAdd(&P.header->ticket, 1u);
-  __syncthreads();
-  const uint32_t item_idx = s_item;
-  if (item_idx >= P.n_items) return;
-  const Item it = P.items[item_idx];
-  const DevUnit u = P.units[it.unit];
-  const uint32_t W4 = u.W >> 2;
-  const uint4* __restrict__ base = reinterpret_cast<const uint4*>(P.planes + u.plane_off);
-  const uint8_t* __restrict__ flags = P.site_flags + u.site_off;
   const LnGlobal ln{P.lntab};
   const bool het_only = (P.mode & LGMI_MODE_HET_ONLY) != 0u;
   const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
+  if (*P.n_generic == 0u) return;  // every item was a small unit taken by k_pairs_fast
 
-  // ---- phase 1: counts + MI for every candidate pair of the item
-  for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
-    uint32_t i, j;
-    lg_pair_ij(it.pair_begin + pl, u.S, i, j);
-    s_ij[pl] = (i << 16) | j;
-    double mi = lg_nan();
-    bool evaluate = true;
-    if (skip_nonhet) {
-      evaluate = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
-                 ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
-    }
-    if (evaluate) {
-      const uint4* ri = base + (size_t)i * 3u * W4;
-      const uint4* rj = base + (size_t)j * 3u * W4;
-      const uint32_t n_common = pair_common(ri, rj, W4);
-      if ((int)n_common >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
-        uint32_t T[9];
-        if (pair_table(ri, rj, W4, n_common, T))
-          mi = lg_mi_from_2x2(T[4], T[5], T[7], T[8], ln);
-        else
-          mi = lg_mi_from_table(T, ln);
+  for (uint32_t item_idx = blockIdx.x; item_idx < P.n_items; item_idx += gridDim.x) {
+    const Item it = P.items[item_idx];
+    if ((it.flags & ITEM_FAST) && !P.item_dense[item_idx]) continue;  // k_pairs_fast's
+    const DevUnit u = P.units[it.unit];
+    const uint32_t W4 = u.W >> 2;
+    const uint4* __restrict__ base = reinterpret_cast<const uint4*>(P.planes + u.plane_off);
+    const uint8_t* __restrict__ flags = P.site_flags + u.site_off;
+    __syncthreads();  // previous item fully consumed
+
+    // ---- counts + MI for every candidate pair of the item
+    for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
+      uint32_t i, j;
+      lg_pair_ij(it.pair_begin + pl, u.S, i, j);
+      s_ij[pl] = (i << 16) | j;
+      double mi = lg_nan();
+      bool evaluate = true;
+      if (skip_nonhet)
+        evaluate = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
+                   ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+      if (evaluate) {
+        const uint4* ri = base + (size_t)i * 3u * W4;
+        const uint4* rj = base + (size_t)j * 3u * W4;
+        const uint32_t n_common = pair_common(ri, rj, W4);
+        if ((int)n_common >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
+          uint32_t T[9];
+          if (pair_table(ri, rj, W4, n_common, T))
+            mi = lg_mi_from_2x2(T[4], T[5], T[7], T[8], ln);
+          else
+            mi = lg_mi_from_table(T, ln);
+        }
       }
+      s_mi[pl] = mi;
     }
-    s_mi[pl] = mi;
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- phase 2: how many pairs does this item emit?
-  uint32_t my_emit = 0;
-  for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
-    bool e = !isnan(s_mi[pl]);
-    if (e && het_only) {
-      const uint32_t ij = s_ij[pl];
-      e = ((flags[ij >> 16] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
-          ((flags[ij & 0xffffu] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+    // ---- ordered write: each warp owns a contiguous, 32-aligned range of pairs
+    const uint32_t per_warp = ((it.pair_cnt + kThreads - 1) / kThreads) * 32u;
+    const uint32_t p_begin = warp * per_warp;
+    const uint32_t p_end = min(p_begin + per_warp, it.pair_cnt);
+    auto emitted = [&](uint32_t pl, double& mi, uint32_t& ij) -> bool {
+      if (pl >= p_end) return false;
+      mi = s_mi[pl];
+      if (isnan(mi)) return false;
+      ij = s_ij[pl];
+      if (het_only)
+        return ((flags[ij >> 16] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
+               ((flags[ij & 0xffffu] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+      return true;
+    };
+    uint32_t mine = 0;
+    for (uint32_t pl = p_begin + lane; pl < p_begin + per_warp; pl += 32) {
+      double mi;
+      uint32_t ij;
+      mine += __popc(__ballot_sync(0xffffffffu, emitted(pl, mi, ij)));
     }
-    my_emit += e ? 1u : 0u;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) my_emit += __shfl_xor_sync(0xffffffffu, my_emit, o);
-  if (lane == 0) s_warp[warp] = my_emit;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t tot = (lane < kThreads / 32) ? s_warp[lane] : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    const unsigned long long excl = lookback_exclusive(P.status, item_idx, tot);
-    if (lane == 0) {
-      s_base = excl;
-      s_total = tot;
-      if (it.flags & ITEM_FIRST) P.unit_rec_off[it.unit] = excl;
-      if (item_idx == P.n_items - 1) {
-        P.header->n_records = excl + tot;
-        P.unit_rec_off[P.n_units] = excl + tot;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 3: ordered write of the emitted pairs
-  unsigned long long out = s_base;
-  if (s_total != 0u) {
-    for (uint32_t c0 = 0; c0 < it.pair_cnt; c0 += kThreads) {
-      const uint32_t pl = c0 + tid;
-      bool e = false;
+    if (lane == 0) s_warp[warp] = mine;
+    __syncthreads();
+    unsigned long long out = P.item_off[item_idx];
+    if (tid == 0 && (it.flags & ITEM_FIRST)) P.unit_rec_off[it.unit] = out;
+    for (uint32_t w = 0; w < warp; ++w) out += s_warp[w];
+    for (uint32_t pl = p_begin + lane; pl < p_begin + per_warp; pl += 32) {
       double mi = 0.0;
       uint32_t ij = 0;
-      if (pl < it.pair_cnt) {
-        mi = s_mi[pl];
-        ij = s_ij[pl];
-        e = !isnan(mi);
-        if (e && het_only)
-          e = ((flags[ij >> 16] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
-              ((flags[ij & 0xffffu] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
-      }
+      const bool e = emitted(pl, mi, ij);
       const uint32_t bal = __ballot_sync(0xffffffffu, e);
-      if (lane == 0) s_warp[warp] = __popc(bal);
-      __syncthreads();
-      uint32_t before = 0, chunk_total = 0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) {
-        const uint32_t c = s_warp[w];
-        before += (w < (int)warp) ? c : 0u;
-        chunk_total += c;
-      }
       if (e) {
-        const unsigned long long slot = out + before + __popc(bal & ((1u << lane) - 1u));
-        lgmi_pair_rec r;
-        r.unit = it.unit;
-        r.i = (uint16_t)(ij >> 16);
-        r.j = (uint16_t)(ij & 0xffffu);
-        r.mi = mi;
-        P.records[slot] = r;
+        const unsigned long long slot = out + __popc(bal & ((1u << lane) - 1u));
+        uint4 rec;  // {unit, i | j << 16, mi}
+        rec.x = it.unit;
+        rec.y = (ij >> 16) | (ij << 16);
+        rec.z = (uint32_t)__double2loint(mi);
+        rec.w = (uint32_t)__double2hiint(mi);
+        reinterpret_cast<uint4*>(P.records)[slot] = rec;
         if (P.mode & LGMI_MODE_EMIT_COUNTS) {
           const uint4* ri = base + (size_t)(ij >> 16) * 3u * W4;
           const uint4* rj = base + (size_t)(ij & 0xffffu) * 3u * W4;
@@ -306,31 +233,138 @@ __global__ void __launch_bounds__(kThreads) k_pairs(const RunParams P) {
           for (int k = 0; k < 9; ++k) P.counts[slot * 9ull + k] = T[k];
         }
       }
-      out += chunk_total;
-      __syncthreads();
+      out += __popc(bal);
+    }
+
+    // ---- per-site mean over the het-kept pairs (mutual_information.py:48-60)
+    if (it.flags & ITEM_SINGLE) {
+      for (uint32_t s = tid; s < u.S; s += kThreads) {
+        const bool s_het = (flags[s] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
+        lg_neumaier acc;
+        lg_neumaier_init(acc);
+        for (uint32_t t = 0; t < u.S; ++t) {
+          if (t == s) continue;
+          if (!s_het && (flags[t] & LGMI_SITE_TYPE_MASK) != LGMI_SITE_HET_SNP) continue;
+          const uint32_t p = (t < s) ? (uint32_t)lg_row_off(t, u.S) + (s - t - 1u)
+                                     : (uint32_t)lg_row_off(s, u.S) + (t - s - 1u);
+          const double v = s_mi[p];
+          if (!isnan(v)) lg_neumaier_add(acc, v);
+        }
+        P.site_mean[u.site_off + s] = lg_neumaier_mean(acc);
+        P.site_cnt[u.site_off + s] = (uint32_t)acc.n;
+      }
+    } else {
+      for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) P.dense[u.dense_off + it.pair_begin + pl] = s_mi[pl];
     }
   }
+}
 
-  // ---- phase 4: per-site mean over the het-kept pairs (mutual_information.py:48-60)
-  if (it.flags & ITEM_SINGLE) {
-    for (uint32_t s = tid; s < u.S; s += kThreads) {
-      const bool s_het = (flags[s] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
-      lg_neumaier acc;
-      lg_neumaier_init(acc);
-      for (uint32_t t = 0; t < u.S; ++t) {
-        if (t == s) continue;
-        if (!s_het && (flags[t] & LGMI_SITE_TYPE_MASK) != LGMI_SITE_HET_SNP) continue;
-        const uint32_t p = (t < s) ? (uint32_t)lg_row_off(t, u.S) + (s - t - 1u)
-                                   : (uint32_t)lg_row_off(s, u.S) + (t - s - 1u);
-        const double v = s_mi[p];
-        if (!isnan(v)) lg_neumaier_add(acc, v);
-      }
-      P.site_mean[u.site_off + s] = lg_neumaier_mean(acc);
-      P.site_cnt[u.site_off + s] = (uint32_t)acc.n;
+// ---------------------------------------------------------------------------
+// K0: number of pairs each item will emit -- |Ci & Cj| >= min_common (and the
+// het filter of the mode).  Its exclusive scan gives every item its place in
+// the ordered output, so k_pairs needs no inter-CTA communication.
+constexpr int kCountStride = 12;  // words per staged C row (48 B: conflict-free LDS.128)
+
+template <int NW>
+__device__ __forceinline__ uint32_t count_fast_item(const uint32_t* __restrict__ s_c, const uint8_t* __restrict__ s_flags,
+                                                    uint32_t S, int min_common, bool het_only, bool skip_nonhet) {
+  const uint32_t n_pairs = S * (S - 1u) / 2u;
+  uint32_t mine = 0;
+  // walk the triangle row by row: thread -> (i, k), advanced by blockDim
+  uint32_t i = 0, k = threadIdx.x;
+  uint32_t len = S - 1u;
+  for (uint32_t p = threadIdx.x; p < n_pairs; p += kThreads) {
+    while (k >= len) {
+      k -= len;
+      ++i;
+      --len;
     }
-  } else {
-    for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads)
-      P.dense[u.dense_off + it.pair_begin + pl] = s_mi[pl];
+    const uint32_t j = i + 1u + k;
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int q = 0; q < (NW + 3) / 4; ++q) {
+      const uint4 x = *reinterpret_cast<const uint4*>(s_c + i * kCountStride + 4 * q);
+      const uint4 y = *reinterpret_cast<const uint4*>(s_c + j * kCountStride + 4 * q);
+      a[4 * q] = x.x; a[4 * q + 1] = x.y; a[4 * q + 2] = x.z; a[4 * q + 3] = x.w;
+      b[4 * q] = y.x; b[4 * q + 1] = y.y; b[4 * q + 2] = y.z; b[4 * q + 3] = y.w;
+    }
+    const uint32_t n = and_popc<NW>(a, b);
+    const bool het = ((s_flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
+                     ((s_flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+    const bool emit = ((int)n >= min_common) && (het || !(het_only || skip_nonhet));
+    mine += emit ? 1u : 0u;
+    k += kThreads;
+  }
+  return mine;
+}
+
+__global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
+  __shared__ __align__(16) uint32_t s_c[kFastMaxS * kCountStride];
+  __shared__ uint8_t s_flags[kFastMaxS];
+  __shared__ uint32_t s_noth[kFastMaxS];
+  __shared__ uint32_t s_warp[kThreads / 32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const bool het_only = (P.mode & LGMI_MODE_HET_ONLY) != 0u;
+  const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
+  for (uint32_t item_idx = blockIdx.x; item_idx < P.n_items; item_idx += gridDim.x) {
+    const Item it = P.items[item_idx];
+    const DevUnit u = P.units[it.unit];
+    const uint8_t* __restrict__ flags = P.site_flags + u.site_off;
+    uint32_t mine = 0;
+    __syncthreads();
+    if (it.flags & ITEM_FAST) {
+      const uint32_t W = u.W;
+      const uint32_t* __restrict__ planes = P.planes + u.plane_off;
+      if (tid < (uint32_t)kFastMaxS) s_noth[tid] = 0u;
+      __syncthreads();
+      for (uint32_t e = tid; e < u.S * 8u; e += kThreads) {
+        const uint32_t s = e >> 3, k = e & 7u;
+        uint32_t C = 0u;
+        if (k < W) {
+          const uint32_t* row = planes + (size_t)s * 3u * W;
+          C = __ldg(row + 2u * W + k);
+          const uint32_t n_other = __popc(C & ~(__ldg(row + k) | __ldg(row + W + k)));
+          if (n_other) atomicAdd(&s_noth[s], n_other);
+        }
+        s_c[s * kCountStride + k] = C;
+      }
+      if (tid < u.S) s_flags[tid] = flags[tid];
+      __syncthreads();
+      {
+        const bool over = tid < u.S && s_noth[tid] > (uint32_t)kOthCap;
+        if (__syncthreads_or(over) && tid == 0) {
+          P.item_dense[item_idx] = 1;
+          atomicAdd(P.n_generic, 1u);
+        }
+      }
+      const uint32_t nw = (u.R + 31u) >> 5;
+      if (nw <= 2u) mine = count_fast_item<2>(s_c, s_flags, u.S, P.min_common, het_only, skip_nonhet);
+      else if (nw <= 4u) mine = count_fast_item<4>(s_c, s_flags, u.S, P.min_common, het_only, skip_nonhet);
+      else if (nw <= 7u) mine = count_fast_item<7>(s_c, s_flags, u.S, P.min_common, het_only, skip_nonhet);
+      else mine = count_fast_item<8>(s_c, s_flags, u.S, P.min_common, het_only, skip_nonhet);
+    } else {
+      const uint32_t W4 = u.W >> 2;
+      const uint4* __restrict__ base = reinterpret_cast<const uint4*>(P.planes + u.plane_off);
+      for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
+        uint32_t i, j;
+        lg_pair_ij(it.pair_begin + pl, u.S, i, j);
+        const bool het = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
+                         ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+        if (!het && (het_only || skip_nonhet)) continue;
+        const uint32_t n = pair_common(base + (size_t)i * 3u * W4, base + (size_t)j * 3u * W4, W4);
+        mine += ((int)n >= P.min_common) ? 1u : 0u;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) s_warp[warp] = mine;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t tot = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) tot += s_warp[w];
+      P.item_cnt[item_idx] = tot;
+    }
   }
 }
 

@@ -115,6 +115,35 @@ def math_host(liblgmi_path):
 
 
 @pytest.fixture(scope="session")
+def fast_host(liblgmi_path):
+    """Host build of the pure device functions of csrc/lgmi_fast.cuh."""
+    out = os.path.join(ROOT, "tests", "csrc", "libfast_host.so")
+    srcs = [os.path.join(ROOT, "tests", "csrc", "fast_host.cpp"),
+            os.path.join(ROOT, "l-giremi_b200", "csrc", "lgmi_fast.cuh"),
+            os.path.join(ROOT, "l-giremi_b200", "csrc", "lgmi_math.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-std=c++17", "-Wno-attributes",
+                        "-I/usr/local/cuda/include", "-o", out, srcs[0]], check=True)
+    lib = ctypes.CDLL(out)
+    vp, u32 = ctypes.c_void_p, ctypes.c_uint32
+    lib.f_mi_2x2.restype = ctypes.c_double
+    lib.f_mi_2x2.argtypes = [u32] * 4 + [vp, u32]
+    lib.f_mi_3x3.restype = ctypes.c_double
+    lib.f_mi_3x3.argtypes = [vp, vp, u32]
+    lib.f_mi_2x2_many.restype = None
+    lib.f_mi_2x2_many.argtypes = [vp, ctypes.c_int64, vp, u32, vp]
+    lib.f_mi_3x3_many.restype = None
+    lib.f_mi_3x3_many.argtypes = [vp, ctypes.c_int64, vp, u32, vp]
+    lib.f_markstein_mismatches.restype = ctypes.c_int64
+    lib.f_markstein_mismatches.argtypes = [u32]
+    lib.f_and_popc.restype = u32
+    lib.f_and_popc.argtypes = [ctypes.c_int, vp, vp]
+    lib.f_pair_counts.restype = ctypes.c_uint64
+    lib.f_pair_counts.argtypes = [ctypes.c_int, vp, vp]
+    return lib
+
+
+@pytest.fixture(scope="session")
 def lntab(math_host):
     n = 1 << 17
     tab = np.empty(2 * n, dtype=np.float64)

@@ -1,0 +1,81 @@
+// Host build of the pure device functions of l-giremi_b200/csrc/lgmi_fast.cuh
+// (carry-save popcount, branch-free 2x2 / 3x3 MI epilogues) for the CPU unit
+// tests.  The CUDA rounding intrinsics are shimmed with the IEEE operations
+// they denote (compiled with -ffp-contract=off).  Test infrastructure only.
+#include <cmath>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline double __longlong_as_double(long long v) { double d; __builtin_memcpy(&d, &v, 8); return d; }
+
+#include "../../l-giremi_b200/csrc/lgmi_fast.cuh"
+
+using namespace lgmi;
+
+static std::vector<FastTabEntry> make_tab(const double* lntab, uint32_t n) {
+  std::vector<FastTabEntry> t(n);
+  for (uint32_t k = 0; k < n; ++k) {
+    t[k].ln_hi = lntab[2 * k];
+    t[k].ln_lo = lntab[2 * k + 1];
+    t[k].dk = (double)k;
+    t[k].inv = k ? 1.0 / (double)k : 0.0;
+  }
+  return t;
+}
+
+extern "C" {
+double f_mi_2x2(uint32_t mm, uint32_t mM, uint32_t Mm, uint32_t MM, const double* lntab, uint32_t n) {
+  auto t = make_tab(lntab, n);
+  return mi_2x2(t.data(), mm, mM, Mm, MM);
+}
+double f_mi_3x3(const uint32_t* T, const double* lntab, uint32_t n) {
+  auto t = make_tab(lntab, n);
+  return mi_3x3(t.data(), T);
+}
+// batch versions (one table build)
+void f_mi_2x2_many(const uint32_t* cells, int64_t m, const double* lntab, uint32_t n, double* out) {
+  auto t = make_tab(lntab, n);
+  for (int64_t k = 0; k < m; ++k) out[k] = mi_2x2(t.data(), cells[4 * k], cells[4 * k + 1], cells[4 * k + 2], cells[4 * k + 3]);
+}
+void f_mi_3x3_many(const uint32_t* T, int64_t m, const double* lntab, uint32_t n, double* out) {
+  auto t = make_tab(lntab, n);
+  for (int64_t k = 0; k < m; ++k) out[k] = mi_3x3(t.data(), T + 9 * k);
+}
+// number of (n, N) with 0 <= n <= N <= n_max where the Markstein quotient differs from n / N
+int64_t f_markstein_mismatches(uint32_t n_max) {
+  int64_t bad = 0;
+  for (uint32_t N = 1; N <= n_max; ++N) {
+    const double dN = (double)N, y = 1.0 / dN;
+    for (uint32_t n = 0; n <= N; ++n) {
+      const double dn = (double)n;
+      const double q0 = dn * y;
+      const double r = std::fma(-q0, dN, dn);
+      const double q = std::fma(r, y, q0);
+      bad += (q != dn / dN);
+    }
+  }
+  return bad;
+}
+uint32_t f_and_popc(int nw, const uint32_t* x, const uint32_t* y) {
+  switch (nw) {
+    case 2: return and_popc<2>(x, y);
+    case 4: return and_popc<4>(x, y);
+    case 7: return and_popc<7>(x, y);
+    default: return and_popc<8>(x, y);
+  }
+}
+uint64_t f_pair_counts(int nw, const uint32_t* ri, const uint32_t* rj) {
+  switch (nw) {
+    case 2: return pair_counts<2>(ri, rj);
+    case 4: return pair_counts<4>(ri, rj);
+    case 7: return pair_counts<7>(ri, rj);
+    default: return pair_counts<8>(ri, rj);
+  }
+}
+}

@@ -1,0 +1,100 @@
+"""The small-unit ("fast") path's device functions (csrc/lgmi_fast.cuh), built
+for the host: they must give the SAME BITS as the straightforward arithmetic in
+csrc/lgmi_math.cuh (which test_math_host.py pins to sklearn's golden values)."""
+import numpy as np
+
+from conftest import unhex
+
+NTAB = 4096
+
+
+def u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def test_markstein_quotient_is_the_rounded_quotient(fast_host):
+    """q0 = n*RN(1/N); r = fma(-q0,N,n); q = fma(r,RN(1/N),q0) == RN(n/N) for all 0<=n<=N<=3000."""
+    assert fast_host.f_markstein_mismatches(3000) == 0
+
+
+def test_carry_save_popcount(fast_host):
+    rng = np.random.default_rng(1)
+    for nw in (2, 4, 7, 8):
+        for _ in range(3000):
+            x = rng.integers(0, 1 << 32, 8, dtype=np.uint64).astype(np.uint32)
+            y = rng.integers(0, 1 << 32, 8, dtype=np.uint64).astype(np.uint32)
+            if rng.random() < 0.2:
+                x[:] = 0xffffffff
+                y[:] = 0xffffffff
+            want = sum(bin(int(a) & int(b)).count("1") for a, b in zip(x[:nw], y[:nw]))
+            assert fast_host.f_and_popc(nw, x.ctypes.data, y.ctypes.data) == want
+
+
+def test_pair_counts_packing(fast_host):
+    rng = np.random.default_rng(2)
+    for nw in (2, 4, 7, 8):
+        for _ in range(500):
+            ri = np.zeros(20, np.uint32)
+            rj = np.zeros(20, np.uint32)
+            for row in (ri, rj):
+                P = rng.integers(0, 1 << 32, 8, dtype=np.uint64).astype(np.uint32)
+                M = P & rng.integers(0, 1 << 32, 8, dtype=np.uint64).astype(np.uint32)
+                P[nw:] = 0
+                M[nw:] = 0
+                row[:8], row[8:16] = M, P
+            v = fast_host.f_pair_counts(nw, ri.ctypes.data, rj.ctypes.data)
+            pc = lambda a, b: int(sum(bin(int(x) & int(y)).count("1") for x, y in zip(a, b)))
+            want = (pc(ri[8:16], rj[8:16]), pc(ri[:8], rj[8:16]), pc(ri[8:16], rj[:8]), pc(ri[:8], rj[:8]))
+            got = (v & 0xffff, (v >> 16) & 0xffff, (v >> 32) & 0xffff, v >> 48)
+            assert got == want
+
+
+def test_fast_2x2_same_bits_as_reference_arithmetic(fast_host, math_host, lntab):
+    rng = np.random.default_rng(3)
+    cells = []
+    for _ in range(40000):
+        c = rng.integers(0, int(rng.choice([2, 4, 12, 60, 250])), 4)
+        c[rng.random(4) < rng.choice([0.0, 0.3])] = 0
+        if 0 < c.sum() < NTAB:
+            cells.append(c)
+    cells = u32(np.array(cells))
+    out = np.empty(len(cells))
+    fast_host.f_mi_2x2_many(cells.ctypes.data, len(cells), lntab.ctypes.data, NTAB, out.ctypes.data)
+    for c, got in zip(cells.tolist(), out.tolist()):
+        want = math_host.t_mi_from_2x2(c[0], c[1], c[2], c[3], lntab.ctypes.data)
+        assert got == want, c
+
+
+def test_fast_3x3_same_bits_as_reference_arithmetic(fast_host, math_host, lntab):
+    rng = np.random.default_rng(4)
+    tabs = []
+    for _ in range(40000):
+        t = rng.integers(0, int(rng.choice([2, 3, 10, 40, 200])), 9)
+        if rng.random() < 0.6:                       # "other" cells are small in practice
+            t[[0, 1, 2, 3, 6]] = rng.integers(0, 3, 5)
+        t[rng.random(9) < rng.choice([0.0, 0.3, 0.6])] = 0
+        if 0 < t.sum() < NTAB:
+            tabs.append(t)
+    tabs = u32(np.array(tabs))
+    out = np.empty(len(tabs))
+    fast_host.f_mi_3x3_many(tabs.ctypes.data, len(tabs), lntab.ctypes.data, NTAB, out.ctypes.data)
+    n8 = 0
+    for t, got in zip(tabs, out.tolist()):
+        want = math_host.t_mi_from_table(t.ctypes.data, lntab.ctypes.data)
+        assert got == want, t
+        n8 += int((t != 0).sum() >= 8)
+    assert n8 > 500                                  # numpy's pairwise branch was exercised
+
+
+def test_fast_paths_match_sklearn_golden(fast_host, lntab, golden):
+    n = 0
+    for case in golden("tables.json"):
+        t = u32(case["table"])
+        if int(t.sum()) >= NTAB:
+            continue
+        assert fast_host.f_mi_3x3(t.ctypes.data, lntab.ctypes.data, NTAB) == unhex(case["mi"]), case
+        if not t[[0, 1, 2, 3, 6]].any():
+            assert fast_host.f_mi_2x2(int(t[4]), int(t[5]), int(t[7]), int(t[8]), lntab.ctypes.data, NTAB) == \
+                unhex(case["mi"]), case
+        n += 1
+    assert n > 1500
