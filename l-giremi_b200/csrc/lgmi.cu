@@ -42,6 +42,7 @@ struct lgmi_ctx {
   // scratch for ecdf / csr
   void* d_scratch = nullptr;
   size_t scratch_cap = 0;
+  uint16_t* d_ij_tab = nullptr;  // triangular pair tables for S <= 64 (lg_ij_tab_off)
   // persistent launch shape of k_pairs
   int num_sms = 0;
   int pairs_ctas_per_sm = 0;
@@ -181,6 +182,21 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
     lgmi_destroy(ctx);
     return rc;
   }
+  {
+    std::vector<uint16_t> tab(kIjTabEntries);
+    for (uint32_t S = 2; S <= (uint32_t)kFastMaxS; ++S) {
+      uint32_t p = lg_ij_tab_off(S);
+      for (uint32_t i = 0; i + 1 < S; ++i)
+        for (uint32_t j = i + 1; j < S; ++j) tab[p++] = (uint16_t)(i * 64u + j);
+    }
+    if (cudaMalloc(&ctx->d_ij_tab, tab.size() * sizeof(uint16_t)) != cudaSuccess ||
+        cudaMemcpy(ctx->d_ij_tab, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+      int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: pair table upload failed (%s)",
+                    cudaGetErrorString(cudaGetLastError()));
+      lgmi_destroy(ctx);
+      return rc;
+    }
+  }
   *out = ctx;
   return LGMI_OK;
 }
@@ -192,6 +208,7 @@ extern "C" void lgmi_destroy(lgmi_t* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->d_lntab) cudaFree(ctx->d_lntab);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_ij_tab) cudaFree(ctx->d_ij_tab);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -477,6 +494,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     F.site_flags = b->d_flags;
     F.lntab = ctx->d_lntab;
     F.ln_cap = P.ln_cap;
+    F.ij_tab = ctx->d_ij_tab;
     F.min_common = min_common;
     F.mode = mode;
     F.item_off = b->d_item_off;

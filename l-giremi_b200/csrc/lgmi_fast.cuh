@@ -42,9 +42,13 @@ constexpr int kFastChunks = kFastMaxPairs / 32;
 constexpr int kRowStride = 28;       // words per landed site row: M[8] | P[8] | C[8] | pad[4]
 constexpr int kOthCap = 7;           // "other" reads kept per site (3-bit cells); more -> generic kernel
 
-// E[k] = {ln_hi(k), (double)k, ln_lo(k), RN(1/k)}, E[0] = 0
-struct __align__(16) FastTabEntry {
-  double ln_hi, dk, ln_lo, inv;
+// ln k as hi + lo (hi = RN(ln k)); entry 0 is {0, 0}
+struct __align__(16) FastLn {
+  double hi, lo;
+};
+struct FastTab {
+  FastLn ln[kFastMaxR + 1];   // 4112 B
+  double inv[kFastMaxR + 1];  // RN(1/k), inv[0] = 0
 };
 
 // one work item of the fast kernel == one whole unit
@@ -59,11 +63,9 @@ struct __align__(16) FastItem {
 };
 
 struct FastSmem {
-  FastTabEntry tab[kFastMaxR + 1];                       // 8224 B
+  FastTab tab;                                           // 6176 B
   uint32_t rows[2][kFastMaxS * kRowStride];              // 14336 B, double-buffered
   unsigned long long val[kFastMaxPairs];                 // 16 KB: packed counts, then MI bits
-  uint16_t oth[kFastMaxPairs];                           // 4 KB: five 3-bit "other" cells per pair
-  uint16_t ij[kFastMaxPairs];                            // 4 KB: i*64+j
   uint16_t list[kFastMaxPairs];                          // 4 KB: pairs with a 2x2 table from the front,
                                                          //       pairs with "other" cells from the back
   uint32_t emit_mask[kFastChunks];                       // ballot of each 32-pair chunk
@@ -71,9 +73,10 @@ struct FastSmem {
   uint16_t oth_list[kFastMaxS * 8];                      // 1 KB
   uint32_t n_oth[kFastMaxS];
   uint8_t flags[kFastMaxS];
-  uint8_t oth_sites[kFastMaxS];
+  uint8_t het_list[kFastMaxS];                           // het sites ascending, then ...
+  uint8_t nonhet_list[kFastMaxS];                        // ... the other sites ascending
   unsigned long long het_mask;
-  uint32_t n_list2, n_list3, n_oth_sites, total;
+  uint32_t n_list2, n_list3, next_chunk, total;
 };
 
 __device__ __forceinline__ double mi_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -108,8 +111,13 @@ __device__ __forceinline__ uint32_t and_popc(const uint32_t* __restrict__ x, con
   }
 }
 
-// the four counts of a pair: |Pi&Pj|, |Mi&Pj|, |Pi&Mj|, |Mi&Mj|, packed 4 x u16.
-// ri / rj point at landed rows: M at word 0, P at word 8.
+// packed per-pair value between the counts phase and the MI phase (R <= 256, so a
+// count needs 9 bits):  bits 0-8 |Pi&Pj|, 9-17 |Mi&Pj|, 18-26 |Pi&Mj|, 27-35 |Mi&Mj|,
+// 36-50 the five 3-bit "other" cells T[0][0], T[0][1], T[0][2], T[1][0], T[2][0].
+// A candidate without MI holds the NaN pattern 0x7ff8000000000000 instead.
+constexpr unsigned long long kNoMi = 0x7ff8000000000000ull;
+
+// the four counts of a pair.  ri / rj point at landed rows: M at word 0, P at word 8.
 template <int NW>
 __device__ __forceinline__ unsigned long long pair_counts(const uint32_t* __restrict__ ri,
                                                           const uint32_t* __restrict__ rj) {
@@ -129,7 +137,7 @@ __device__ __forceinline__ unsigned long long pair_counts(const uint32_t* __rest
   const uint32_t nMP = and_popc<NW>(Mi, Pj);
   const uint32_t nPM = and_popc<NW>(Pi, Mj);
   const uint32_t nMM = and_popc<NW>(Mi, Mj);
-  return (unsigned long long)(nPP | (nMP << 16)) | ((unsigned long long)(nPM | (nMM << 16)) << 32);
+  return (unsigned long long)(nPP | (nMP << 9) | (nPM << 18)) | ((unsigned long long)nMM << 27);
 }
 
 // ---------------------------------------------------------------------------
@@ -138,13 +146,18 @@ struct CellCtx {
   double dN, invN, lnN;
 };
 
-// RN(ln(a*b)) from the table rows of a and b (lg_ln_product)
-__device__ __forceinline__ double ln_prod(const FastTabEntry& a, const FastTabEntry& b) {
-  const double s = __dadd_rn(a.ln_hi, b.ln_hi);
-  const double bb = __dsub_rn(s, a.ln_hi);
-  double e = __dadd_rn(__dsub_rn(a.ln_hi, __dsub_rn(s, bb)), __dsub_rn(b.ln_hi, bb));
-  e = __dadd_rn(e, __dadd_rn(a.ln_lo, b.ln_lo));
+// RN(ln(a*b)) from the double-double logs of a and b (lg_ln_product)
+__device__ __forceinline__ double ln_prod(const FastLn& a, const FastLn& b) {
+  const double s = __dadd_rn(a.hi, b.hi);
+  const double bb = __dsub_rn(s, a.hi);
+  double e = __dadd_rn(__dsub_rn(a.hi, __dsub_rn(s, bb)), __dsub_rn(b.hi, bb));
+  e = __dadd_rn(e, __dadd_rn(a.lo, b.lo));
   return __dadd_rn(s, e);
+}
+
+// (double)n for 0 <= n < 2^32 without a conversion instruction: 2^52 + n is exact
+__device__ __forceinline__ double u32_to_double(uint32_t n) {
+  return __dsub_rn(__hiloint2double(0x43300000, (int)n), 4503599627370496.0);
 }
 
 // one cell's term; n == 0 yields exactly 0.0
@@ -157,29 +170,27 @@ __device__ __forceinline__ double cell_term(double ln_n, double dn, const CellCt
   return (fabs(t) < LG_EPS) ? 0.0 : t;
 }
 
-__device__ __forceinline__ double cell_of(const FastTabEntry* __restrict__ tab, uint32_t n, const CellCtx& cx,
-                                          const FastTabEntry& er, const FastTabEntry& ec) {
-  const double2 e = *reinterpret_cast<const double2*>(&tab[n]);  // {ln_hi(n), (double)n}
-  return cell_term(e.x, e.y, cx, ln_prod(er, ec));
+__device__ __forceinline__ double cell_of(const FastTab& tab, uint32_t n, const CellCtx& cx, const FastLn& er,
+                                          const FastLn& ec) {
+  return cell_term(tab.ln[n].hi, u32_to_double(n), cx, ln_prod(er, ec));
 }
 
 // 2x2 table (no "other" label among the common reads).  Cell order mm, mM, Mm, MM.
-__device__ __forceinline__ double mi_2x2(const FastTabEntry* __restrict__ tab, uint32_t n_mm, uint32_t n_mM,
-                                         uint32_t n_Mm, uint32_t n_MM) {
+__device__ __forceinline__ double mi_2x2(const FastTab& tab, uint32_t n_mm, uint32_t n_mM, uint32_t n_Mm,
+                                         uint32_t n_MM) {
   const uint32_t r_m = n_mm + n_mM, r_M = n_Mm + n_MM;
   const uint32_t c_m = n_mm + n_Mm, c_M = n_mM + n_MM;
   const uint32_t N = r_m + r_M;
-  const FastTabEntry eN = tab[N];
-  const CellCtx cx{eN.dk, eN.inv, eN.ln_hi};
-  const FastTabEntry ecm = tab[c_m], ecM = tab[c_M];
+  const CellCtx cx{u32_to_double(N), tab.inv[N], tab.ln[N].hi};
+  const FastLn ecm = tab.ln[c_m], ecM = tab.ln[c_M];
   double s = 0.0;
   {
-    const FastTabEntry erm = tab[r_m];
+    const FastLn erm = tab.ln[r_m];
     s = __dadd_rn(s, cell_of(tab, n_mm, cx, erm, ecm));
     s = __dadd_rn(s, cell_of(tab, n_mM, cx, erm, ecM));
   }
   {
-    const FastTabEntry erM = tab[r_M];
+    const FastLn erM = tab.ln[r_M];
     s = __dadd_rn(s, cell_of(tab, n_Mm, cx, erM, ecm));
     s = __dadd_rn(s, cell_of(tab, n_MM, cx, erM, ecM));
   }
@@ -188,7 +199,7 @@ __device__ __forceinline__ double mi_2x2(const FastTabEntry* __restrict__ tab, u
 }
 
 // 3x3 table T[a*3+b] (label order other, minor, major)
-__device__ __forceinline__ double mi_3x3(const FastTabEntry* __restrict__ tab, const uint32_t T[9]) {
+__device__ __forceinline__ double mi_3x3(const FastTab& tab, const uint32_t T[9]) {
   uint32_t r[3], c[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) r[a] = T[3 * a] + T[3 * a + 1] + T[3 * a + 2];
@@ -200,26 +211,28 @@ __device__ __forceinline__ double mi_3x3(const FastTabEntry* __restrict__ tab, c
   int nnz = 0;
 #pragma unroll
   for (int k = 0; k < 9; ++k) nnz += (T[k] != 0u);
-  const FastTabEntry eN = tab[N];
-  const CellCtx cx{eN.dk, eN.inv, eN.ln_hi};
+  const CellCtx cx{u32_to_double(N), tab.inv[N], tab.ln[N].hi};
+  FastLn ec[3];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) ec[b] = tab.ln[c[b]];
   double s;
   if (nnz < 8) {  // ndarray.sum(): plain loop below 8 elements; absent cells add an exact 0.0
     s = 0.0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const FastTabEntry er = tab[r[a]];
+      const FastLn er = tab.ln[r[a]];
 #pragma unroll
-      for (int b = 0; b < 3; ++b) s = __dadd_rn(s, cell_of(tab, T[3 * a + b], cx, er, tab[c[b]]));
+      for (int b = 0; b < 3; ++b) s = __dadd_rn(s, cell_of(tab, T[3 * a + b], cx, er, ec[b]));
     }
   } else {        // numpy pairwise_sum over the 8 or 9 present cells (z = the absent one, if any); rare
     double t[9];
     int z = 9;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const FastTabEntry er = tab[r[a]];
+      const FastLn er = tab.ln[r[a]];
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
-        t[3 * a + b] = cell_of(tab, T[3 * a + b], cx, er, tab[c[b]]);
+        t[3 * a + b] = cell_of(tab, T[3 * a + b], cx, er, ec[b]);
         if (T[3 * a + b] == 0u) z = 3 * a + b;
       }
     }
@@ -232,5 +245,10 @@ __device__ __forceinline__ double mi_3x3(const FastTabEntry* __restrict__ tab, c
   }
   return (nrow <= 1 || ncol <= 1 || !(s > 0.0)) ? 0.0 : s;
 }
+
+// triangular pair tables: for every S in [2, 64] the (i, j) of its S(S-1)/2 pairs in
+// lexicographic order, i * 64 + j as u16; table of S starts at C(S, 3) entries.
+constexpr uint32_t kIjTabEntries = 64u * 63u * 62u / 6u + 64u * 63u / 2u;  // C(64,3) + C(64,2)
+LG_HD uint32_t lg_ij_tab_off(uint32_t S) { return S * (S - 1u) * (S - 2u) / 6u; }
 
 }  // namespace lgmi

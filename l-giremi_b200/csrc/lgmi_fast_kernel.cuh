@@ -16,6 +16,7 @@ struct FastParams {
   const uint8_t* site_flags;
   const lg_dd* lntab;
   uint32_t ln_cap;
+  const uint16_t* ij_tab;              // triangular pair tables, see lg_ij_tab_off
   int min_common;
   uint32_t mode;
   const unsigned long long* item_off;  // exclusive scan of the per-item emit counts
@@ -86,78 +87,73 @@ __device__ __forceinline__ void fast_land(FastSmem& sm, uint32_t* __restrict__ r
   }
 }
 
-// list of the sites that have "other" reads (any order)
-__device__ __forceinline__ void fast_other_sites(FastSmem& sm, uint32_t S) {
-  const uint32_t tid = threadIdx.x;
-  if (tid < S && sm.n_oth[tid] != 0u) sm.oth_sites[atomicAdd(&sm.n_oth_sites, 1u)] = (uint8_t)tid;
-}
-
-// the cells that involve an "other" label, from the sparse lists.
-// field f of sm.oth[p] (3 bits each): 0 T[0][0], 1 T[0][1], 2 T[0][2], 3 T[1][0], 4 T[2][0]
-__device__ __forceinline__ void fast_fixup(FastSmem& sm, const uint32_t* __restrict__ rows, uint32_t S) {
-  const uint32_t n_items = sm.n_oth_sites * 64u;
-  for (uint32_t e = threadIdx.x; e < n_items; e += kFastThreads) {
-    const uint32_t a = sm.oth_sites[e >> 6], b = e & 63u;
-    if (b >= S || a == b) continue;
-    const uint32_t na = sm.n_oth[a];
-    uint32_t add = 0u;
-    for (uint32_t q = 0; q < na; ++q) {
-      const uint32_t r = sm.oth_list[a * 8u + q];
-      const uint32_t w = r >> 5, bit = r & 31u;
-      if ((rows[b * kRowStride + 8u + w] >> bit) & 1u) {
-        const uint32_t label_b = 1u + ((rows[b * kRowStride + w] >> bit) & 1u);  // 1 minor, 2 major
-        add += 1u << (3u * ((a < b) ? label_b : (2u + label_b)));
-      } else if (a < b && ((rows[b * kRowStride + 16u + w] >> bit) & 1u)) {
-        add += 1u;  // "other" at both sites: counted once, from the lower site
-      }
-    }
-    if (add) {
-      const uint32_t i = min(a, b), j = max(a, b);
-      const uint32_t p = ((i * (2u * S - i - 1u)) >> 1) + (j - i - 1u);
-      // 16-bit cells packed two per word: add into the right half
-      atomicAdd(reinterpret_cast<uint32_t*>(sm.oth) + (p >> 1), add << ((p & 1u) * 16u));
-    }
+// ordered lists of the het sites and of the other sites (for the mean phase)
+__device__ __forceinline__ void fast_site_lists(FastSmem& sm, uint32_t S) {
+  const uint32_t s = threadIdx.x;
+  if (s < S) {
+    const unsigned long long het = sm.het_mask;
+    const uint32_t rank = __popcll(het & ((1ull << s) - 1ull));
+    if ((het >> s) & 1ull) sm.het_list[rank] = (uint8_t)s;
+    else sm.nonhet_list[s - rank] = (uint8_t)s;
   }
 }
 
-// the four AND+popcount sets of every pair, min-common filter, emit masks, lists
+// the table cells that involve an "other" label of pair (i, j), from the sparse per-site
+// lists: five 3-bit cells T[0][0], T[0][1], T[0][2], T[1][0], T[2][0]
+__device__ __forceinline__ uint32_t other_cells(const FastSmem& sm, const uint32_t* __restrict__ rows, uint32_t i,
+                                                uint32_t j, uint32_t ni, uint32_t nj) {
+  uint32_t o = 0u;
+  const uint32_t* ri = rows + i * kRowStride;
+  const uint32_t* rj = rows + j * kRowStride;
+  for (uint32_t q = 0; q < ni; ++q) {  // "other" at i: row 0 of the table
+    const uint32_t r = sm.oth_list[i * 8u + q];
+    const uint32_t w = r >> 5, bit = r & 31u;
+    if ((rj[8u + w] >> bit) & 1u) o += 8u << (3u * ((rj[w] >> bit) & 1u));  // j minor -> cell 1, major -> cell 2
+    else o += (rj[16u + w] >> bit) & 1u;                                    // "other" at both
+  }
+  for (uint32_t q = 0; q < nj; ++q) {  // "other" at j, not at i: column 0
+    const uint32_t r = sm.oth_list[j * 8u + q];
+    const uint32_t w = r >> 5, bit = r & 31u;
+    if ((ri[8u + w] >> bit) & 1u) o += 512u << (3u * ((ri[w] >> bit) & 1u));  // i minor -> cell 3, major -> cell 4
+  }
+  return o;
+}
+
+// the four AND+popcount sets of every pair, "other" cells, min-common filter, emit masks, lists
 template <int NW>
 __device__ __forceinline__ void fast_counts(const FastParams& P, FastSmem& sm, const uint32_t* __restrict__ rows,
-                                            uint32_t S, uint32_t n_pairs) {
+                                            const uint16_t* __restrict__ ijt, uint32_t n_pairs) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const bool het_only = (P.mode & LGMI_MODE_HET_ONLY) != 0u;
   const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
   const uint32_t n_slots = (n_pairs + 31u) & ~31u;
   const uint32_t lt = (1u << lane) - 1u;
-  uint32_t i = 0, k = tid, len = S - 1u;  // lexicographic walk: p -> (i, j = i + 1 + k)
   for (uint32_t p = tid; p < n_slots; p += kFastThreads) {
-    uint32_t cls = 0u;  // 0 dropped, 2 -> 2x2 list, 3 -> 3x3 list
+    uint32_t cls = 0u;  // 0 no MI, 2 -> 2x2 list, 3 -> 3x3 list
     bool emit = false;
     if (p < n_pairs) {
-      while (k >= len) {
-        k -= len;
-        ++i;
-        --len;
-      }
-      const uint32_t j = i + 1u + k;
-      sm.ij[p] = (uint16_t)(i * 64u + j);
+      const uint32_t ij = __ldg(ijt + p);
+      const uint32_t i = ij >> 6, j = ij & 63u;
       const bool het = ((sm.flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
                        ((sm.flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
-      unsigned long long v = 0x7ff8000000000000ull;  // NaN: no MI for this candidate
+      unsigned long long v = kNoMi;
       if (het || !skip_nonhet) {
         const unsigned long long cnt = pair_counts<NW>(rows + i * kRowStride, rows + j * kRowStride);
-        const uint32_t o = sm.oth[p];
-        const uint32_t n_oth = (o & 7u) + ((o >> 3) & 7u) + ((o >> 6) & 7u) + ((o >> 9) & 7u) + ((o >> 12) & 7u);
-        const uint32_t n_common = (uint32_t)(cnt & 0xffffu) + n_oth;
+        uint32_t n_common = (uint32_t)cnt & 511u;
+        const uint32_t ni = sm.n_oth[i], nj = sm.n_oth[j];
+        uint32_t o = 0u;
+        if (ni | nj) {
+          o = other_cells(sm, rows, i, j, ni, nj);
+          n_common += (o & 7u) + ((o >> 3) & 7u) + ((o >> 6) & 7u) + ((o >> 9) & 7u) + ((o >> 12) & 7u);
+        }
         if ((int)n_common >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
-          v = cnt;
+          v = cnt | ((unsigned long long)o << 36);
           cls = o ? 3u : 2u;
           emit = het || !het_only;
         }
       }
       sm.val[p] = v;
     }
-    k += kFastThreads;
     // warp-aggregated bookkeeping: this warp's 32 pairs are one lexicographic chunk
     const uint32_t me = __ballot_sync(0xffffffffu, emit);
     const uint32_t m2 = __ballot_sync(0xffffffffu, cls == 2u);
@@ -175,6 +171,16 @@ __device__ __forceinline__ void fast_counts(const FastParams& P, FastSmem& sm, c
   }
 }
 
+__device__ __forceinline__ void unpack_counts(unsigned long long v, uint32_t& n_mm, uint32_t& n_mM, uint32_t& n_Mm,
+                                              uint32_t& n_MM) {
+  const uint32_t lo = (uint32_t)v;
+  const uint32_t nPP = lo & 511u, nMP = (lo >> 9) & 511u, nPM = (lo >> 18) & 511u;
+  n_MM = (uint32_t)(v >> 27) & 511u;
+  n_Mm = nMP - n_MM;  // i major, j minor
+  n_mM = nPM - n_MM;  // i minor, j major
+  n_mm = nPP - nMP - nPM + n_MM;
+}
+
 // MI of the listed pairs, in place of their packed counts; warp-sized chunks of both lists
 __device__ __forceinline__ void fast_mi(FastSmem& sm) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -185,31 +191,24 @@ __device__ __forceinline__ void fast_mi(FastSmem& sm) {
       const uint32_t q = c * 32u + lane;
       if (q < n2) {
         const uint32_t p = sm.list[q];
-        const unsigned long long cnt = sm.val[p];
-        const uint32_t nPP = (uint32_t)(cnt & 0xffffu), nMP = (uint32_t)((cnt >> 16) & 0xffffu);
-        const uint32_t nPM = (uint32_t)((cnt >> 32) & 0xffffu), nMM = (uint32_t)(cnt >> 48);
-        // i major & j minor = nMP - nMM ; i minor & j major = nPM - nMM
-        const double mi = mi_2x2(sm.tab, nPP - nMP - nPM + nMM, nPM - nMM, nMP - nMM, nMM);
+        uint32_t n_mm, n_mM, n_Mm, n_MM;
+        unpack_counts(sm.val[p], n_mm, n_mM, n_Mm, n_MM);
+        const double mi = mi_2x2(sm.tab, n_mm, n_mM, n_Mm, n_MM);
         sm.val[p] = (unsigned long long)__double_as_longlong(mi);
       }
     } else {
       const uint32_t q = (c - nc2) * 32u + lane;
       if (q < n3) {
         const uint32_t p = sm.list[kFastMaxPairs - 1u - q];
-        const unsigned long long cnt = sm.val[p];
-        const uint32_t o = sm.oth[p];
-        const uint32_t nPP = (uint32_t)(cnt & 0xffffu), nMP = (uint32_t)((cnt >> 16) & 0xffffu);
-        const uint32_t nPM = (uint32_t)((cnt >> 32) & 0xffffu), nMM = (uint32_t)(cnt >> 48);
+        const unsigned long long v = sm.val[p];
+        const uint32_t o = (uint32_t)(v >> 36);
         uint32_t T[9];
+        unpack_counts(v, T[4], T[5], T[7], T[8]);
         T[0] = o & 7u;
         T[1] = (o >> 3) & 7u;
         T[2] = (o >> 6) & 7u;
         T[3] = (o >> 9) & 7u;
         T[6] = (o >> 12) & 7u;
-        T[4] = nPP - nMP - nPM + nMM;
-        T[5] = nPM - nMM;
-        T[7] = nMP - nMM;
-        T[8] = nMM;
         const double mi = mi_3x3(sm.tab, T);
         sm.val[p] = (unsigned long long)__double_as_longlong(mi);
       }
@@ -233,20 +232,29 @@ __device__ __forceinline__ void fast_chunk_prefix(FastSmem& sm, uint32_t n_chunk
     if (c < n_chunks) sm.chunk_off[c] = carry + inc - v;
     carry += __shfl_sync(0xffffffffu, inc, 31);
   }
-  if (lane == 0) sm.total = carry;
+  if (lane == 0) {
+    sm.total = carry;
+    sm.next_chunk = 0u;
+  }
 }
 
-// ordered write of the surviving pairs: one 16-byte record {unit, i | j << 16, mi} each
+// ordered write of the surviving pairs: one 16-byte record {unit, i | j << 16, mi} each.
+// Warps pull chunks from a shared counter, so the warps busy with the mean phase join late.
 __device__ __forceinline__ void fast_emit(const FastParams& P, FastSmem& sm, const FastItem& it,
-                                          unsigned long long base, uint32_t n_chunks) {
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+                                          const uint16_t* __restrict__ ijt, unsigned long long base,
+                                          uint32_t n_chunks) {
+  const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt = (1u << lane) - 1u;
-  for (uint32_t c = warp; c < n_chunks; c += kFastWarps) {
+  while (true) {
+    uint32_t c = 0u;
+    if (lane == 0) c = atomicAdd(&sm.next_chunk, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= n_chunks) break;
     const uint32_t mask = sm.emit_mask[c];
     if ((mask >> lane) & 1u) {
       const uint32_t p = c * 32u + lane;
       const unsigned long long slot = base + sm.chunk_off[c] + __popc(mask & lt);
-      const uint32_t ij = sm.ij[p];
+      const uint32_t ij = __ldg(ijt + p);
       const unsigned long long bits = sm.val[p];
       uint4 rec;
       rec.x = it.unit;
@@ -271,63 +279,75 @@ __device__ __forceinline__ void fast_emit_counts(const FastParams& P, FastSmem& 
     if ((mask >> lane) & 1u) {
       const uint32_t p = c * 32u + lane;
       const unsigned long long slot = base + sm.chunk_off[c] + __popc(mask & lt);
-      const unsigned long long cnt = sm.val[p];
-      const uint32_t o = sm.oth[p];
-      const uint32_t nPP = (uint32_t)(cnt & 0xffffu), nMP = (uint32_t)((cnt >> 16) & 0xffffu);
-      const uint32_t nPM = (uint32_t)((cnt >> 32) & 0xffffu), nMM = (uint32_t)(cnt >> 48);
+      const unsigned long long v = sm.val[p];
+      const uint32_t o = (uint32_t)(v >> 36);
       uint32_t* out = P.counts + slot * 9ull;
+      uint32_t n_mm, n_mM, n_Mm, n_MM;
+      unpack_counts(v, n_mm, n_mM, n_Mm, n_MM);
       out[0] = o & 7u;
       out[1] = (o >> 3) & 7u;
       out[2] = (o >> 6) & 7u;
       out[3] = (o >> 9) & 7u;
-      out[4] = nPP - nMP - nPM + nMM;
-      out[5] = nPM - nMM;
+      out[4] = n_mm;
+      out[5] = n_mM;
       out[6] = (o >> 12) & 7u;
-      out[7] = nMP - nMM;
-      out[8] = nMM;
+      out[7] = n_Mm;
+      out[8] = n_MM;
     }
   }
 }
 
 // per-site mean over the het-kept pairs (mutual_information.py:48-60): partners in
-// ascending order, CPython's compensated float sum.  Het sites sum over every
-// partner, the others over the het sites only.
-__device__ __forceinline__ uint32_t nth_set_bit(unsigned long long m, uint32_t n) {
-  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-  const uint32_t c = __popc(lo);
-  return (n < c) ? __fns(lo, 0, n + 1) : 32u + __fns(hi, 0, n - c + 1);
-}
+// ascending order, CPython's compensated float sum (all MI values are >= 0, so
+// |s| >= |x| is s >= x).  Het sites sum over every partner, the others over the
+// het sites only.  Threads [0, n_het) take the het sites (the long chains share
+// warps), the next S - n_het threads the other sites.
+struct MeanAcc {
+  double s, c;
+  uint32_t n;
+  __device__ __forceinline__ void add(const double* __restrict__ s_mi, uint32_t p) {
+    const double x = s_mi[p];
+    if (__double2hiint(x) >= 0x7ff00000) return;  // NaN pattern: no MI for this pair
+    const double t = __dadd_rn(s, x);
+    const double big = (s >= x) ? s : x, small = (s >= x) ? x : s;
+    c = __dadd_rn(c, __dadd_rn(__dsub_rn(big, t), small));
+    s = t;
+    ++n;
+  }
+};
 
 __device__ __forceinline__ void fast_means(const FastParams& P, FastSmem& sm, const FastItem& it) {
   const uint32_t tid = threadIdx.x, S = it.S;
-  const unsigned long long het = sm.het_mask;
-  const uint32_t n_het = __popcll(het);
-  const unsigned long long all = (S == 64u) ? ~0ull : ((1ull << S) - 1ull);
-  // threads [0, n_het): het sites (long chains, packed into the first warps); then the other sites
-  uint32_t s;
-  unsigned long long partners;
-  if (tid < n_het) {
-    s = nth_set_bit(het, tid);
-    partners = all & ~(1ull << s);
-  } else if (tid < S) {
-    s = nth_set_bit(all & ~het, tid - n_het);
-    partners = het;
-  } else {
-    return;
-  }
+  if (tid >= S) return;
+  const uint32_t n_het = __popcll(sm.het_mask);
   const double* s_mi = reinterpret_cast<const double*>(sm.val);
-  const uint32_t row_s = (s * (2u * S - s - 1u)) >> 1;
-  lg_neumaier acc;
-  lg_neumaier_init(acc);
-  while (partners) {
-    const uint32_t t = __ffsll((long long)partners) - 1u;
-    partners &= partners - 1ull;
-    const uint32_t p = (t < s) ? (((t * (2u * S - t - 1u)) >> 1) + (s - t - 1u)) : (row_s + (t - s - 1u));
-    const double v = s_mi[p];
-    if (__double2hiint(v) != 0x7ff80000) lg_neumaier_add(acc, v);  // NaN pattern: no MI for this pair
+  MeanAcc acc{0.0, 0.0, 0u};
+  uint32_t s;
+  if (tid < n_het) {
+    s = sm.het_list[tid];
+    uint32_t p = s - 1u;  // pair (t, s) for t = 0; the next one is S - t - 2 further
+    for (uint32_t t = 0; t < s; ++t) {
+      acc.add(s_mi, p);
+      p += S - t - 2u;
+    }
+    p = (s * (2u * S - s - 1u)) >> 1;  // pair (s, s + 1)
+    for (uint32_t t = s + 1u; t < S; ++t, ++p) acc.add(s_mi, p);
+  } else {
+    s = sm.nonhet_list[tid - n_het];
+    const uint32_t row_s = (s * (2u * S - s - 1u)) >> 1;
+    for (uint32_t q = 0; q < n_het; ++q) {
+      const uint32_t t = sm.het_list[q];
+      acc.add(s_mi, (t < s) ? (((t * (2u * S - t - 1u)) >> 1) + (s - t - 1u)) : (row_s + (t - s - 1u)));
+    }
   }
-  P.site_mean[it.site_off + s] = lg_neumaier_mean(acc);
-  P.site_cnt[it.site_off + s] = (uint32_t)acc.n;
+  double mean = mi_nan();
+  if (acc.n) {
+    double tot = acc.s;
+    if (acc.c != 0.0) tot = __dadd_rn(tot, acc.c);  // every term is finite, so is the compensation
+    mean = __ddiv_rn(tot, (double)acc.n);
+  }
+  P.site_mean[it.site_off + s] = mean;
+  P.site_cnt[it.site_off + s] = acc.n;
 }
 
 __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams P) {
@@ -335,15 +355,12 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
   FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x;
 
-  // per-CTA table: ln k (hi, lo), (double)k, RN(1/k) for k <= 256
+  // per-CTA table: ln k (hi, lo) and RN(1/k) for k <= 256
   for (uint32_t k = tid; k <= (uint32_t)kFastMaxR; k += kFastThreads) {
-    FastTabEntry e;
     const double2 v = (k < P.ln_cap) ? __ldg(reinterpret_cast<const double2*>(P.lntab) + k) : make_double2(0.0, 0.0);
-    e.ln_hi = v.x;
-    e.ln_lo = v.y;
-    e.dk = (double)k;
-    e.inv = k ? __drcp_rn((double)k) : 0.0;
-    sm.tab[k] = e;
+    sm.tab.ln[k].hi = v.x;
+    sm.tab.ln[k].lo = v.y;
+    sm.tab.inv[k] = k ? __drcp_rn((double)k) : 0.0;
   }
 
   uint32_t idx = blockIdx.x;
@@ -369,30 +386,26 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
     const uint32_t n_pairs = S * (S - 1u) / 2u;
     const uint32_t n_chunks = (n_pairs + 31u) >> 5;
     const bool dense = P.item_dense[it.item] != 0u;  // handled by the generic kernel
+    const unsigned long long base = P.item_off[it.item];
     if (!dense) {
       uint32_t* rows = sm.rows[buf];
-      for (uint32_t p = tid; p < (n_chunks * 32u + 1u) / 2u; p += kFastThreads) reinterpret_cast<uint32_t*>(sm.oth)[p] = 0u;
+      const uint16_t* __restrict__ ijt = P.ij_tab + lg_ij_tab_off(S);
       if (tid < (uint32_t)kFastMaxS) sm.n_oth[tid] = 0u;
       if (tid == 0) {
         sm.n_list2 = 0u;
         sm.n_list3 = 0u;
-        sm.n_oth_sites = 0u;
       }
       cp_async_wait<1>();  // this item's rows have landed (the next item's may still be in flight)
       __syncthreads();
       fast_land(sm, rows, it, P.site_flags + it.site_off);
       __syncthreads();
-      fast_other_sites(sm, S);
-      __syncthreads();
-      fast_fixup(sm, rows, S);
-      __syncthreads();
+      fast_site_lists(sm, S);
       const uint32_t nw = ((uint32_t)it.R + 31u) >> 5;
-      if (nw <= 2u) fast_counts<2>(P, sm, rows, S, n_pairs);
-      else if (nw <= 4u) fast_counts<4>(P, sm, rows, S, n_pairs);
-      else if (nw <= 7u) fast_counts<7>(P, sm, rows, S, n_pairs);
-      else fast_counts<8>(P, sm, rows, S, n_pairs);
+      if (nw <= 2u) fast_counts<2>(P, sm, rows, ijt, n_pairs);
+      else if (nw <= 4u) fast_counts<4>(P, sm, rows, ijt, n_pairs);
+      else if (nw <= 7u) fast_counts<7>(P, sm, rows, ijt, n_pairs);
+      else fast_counts<8>(P, sm, rows, ijt, n_pairs);
       __syncthreads();
-      const unsigned long long base = P.item_off[it.item];
       if (tid < 32u) fast_chunk_prefix(sm, n_chunks);
       if (P.mode & LGMI_MODE_EMIT_COUNTS) {
         __syncthreads();
@@ -401,8 +414,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
       fast_mi(sm);
       __syncthreads();
       if (tid == 0) P.unit_rec_off[it.unit] = base;
-      fast_emit(P, sm, it, base, n_chunks);
-      fast_means(P, sm, it);
+      fast_means(P, sm, it);                      // warps 0-1 (S <= 64 threads) ...
+      fast_emit(P, sm, it, ijt, base, n_chunks);  // ... while the others already write records
     } else {
       cp_async_wait<1>();
     }

@@ -13,18 +13,22 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline double __longlong_as_double(long long v) { double d; __builtin_memcpy(&d, &v, 8); return d; }
+static inline double __hiloint2double(int hi, int lo) {
+  const unsigned long long v = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+  double d; __builtin_memcpy(&d, &v, 8); return d;
+}
 
 #include "../../l-giremi_b200/csrc/lgmi_fast.cuh"
 
 using namespace lgmi;
 
-static std::vector<FastTabEntry> make_tab(const double* lntab, uint32_t n) {
-  std::vector<FastTabEntry> t(n);
-  for (uint32_t k = 0; k < n; ++k) {
-    t[k].ln_hi = lntab[2 * k];
-    t[k].ln_lo = lntab[2 * k + 1];
-    t[k].dk = (double)k;
-    t[k].inv = k ? 1.0 / (double)k : 0.0;
+// the kernel's table covers k <= 256 (kFastMaxR); `n` is ignored beyond that
+static FastTab make_tab(const double* lntab, uint32_t n) {
+  FastTab t;
+  for (uint32_t k = 0; k <= (uint32_t)kFastMaxR; ++k) {
+    t.ln[k].hi = k < n ? lntab[2 * k] : 0.0;
+    t.ln[k].lo = k < n ? lntab[2 * k + 1] : 0.0;
+    t.inv[k] = k ? 1.0 / (double)k : 0.0;
   }
   return t;
 }
@@ -32,20 +36,20 @@ static std::vector<FastTabEntry> make_tab(const double* lntab, uint32_t n) {
 extern "C" {
 double f_mi_2x2(uint32_t mm, uint32_t mM, uint32_t Mm, uint32_t MM, const double* lntab, uint32_t n) {
   auto t = make_tab(lntab, n);
-  return mi_2x2(t.data(), mm, mM, Mm, MM);
+  return mi_2x2(t, mm, mM, Mm, MM);
 }
 double f_mi_3x3(const uint32_t* T, const double* lntab, uint32_t n) {
   auto t = make_tab(lntab, n);
-  return mi_3x3(t.data(), T);
+  return mi_3x3(t, T);
 }
 // batch versions (one table build)
 void f_mi_2x2_many(const uint32_t* cells, int64_t m, const double* lntab, uint32_t n, double* out) {
   auto t = make_tab(lntab, n);
-  for (int64_t k = 0; k < m; ++k) out[k] = mi_2x2(t.data(), cells[4 * k], cells[4 * k + 1], cells[4 * k + 2], cells[4 * k + 3]);
+  for (int64_t k = 0; k < m; ++k) out[k] = mi_2x2(t, cells[4 * k], cells[4 * k + 1], cells[4 * k + 2], cells[4 * k + 3]);
 }
 void f_mi_3x3_many(const uint32_t* T, int64_t m, const double* lntab, uint32_t n, double* out) {
   auto t = make_tab(lntab, n);
-  for (int64_t k = 0; k < m; ++k) out[k] = mi_3x3(t.data(), T + 9 * k);
+  for (int64_t k = 0; k < m; ++k) out[k] = mi_3x3(t, T + 9 * k);
 }
 // number of (n, N) with 0 <= n <= N <= n_max where the Markstein quotient differs from n / N
 int64_t f_markstein_mismatches(uint32_t n_max) {
@@ -70,6 +74,7 @@ uint32_t f_and_popc(int nw, const uint32_t* x, const uint32_t* y) {
     default: return and_popc<8>(x, y);
   }
 }
+double f_u32_to_double(uint32_t n) { return u32_to_double(n); }
 uint64_t f_pair_counts(int nw, const uint32_t* ri, const uint32_t* rj) {
   switch (nw) {
     case 2: return pair_counts<2>(ri, rj);

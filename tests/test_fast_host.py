@@ -5,7 +5,7 @@ import numpy as np
 
 from conftest import unhex
 
-NTAB = 4096
+NTAB = 257          # the kernel's shared-memory table covers counts up to 256 reads
 
 
 def u32(a):
@@ -15,6 +15,14 @@ def u32(a):
 def test_markstein_quotient_is_the_rounded_quotient(fast_host):
     """q0 = n*RN(1/N); r = fma(-q0,N,n); q = fma(r,RN(1/N),q0) == RN(n/N) for all 0<=n<=N<=3000."""
     assert fast_host.f_markstein_mismatches(3000) == 0
+
+
+def test_u32_to_double_trick(fast_host):
+    import ctypes
+    fast_host.f_u32_to_double.restype = ctypes.c_double
+    fast_host.f_u32_to_double.argtypes = [ctypes.c_uint32]
+    for n in list(range(0, 600)) + [65535, 65536, 2**31 - 1, 2**31, 2**32 - 1]:
+        assert fast_host.f_u32_to_double(n) == float(n)
 
 
 def test_carry_save_popcount(fast_host):
@@ -45,7 +53,8 @@ def test_pair_counts_packing(fast_host):
             v = fast_host.f_pair_counts(nw, ri.ctypes.data, rj.ctypes.data)
             pc = lambda a, b: int(sum(bin(int(x) & int(y)).count("1") for x, y in zip(a, b)))
             want = (pc(ri[8:16], rj[8:16]), pc(ri[:8], rj[8:16]), pc(ri[8:16], rj[:8]), pc(ri[:8], rj[:8]))
-            got = (v & 0xffff, (v >> 16) & 0xffff, (v >> 32) & 0xffff, v >> 48)
+            got = (v & 511, (v >> 9) & 511, (v >> 18) & 511, (v >> 27) & 511)
+            assert v >> 36 == 0
             assert got == want
 
 
@@ -53,7 +62,7 @@ def test_fast_2x2_same_bits_as_reference_arithmetic(fast_host, math_host, lntab)
     rng = np.random.default_rng(3)
     cells = []
     for _ in range(40000):
-        c = rng.integers(0, int(rng.choice([2, 4, 12, 60, 250])), 4)
+        c = rng.integers(0, int(rng.choice([2, 4, 12, 60, 120])), 4)
         c[rng.random(4) < rng.choice([0.0, 0.3])] = 0
         if 0 < c.sum() < NTAB:
             cells.append(c)
@@ -69,7 +78,7 @@ def test_fast_3x3_same_bits_as_reference_arithmetic(fast_host, math_host, lntab)
     rng = np.random.default_rng(4)
     tabs = []
     for _ in range(40000):
-        t = rng.integers(0, int(rng.choice([2, 3, 10, 40, 200])), 9)
+        t = rng.integers(0, int(rng.choice([2, 3, 10, 40, 56])), 9)
         if rng.random() < 0.6:                       # "other" cells are small in practice
             t[[0, 1, 2, 3, 6]] = rng.integers(0, 3, 5)
         t[rng.random(9) < rng.choice([0.0, 0.3, 0.6])] = 0
@@ -97,4 +106,4 @@ def test_fast_paths_match_sklearn_golden(fast_host, lntab, golden):
             assert fast_host.f_mi_2x2(int(t[4]), int(t[5]), int(t[7]), int(t[8]), lntab.ctypes.data, NTAB) == \
                 unhex(case["mi"]), case
         n += 1
-    assert n > 1500
+    assert n > 1000
