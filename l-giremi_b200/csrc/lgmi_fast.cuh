@@ -73,6 +73,7 @@ struct FastSmem {
   uint16_t oth_list[kFastMaxS * 8];                      // 1 KB
   uint32_t n_oth[kFastMaxS];
   uint8_t flags[kFastMaxS];
+  uint8_t info[kFastMaxS];                               // bit 0 het_snp, bits 1-4 number of "other" reads
   uint8_t het_list[kFastMaxS];                           // het sites ascending, then ...
   uint8_t nonhet_list[kFastMaxS];                        // ... the other sites ascending
   unsigned long long het_mask;

@@ -87,10 +87,13 @@ __device__ __forceinline__ void fast_land(FastSmem& sm, uint32_t* __restrict__ r
   }
 }
 
-// ordered lists of the het sites and of the other sites (for the mean phase)
+// ordered lists of the het sites and of the other sites (for the mean phase), and the
+// per-site byte the counts phase reads: bit 0 het_snp, bits 1-4 number of "other" reads
 __device__ __forceinline__ void fast_site_lists(FastSmem& sm, uint32_t S) {
   const uint32_t s = threadIdx.x;
   if (s < S) {
+    sm.info[s] = (uint8_t)(((sm.flags[s] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP ? 1u : 0u) |
+                           (min(sm.n_oth[s], (uint32_t)kOthCap) << 1));
     const unsigned long long het = sm.het_mask;
     const uint32_t rank = __popcll(het & ((1ull << s) - 1ull));
     if ((het >> s) & 1ull) sm.het_list[rank] = (uint8_t)s;
@@ -101,21 +104,27 @@ __device__ __forceinline__ void fast_site_lists(FastSmem& sm, uint32_t S) {
 // the table cells that involve an "other" label of pair (i, j), from the sparse per-site
 // lists: five 3-bit cells T[0][0], T[0][1], T[0][2], T[1][0], T[2][0]
 __device__ __forceinline__ uint32_t other_cells(const FastSmem& sm, const uint32_t* __restrict__ rows, uint32_t i,
-                                                uint32_t j, uint32_t ni, uint32_t nj) {
-  uint32_t o = 0u;
+                                                uint32_t j, uint32_t ni, uint32_t nj, uint32_t& n_cells) {
+  uint32_t o = 0u, n = 0u;
   const uint32_t* ri = rows + i * kRowStride;
   const uint32_t* rj = rows + j * kRowStride;
   for (uint32_t q = 0; q < ni; ++q) {  // "other" at i: row 0 of the table
     const uint32_t r = sm.oth_list[i * 8u + q];
     const uint32_t w = r >> 5, bit = r & 31u;
+    const uint32_t covered = (rj[16u + w] >> bit) & 1u;
+    n += covered;
     if ((rj[8u + w] >> bit) & 1u) o += 8u << (3u * ((rj[w] >> bit) & 1u));  // j minor -> cell 1, major -> cell 2
-    else o += (rj[16u + w] >> bit) & 1u;                                    // "other" at both
+    else o += covered;                                                      // "other" at both
   }
   for (uint32_t q = 0; q < nj; ++q) {  // "other" at j, not at i: column 0
     const uint32_t r = sm.oth_list[j * 8u + q];
     const uint32_t w = r >> 5, bit = r & 31u;
-    if ((ri[8u + w] >> bit) & 1u) o += 512u << (3u * ((ri[w] >> bit) & 1u));  // i minor -> cell 3, major -> cell 4
+    if ((ri[8u + w] >> bit) & 1u) {
+      o += 512u << (3u * ((ri[w] >> bit) & 1u));  // i minor -> cell 3, major -> cell 4
+      ++n;
+    }
   }
+  n_cells = n;
   return o;
 }
 
@@ -134,17 +143,17 @@ __device__ __forceinline__ void fast_counts(const FastParams& P, FastSmem& sm, c
     if (p < n_pairs) {
       const uint32_t ij = __ldg(ijt + p);
       const uint32_t i = ij >> 6, j = ij & 63u;
-      const bool het = ((sm.flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
-                       ((sm.flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+      const uint32_t fi = sm.info[i], fj = sm.info[j];
+      const bool het = ((fi | fj) & 1u) != 0u;
       unsigned long long v = kNoMi;
       if (het || !skip_nonhet) {
         const unsigned long long cnt = pair_counts<NW>(rows + i * kRowStride, rows + j * kRowStride);
         uint32_t n_common = (uint32_t)cnt & 511u;
-        const uint32_t ni = sm.n_oth[i], nj = sm.n_oth[j];
         uint32_t o = 0u;
-        if (ni | nj) {
-          o = other_cells(sm, rows, i, j, ni, nj);
-          n_common += (o & 7u) + ((o >> 3) & 7u) + ((o >> 6) & 7u) + ((o >> 9) & 7u) + ((o >> 12) & 7u);
+        if ((fi | fj) >> 1) {
+          uint32_t n_o = 0u;
+          o = other_cells(sm, rows, i, j, fi >> 1, fj >> 1, n_o);
+          n_common += n_o;
         }
         if ((int)n_common >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
           v = cnt | ((unsigned long long)o << 36);
@@ -239,17 +248,13 @@ __device__ __forceinline__ void fast_chunk_prefix(FastSmem& sm, uint32_t n_chunk
 }
 
 // ordered write of the surviving pairs: one 16-byte record {unit, i | j << 16, mi} each.
-// Warps pull chunks from a shared counter, so the warps busy with the mean phase join late.
+// Warps [first_warp, 8) share the chunks; the first two warps are busy with the mean phase.
 __device__ __forceinline__ void fast_emit(const FastParams& P, FastSmem& sm, const FastItem& it,
                                           const uint16_t* __restrict__ ijt, unsigned long long base,
-                                          uint32_t n_chunks) {
-  const uint32_t lane = threadIdx.x & 31u;
+                                          uint32_t n_chunks, uint32_t first_warp) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  while (true) {
-    uint32_t c = 0u;
-    if (lane == 0) c = atomicAdd(&sm.next_chunk, 1u);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    if (c >= n_chunks) break;
+  for (uint32_t c = warp - first_warp; c < n_chunks; c += kFastWarps - first_warp) {
     const uint32_t mask = sm.emit_mask[c];
     if ((mask >> lane) & 1u) {
       const uint32_t p = c * 32u + lane;
@@ -400,6 +405,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
       fast_land(sm, rows, it, P.site_flags + it.site_off);
       __syncthreads();
       fast_site_lists(sm, S);
+      __syncthreads();  // sm.info is read by every thread of the counts phase
       const uint32_t nw = ((uint32_t)it.R + 31u) >> 5;
       if (nw <= 2u) fast_counts<2>(P, sm, rows, ijt, n_pairs);
       else if (nw <= 4u) fast_counts<4>(P, sm, rows, ijt, n_pairs);
@@ -414,8 +420,10 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
       fast_mi(sm);
       __syncthreads();
       if (tid == 0) P.unit_rec_off[it.unit] = base;
-      fast_means(P, sm, it);                      // warps 0-1 (S <= 64 threads) ...
-      fast_emit(P, sm, it, ijt, base, n_chunks);  // ... while the others already write records
+      // the serial per-site sums occupy the first one or two warps; the others write the records
+      const uint32_t mean_warps = (S + 31u) >> 5;
+      if ((tid >> 5) < mean_warps) fast_means(P, sm, it);
+      else fast_emit(P, sm, it, ijt, base, n_chunks, mean_warps);
     } else {
       cp_async_wait<1>();
     }
