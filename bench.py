@@ -15,7 +15,7 @@ time), so scaling is "weak".
 
 Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM;
 `e2e` goes through the C-ABI calls with pinned HOST buffers, H2D and D2H inside
-the timed region.  `roofline` is for the dominant kernel (k_pairs), timed live
+the timed region.  `roofline` is for the dominant kernel (k_pairs_fast), timed live
 with CUDA events on the launching stream.  `cpu_baseline` times the oracle's
 port of the reference step on the host cores on a bounded sample of the same
 units.
@@ -309,7 +309,7 @@ def run_gpu(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_pairs_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("k_pairs_fast_dram_bytes_per_launch")
         except (OSError, ValueError):
             traffic = None
 
@@ -323,7 +323,7 @@ def run_gpu(args):
                    "every survivor written)", "l2": "512 MiB buffer written between timed iterations",
                    "partition": "LPT over %d units -> %d bins, loads equal" % (G * world, world)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "k_pairs", "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes,
+                     "traffic": traffic, "kernel": "k_pairs_fast", "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes,
                      "peak_source": peak_src,
                      "kernel_share_of_step": k_ms * args.steps / dev_ms if dev_ms else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

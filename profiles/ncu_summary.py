@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep: headline metrics + instruction/stall share per source function.
-usage: python profiles/ncu_summary.py gpurun_out/prof.ncu-rep [kernel_source_file ...]"""
+usage: python profiles/ncu_summary.py gpurun_out/prof.ncu-rep [-k kernel_regex] [kernel_source_file ...]"""
 import collections, csv, io, re, subprocess, sys
 
+KFILTER = []
+
 def run(args):
-    return subprocess.run(["ncu", "-i"] + args, capture_output=True, text=True).stdout
+    return subprocess.run(["ncu", "-i"] + args + KFILTER, capture_output=True, text=True).stdout
 
 def main():
     rep = sys.argv[1]
+    if len(sys.argv) > 3 and sys.argv[2] == "-k":
+        KFILTER.extend(["-k", "regex:" + sys.argv[3]])
+        del sys.argv[2:4]
     raw = list(csv.reader(io.StringIO(run([rep, "--page", "raw", "--csv"]))))
     d = {h: (u, v) for h, u, v in zip(raw[0], raw[1], raw[2])}
     keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread",
