@@ -135,6 +135,10 @@ typedef struct {
   float kernel_ms;              /* device time of all compute kernels of the   */
                                 /* run (CUDA events on the launching stream)   */
   float pairs_kernel_ms;        /* device time of the pair kernel alone        */
+  float dense_kernel_ms;        /* device time of the tensor-core path         */
+                                /* (plane expansion + int8 Gram kernel)        */
+  uint32_t n_dense_units;       /* units that took the tensor-core path        */
+  uint64_t dense_macs;          /* int8 multiply-accumulates issued for them   */
 } lgmi_result;
 
 typedef struct lgmi_ctx lgmi_t;
@@ -154,6 +158,12 @@ LGMI_API int lgmi_pinned_alloc(lgmi_t* ctx, size_t bytes, void** out);
 LGMI_API int lgmi_pinned_free(lgmi_t* ctx, void* ptr);
 /* number of kernels this library has launched on the context so far           */
 LGMI_API uint64_t lgmi_launch_count(const lgmi_t* ctx);
+/* Units with n_sites >= min_sites and n_reads >= min_reads build their        *
+ * contingency counts as a dense int8 contraction on the tensor cores          *
+ * (tcgen05 / TMEM / TMA) instead of AND+popcount; same counts, bit for bit    *
+ * (mutual_information.py:15-40).  Default 512 sites x 8192 reads; applies to  *
+ * batches created afterwards.  Tests lower it to force the path.              */
+LGMI_API int lgmi_set_dense_threshold(lgmi_t* ctx, uint32_t min_sites, uint32_t min_reads);
 
 /* ----- batched MI step: replaces the per-unit loop                           *
  *   mismatch.py:387-404 = mutual_information.py:6-45 -> het filter -> :48-60  */

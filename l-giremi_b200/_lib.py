@@ -34,7 +34,7 @@ ERR_NODEVICE = -5
 
 EXPORTS = (
     "lgmi_version", "lgmi_create", "lgmi_destroy", "lgmi_last_error", "lgmi_set_stream",
-    "lgmi_pinned_alloc", "lgmi_pinned_free", "lgmi_launch_count",
+    "lgmi_pinned_alloc", "lgmi_pinned_free", "lgmi_launch_count", "lgmi_set_dense_threshold",
     "lgmi_batch_create", "lgmi_batch_destroy", "lgmi_batch_upload", "lgmi_batch_run",
     "lgmi_batch_download", "lgmi_batch_sync", "lgmi_batch_device_ptrs",
     "lgmi_batch_algorithmic_bytes", "lgmi_submit", "lgmi_wait", "lgmi_site_mean_csr",
@@ -55,6 +55,9 @@ class Result(C.Structure):
         ("unit_rec_off", C.c_void_p),
         ("kernel_ms", C.c_float),
         ("pairs_kernel_ms", C.c_float),
+        ("dense_kernel_ms", C.c_float),
+        ("n_dense_units", C.c_uint32),
+        ("dense_macs", C.c_uint64),
     ]
 
 
@@ -88,6 +91,7 @@ def load():
         "lgmi_pinned_alloc": (i32, [vp, C.c_size_t, pvp]),
         "lgmi_pinned_free": (i32, [vp, vp]),
         "lgmi_launch_count": (u64, [vp]),
+        "lgmi_set_dense_threshold": (i32, [vp, u32, u32]),
         "lgmi_batch_create": (i32, [vp, vp, u32, u64, u64, pvp]),
         "lgmi_batch_destroy": (None, [vp]),
         "lgmi_batch_upload": (i32, [vp, vp, vp]),

@@ -50,6 +50,10 @@ class Context:
         """Launch on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
         check(self._lib.lgmi_set_stream(self.handle, C.c_void_p(cuda_stream_ptr or 0)), self.handle)
 
+    def set_dense_threshold(self, min_sites, min_reads):
+        """Units at least this large take the int8 tensor-core path (batches created afterwards)."""
+        check(self._lib.lgmi_set_dense_threshold(self.handle, int(min_sites), int(min_reads)), self.handle)
+
     @property
     def launch_count(self):
         return int(self._lib.lgmi_launch_count(self.handle))
@@ -104,6 +108,9 @@ class StepResult:
         self.n_records = int(res.n_records)
         self.kernel_ms = float(res.kernel_ms)
         self.pairs_kernel_ms = float(res.pairs_kernel_ms)
+        self.dense_kernel_ms = float(res.dense_kernel_ms)
+        self.n_dense_units = int(res.n_dense_units)
+        self.dense_macs = int(res.dense_macs)
         rec = array_at(res.records, PAIR_REC, self.n_records)
         mean = array_at(res.site_mean, np.float64, int(res.n_sites))
         cnt = array_at(res.site_cnt, np.uint32, int(res.n_sites))

@@ -4,6 +4,7 @@
 // per-batch work tables and launches the kernels in lgmi_kernels.cuh.  There is
 // no CPU implementation of the MI step in this library: every entry point that
 // computes does so on the device, and lgmi_create() fails without one.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -46,6 +47,17 @@ struct lgmi_ctx {
   // persistent launch shape of k_pairs
   int num_sms = 0;
   int pairs_ctas_per_sm = 0;
+  // tensor-core path: units at least this large build their tables with k_gram_i8
+  uint32_t dense_min_sites = 512, dense_min_reads = 8192;
+  void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
+  cudaEvent_t ev4 = nullptr, ev5 = nullptr;
+};
+
+// one unit of the tensor-core path
+struct DensePlan {
+  uint32_t unit = 0, S = 0, W = 0, S_pad = 0, k_blocks = 0, n_tiles = 0;
+  uint64_t plane_off = 0, gram_off = 0, tile_off = 0;
+  CUtensorMap tmap;
 };
 
 struct lgmi_batch {
@@ -77,6 +89,12 @@ struct lgmi_batch {
   uint32_t* d_site_cnt = nullptr;
   double* d_dense = nullptr;
   unsigned long long* d_unit_rec_off = nullptr;
+  // tensor-core path
+  std::vector<DensePlan> dense_plans;
+  uint8_t* d_x = nullptr;       // indicator matrix of the unit being contracted (reused unit after unit)
+  uint32_t* d_gram = nullptr;   // nine count matrices per dense unit
+  DenseTile* d_tiles = nullptr;
+  uint64_t dense_macs = 0;      // multiply-accumulates the tile lists amount to
   // host (pinned) mirrors
   Header* h_header = nullptr;
   lgmi_pair_rec* h_records = nullptr;
@@ -165,7 +183,8 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev4) != cudaSuccess || cudaEventCreate(&ctx->ev5) != cudaSuccess) {
     int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
     return rc;
@@ -181,6 +200,18 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
                   cudaGetErrorString(cudaGetLastError()));
     lgmi_destroy(ctx);
     return rc;
+  }
+  {
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !ctx->encode_tiled ||
+        cudaFuncSetAttribute(k_gram_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmemBytes) !=
+            cudaSuccess) {
+      int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: tensor-core path unavailable (%s)",
+                    cudaGetErrorString(cudaGetLastError()));
+      lgmi_destroy(ctx);
+      return rc;
+    }
   }
   {
     std::vector<uint16_t> tab(kIjTabEntries);
@@ -213,6 +244,8 @@ extern "C" void lgmi_destroy(lgmi_t* ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev2) cudaEventDestroy(ctx->ev2);
   if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+  if (ctx->ev4) cudaEventDestroy(ctx->ev4);
+  if (ctx->ev5) cudaEventDestroy(ctx->ev5);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -244,6 +277,14 @@ extern "C" int lgmi_pinned_free(lgmi_t* ctx, void* ptr) {
 
 extern "C" uint64_t lgmi_launch_count(const lgmi_t* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int lgmi_set_dense_threshold(lgmi_t* ctx, uint32_t min_sites, uint32_t min_reads) {
+  if (!ctx) return LGMI_ERR_ARG;
+  if (min_sites < 2) return fail(ctx, LGMI_ERR_ARG, "lgmi_set_dense_threshold: min_sites must be >= 2");
+  ctx->dense_min_sites = min_sites;
+  ctx->dense_min_reads = min_reads;
+  return LGMI_OK;
+}
+
 // --------------------------------------------------------------------------- batch
 extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   if (!b) return;
@@ -270,6 +311,9 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   cudaFree(b->d_site_cnt);
   cudaFree(b->d_dense);
   cudaFree(b->d_unit_rec_off);
+  cudaFree(b->d_x);
+  cudaFree(b->d_gram);
+  cudaFree(b->d_tiles);
   cudaFreeHost(b->h_header);
   cudaFreeHost(b->h_records);
   cudaFreeHost(b->h_counts);
@@ -295,7 +339,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   std::vector<DevUnit> du(n_units);
   std::vector<FastItem> fast_items;
   std::vector<MeanItem> mean_items;
-  uint64_t dense = 0;
+  std::vector<DenseTile> dense_tiles;
+  uint64_t dense = 0, gram_words = 0, x_bytes = 0;
   for (uint32_t k = 0; k < n_units; ++k) {
     const lgmi_unit_desc& u = units[k];
     if (u.n_sites > 65535u) {
@@ -323,6 +368,38 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
     const uint32_t nit = np ? (uint32_t)((np + kPairsMax - 1) / kPairsMax) : 1u;
     d.n_items = nit;
     d.dense_off = ~0ull;
+    d.gram_off = kNoGram;
+    d.S_pad = 0;
+    d.pad = 0;
+    if (np && u.n_sites >= ctx->dense_min_sites && u.n_reads >= ctx->dense_min_reads) {
+      // tensor-core path: the unit's nine count matrices come from k_gram_i8
+      DensePlan pl;
+      pl.unit = k;
+      pl.S = u.n_sites;
+      pl.W = u.row_words;
+      pl.S_pad = (u.n_sites + (uint32_t)kDenseBN - 1u) / (uint32_t)kDenseBN * (uint32_t)kDenseBN;
+      pl.k_blocks = u.row_words * 32u / (uint32_t)kDenseBK;  // W is a multiple of 4: whole 128-read blocks
+      pl.plane_off = u.plane_off;
+      pl.gram_off = gram_words;
+      pl.tile_off = dense_tiles.size();
+      for (uint32_t a = 0; a < 3; ++a)
+        for (uint32_t bb = 0; bb < 3; ++bb)
+          for (uint32_t J = 0; J < pl.S_pad / (uint32_t)kDenseBN; ++J)
+            for (uint32_t I = 0; I < pl.S_pad / (uint32_t)kDenseBM; ++I) {
+              // some pair i < j inside the tile, both real sites
+              const uint32_t i_min = I * (uint32_t)kDenseBM;
+              const uint32_t j_max = std::min(J * (uint32_t)kDenseBN + (uint32_t)kDenseBN, pl.S) - 1u;
+              if (J * (uint32_t)kDenseBN >= pl.S || i_min >= j_max) continue;
+              dense_tiles.push_back(DenseTile{(uint16_t)a, (uint16_t)bb, (uint16_t)I, (uint16_t)J});
+            }
+      pl.n_tiles = (uint32_t)(dense_tiles.size() - pl.tile_off);
+      b->dense_macs += (uint64_t)pl.n_tiles * kDenseBM * kDenseBN * pl.k_blocks * kDenseBK;
+      gram_words += 9ull * pl.S_pad * pl.S_pad;
+      x_bytes = std::max<uint64_t>(x_bytes, 3ull * pl.S_pad * pl.k_blocks * kDenseBK);
+      d.gram_off = pl.gram_off;
+      d.S_pad = pl.S_pad;
+      b->dense_plans.push_back(pl);
+    }
     if (nit > 1) {
       d.dense_off = dense;
       dense += np;
@@ -385,6 +462,33 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   BCU(cudaMalloc(&b->d_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t)));
   BCU(cudaMalloc(&b->d_dense, std::max<uint64_t>(1, dense) * sizeof(double)));
   BCU(cudaMalloc(&b->d_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long)));
+  if (!b->dense_plans.empty()) {
+    BCU(cudaMalloc(&b->d_x, x_bytes));
+    BCU(cudaMemsetAsync(b->d_x, 0, x_bytes, ctx->stream));  // rows of the site padding stay zero
+    BCU(cudaMalloc(&b->d_gram, gram_words * sizeof(uint32_t)));
+    BCU(cudaMalloc(&b->d_tiles, dense_tiles.size() * sizeof(DenseTile)));
+    BCU(cudaMemcpyAsync(b->d_tiles, dense_tiles.data(), dense_tiles.size() * sizeof(DenseTile), cudaMemcpyHostToDevice,
+                        ctx->stream));
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeTiled encode = reinterpret_cast<EncodeTiled>(ctx->encode_tiled);
+    for (DensePlan& pl : b->dense_plans) {
+      // X of this unit: [3 * S_pad rows][K_pad bytes], K contiguous; box = 128 rows x 128 bytes, 128B swizzle
+      const cuuint64_t dims[2] = {(cuuint64_t)pl.k_blocks * kDenseBK, 3ull * pl.S_pad};
+      const cuuint64_t strides[1] = {(cuuint64_t)pl.k_blocks * kDenseBK};
+      const cuuint32_t box[2] = {(cuuint32_t)kDenseBK, 128u};
+      const cuuint32_t estr[2] = {1u, 1u};
+      const CUresult r = encode(&pl.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b->d_x, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        int rc__ = fail(ctx, LGMI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for unit %u", (int)r, pl.unit);
+        lgmi_batch_destroy(b);
+        return rc__;
+      }
+    }
+  }
   b->rec_cap = std::max<uint64_t>(1, b->n_candidates);
   BCU(cudaMalloc(&b->d_records, b->rec_cap * sizeof(lgmi_pair_rec)));
   BCU(cudaHostAlloc(&b->h_header, sizeof(Header), cudaHostAllocDefault));
@@ -460,6 +564,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   P.site_cnt = b->d_site_cnt;
   P.dense = b->d_dense;
   P.unit_rec_off = b->d_unit_rec_off;
+  P.gram = b->d_gram;
 
   CU(ctx, cudaMemsetAsync(b->d_header, 0, sizeof(Header), ctx->stream));
   CU(ctx, cudaMemsetAsync(b->d_unit_rec_off, 0, ((size_t)b->n_units + 1) * sizeof(unsigned long long), ctx->stream));
@@ -472,6 +577,25 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     k_fill_nan<<<(unsigned)((b->n_sites + 255) / 256), 256, 0, ctx->stream>>>(b->d_site_mean, b->d_site_cnt, b->n_sites);
     ++ctx->launches;
   }
+  CU(ctx, cudaEventRecord(ctx->ev4, ctx->stream));
+  for (const DensePlan& pl : b->dense_plans) {
+    // K3: bit-planes -> 0/1 bytes -> nine count matrices on the tensor cores
+    const uint64_t groups = 3ull * pl.S * pl.k_blocks * (kDenseBK / 16);
+    const unsigned egrid = (unsigned)std::min<uint64_t>((groups + 255) / 256, (uint64_t)ctx->num_sms * 16u);
+    k_expand_planes<<<egrid, 256, 0, ctx->stream>>>(b->d_planes + pl.plane_off, pl.S, pl.W, pl.S_pad, b->d_x);
+    ++ctx->launches;
+    DenseParams D;
+    D.tiles = b->d_tiles + pl.tile_off;
+    D.n_tiles = pl.n_tiles;
+    D.k_blocks = pl.k_blocks;
+    D.S_pad = pl.S_pad;
+    D.gram = b->d_gram + pl.gram_off;
+    D.error = reinterpret_cast<uint32_t*>(&b->d_header->pad);
+    const unsigned ggrid = (unsigned)std::min<uint32_t>(pl.n_tiles, (uint32_t)ctx->num_sms);
+    k_gram_i8<<<ggrid, kDenseThreads, kDenseSmemBytes, ctx->stream>>>(pl.tmap, D);
+    ++ctx->launches;
+  }
+  CU(ctx, cudaEventRecord(ctx->ev5, ctx->stream));
   if (b->n_items) {
     // K0 + scan: every item's place in the ordered output
     const unsigned cgrid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 8u);
@@ -541,6 +665,12 @@ static int fill_scalars(lgmi_batch* b, lgmi_result* out) {
   out->kernel_ms = ms;
   CU(ctx, cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
   out->pairs_kernel_ms = ms;
+  CU(ctx, cudaEventElapsedTime(&ms, ctx->ev4, ctx->ev5));
+  out->dense_kernel_ms = ms;
+  out->n_dense_units = (uint32_t)b->dense_plans.size();
+  out->dense_macs = b->dense_macs;
+  if (b->h_header->pad)
+    return fail(ctx, LGMI_ERR_CUDA, "k_gram_i8: a pipeline barrier timed out (tensor-core path)");
   return LGMI_OK;
 }
 

@@ -19,6 +19,7 @@
 #include "../../include/lgmi.h"
 #include "lgmi_math.cuh"
 #include "lgmi_fast_kernel.cuh"
+#include "lgmi_dense.cuh"
 
 namespace lgmi {
 
@@ -28,9 +29,12 @@ constexpr int kPairsMax = 2048; // pairs per work item (>= 64*63/2: a 64-site un
 struct DevUnit {
   uint64_t plane_off;  // words
   uint64_t dense_off;  // first slot in the dense MI scratch (multi-item units), else ~0
+  uint64_t gram_off;   // first word of the unit's nine count matrices (tensor-core path), else ~0
   uint32_t S, R, W, site_off;
   uint32_t first_item, n_items;
+  uint32_t S_pad, pad;
 };
+constexpr uint64_t kNoGram = ~0ull;
 
 enum : uint32_t { ITEM_FIRST = 1u, ITEM_SINGLE = 2u, ITEM_FAST = 4u };
 
@@ -61,6 +65,7 @@ struct RunParams {
   const unsigned long long* item_off;  // exclusive scan of item_cnt, n_items + 1 entries
   uint8_t* item_dense;                 // k_count: fast-eligible item with > kOthCap "other" reads at a site
   uint32_t* n_generic;                 // items k_pairs_generic has to process (host count + dense ones)
+  const uint32_t* gram;                // count matrices of the tensor-core path (DevUnit::gram_off)
   Header* header;
   lgmi_pair_rec* records;
   uint32_t* counts;
@@ -134,6 +139,20 @@ __device__ __forceinline__ bool pair_table(const uint4* __restrict__ ri, const u
   return false;
 }
 
+// 3x3 table of pair (i, j) from the Gram matrices of the tensor-core path; returns N
+__device__ __forceinline__ uint32_t gram_table(const uint32_t* __restrict__ g, uint32_t S_pad, uint32_t i, uint32_t j,
+                                               uint32_t T[9]) {
+  const size_t plane = (size_t)S_pad * S_pad;
+  const uint32_t* p = g + (size_t)i * S_pad + j;
+  uint32_t n = 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    T[k] = __ldg(p + (size_t)k * plane);
+    n += T[k];
+  }
+  return n;
+}
+
 // ---------------------------------------------------------------------------
 // K1 + K2, generic path: up to 2048 consecutive pairs of any unit per work item,
 // one thread per pair, planes read through L1/L2.  Handles everything the
@@ -170,7 +189,14 @@ __global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
       if (skip_nonhet)
         evaluate = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
                    ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
-      if (evaluate) {
+      if (evaluate && u.gram_off != kNoGram) {
+        uint32_t T[9];
+        const uint32_t n_common = gram_table(P.gram + u.gram_off, u.S_pad, i, j, T);
+        if ((int)n_common >= P.min_common) {
+          if ((T[0] | T[1] | T[2] | T[3] | T[6]) == 0u) mi = lg_mi_from_2x2(T[4], T[5], T[7], T[8], ln);
+          else mi = lg_mi_from_table(T, ln);
+        }
+      } else if (evaluate) {
         const uint4* ri = base + (size_t)i * 3u * W4;
         const uint4* rj = base + (size_t)j * 3u * W4;
         const uint32_t n_common = pair_common(ri, rj, W4);
@@ -225,10 +251,14 @@ __global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
         rec.w = (uint32_t)__double2hiint(mi);
         reinterpret_cast<uint4*>(P.records)[slot] = rec;
         if (P.mode & LGMI_MODE_EMIT_COUNTS) {
-          const uint4* ri = base + (size_t)(ij >> 16) * 3u * W4;
-          const uint4* rj = base + (size_t)(ij & 0xffffu) * 3u * W4;
           uint32_t T[9];
-          pair_table(ri, rj, W4, pair_common(ri, rj, W4), T);
+          if (u.gram_off != kNoGram) {
+            gram_table(P.gram + u.gram_off, u.S_pad, ij >> 16, ij & 0xffffu, T);
+          } else {
+            const uint4* ri = base + (size_t)(ij >> 16) * 3u * W4;
+            const uint4* rj = base + (size_t)(ij & 0xffffu) * 3u * W4;
+            pair_table(ri, rj, W4, pair_common(ri, rj, W4), T);
+          }
 #pragma unroll
           for (int k = 0; k < 9; ++k) P.counts[slot * 9ull + k] = T[k];
         }
@@ -351,7 +381,13 @@ __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
         const bool het = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
                          ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
         if (!het && (het_only || skip_nonhet)) continue;
-        const uint32_t n = pair_common(base + (size_t)i * 3u * W4, base + (size_t)j * 3u * W4, W4);
+        uint32_t n;
+        if (u.gram_off != kNoGram) {
+          uint32_t T[9];
+          n = gram_table(P.gram + u.gram_off, u.S_pad, i, j, T);
+        } else {
+          n = pair_common(base + (size_t)i * 3u * W4, base + (size_t)j * 3u * W4, W4);
+        }
         mine += ((int)n >= P.min_common) ? 1u : 0u;
       }
     }

@@ -241,6 +241,52 @@ def test_many_sites_multi_item_unit(lg, gpu_ctx):
     check_batch(lg, gpu_ctx, [small, eu, small], 6)
 
 
+# --------------------------------------------------------------------------- tensor-core path (K3)
+def _synth_unit(rng, S, R, cov):
+    a, k = synth.draw_alleles(rng, 1, S, R, cov)
+    return enc.EncodedUnit([1000 + 37 * s for s in range(S)],
+                           [("mismatch", "snp", "het_snp")[int(x)] for x in k[0]], synth.labels_from_alleles(a[0]))
+
+
+@pytest.fixture()
+def dense_everything(gpu_ctx):
+    """Every unit with a pair goes through k_expand_planes + k_gram_i8."""
+    gpu_ctx.set_dense_threshold(2, 1)
+    yield gpu_ctx
+    gpu_ctx.set_dense_threshold(512, 8192)
+
+
+def test_dense_path_small_shapes(lg, dense_everything):
+    """int8 tcgen05 Gram kernel forced onto small and ragged units: one tile, several
+    tiles per plane pair, S and R off every block boundary, third alleles present.
+    Counts bit-exact against the oracle, MI within tolerance, same records as the
+    popcount path."""
+    ctx = dense_everything
+    rng = np.random.default_rng(31)
+    shapes = [(2, 6), (3, 127), (70, 300), (129, 129), (257, 1000), (300, 90), (513, 260)]
+    eus = [_synth_unit(rng, S, R, float(rng.uniform(0.3, 0.9))) for S, R in shapes]
+    for mc in (1, 6):
+        full = check_batch(lg, ctx, eus, mc)
+        assert full.n_dense_units == len(eus) and full.dense_macs > 0
+    dense = lg.mi_step_batched(lg.pack_units(eus), 6, lg.MODE_ALL_PAIRS | lg.MODE_EMIT_COUNTS, ctx=ctx)
+    ctx.set_dense_threshold(1 << 20, 1 << 30)
+    popc = lg.mi_step_batched(lg.pack_units(eus), 6, lg.MODE_ALL_PAIRS | lg.MODE_EMIT_COUNTS, ctx=ctx)
+    assert popc.n_dense_units == 0
+    assert np.array_equal(dense.records, popc.records) and np.array_equal(dense.counts, popc.counts)
+    assert np.array_equal(dense.site_mean, popc.site_mean, equal_nan=True)
+
+
+def test_dense_path_deep_unit(lg, gpu_ctx):
+    """A unit over the default threshold (520 sites x 12 000 reads) mixed with small
+    units in one batch: the deep one takes the tensor cores, the others do not."""
+    rng = np.random.default_rng(32)
+    deep = _synth_unit(rng, 520, 12000, 0.6)
+    small = [_synth_unit(rng, 40, 150, 0.5) for _ in range(3)]
+    full = check_batch(lg, gpu_ctx, [small[0], deep, small[1], small[2]], 6, min_exact=0.9)
+    assert full.n_dense_units == 1
+    assert full.dense_kernel_ms > 0.0
+
+
 # --------------------------------------------------------------------------- full-size properties (cfg2)
 @pytest.fixture(scope="module")
 def cfg2(lg):

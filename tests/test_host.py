@@ -6,6 +6,7 @@ import ctypes
 import os
 import re
 import subprocess
+import tempfile
 import sys
 
 import numpy as np
@@ -50,7 +51,18 @@ def test_abi_struct_layouts(lg):
     L = importlib_lib()
     assert L.UNIT_DESC.itemsize == 24 and L.UNIT_DESC.fields["site_off"][1] == 20
     assert L.PAIR_REC.itemsize == 16 and L.PAIR_REC.fields["mi"][1] == 8
-    assert ctypes.sizeof(L.Result) == 80
+    assert ctypes.sizeof(L.Result) == 96
+    # ... and the C compiler agrees with the ctypes mirror, field by field
+    fields = [f[0] for f in L.Result._fields_]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "lgmi.h"\nint main(void){printf("%zu", sizeof(lgmi_result));' + \
+        "".join('printf(" %%zu", offsetof(lgmi_result, %s));' % f for f in fields) + "return 0;}"
+    with tempfile.TemporaryDirectory() as tmp:
+        src, exe = os.path.join(tmp, "abi.c"), os.path.join(tmp, "abi")
+        with open(src, "w") as fh:
+            fh.write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [ctypes.sizeof(L.Result)] + [getattr(L.Result, f).offset for f in fields]
 
 
 def test_version_and_pure_host_entry_points(lg):
