@@ -39,6 +39,7 @@ if ROOT not in sys.path:
 METRIC = "site-pairs MI/sec"
 UNIT = "site-pairs/s"
 CFG = dict(units=20000, sites=50, reads=200, cov=0.5, min_common=6, seed=20261020)
+CFG3 = dict(sites=2000, reads=100000, cov=0.6, min_common=6, seed=20261021)
 CHUNK = 500
 L2_FLUSH_BYTES = 512 << 20
 
@@ -180,6 +181,80 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# --------------------------------------------------------------------------- deep unit (cfg3), tensor-core path
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    except OSError:
+        return {}, "fallback (B200_PROFILING.md)"
+
+
+def int8_library_tops(torch):
+    """cuBLASLt int8 GEMM 8192^3 through torch._int_mm, best of 10: context for the int8 peak."""
+    try:
+        a = torch.randint(-4, 4, (8192, 8192), dtype=torch.int8, device="cuda")
+        b = torch.randint(-4, 4, (8192, 8192), dtype=torch.int8, device="cuda").t()
+        for _ in range(3):
+            torch._int_mm(a, b)
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+    except Exception:                                        # noqa: BLE001 (context figure only)
+        return None
+
+
+def dense_leg(lg, synth, ctx, torch, stream, steps, warmup, flush):
+    """BASELINE.json configs[2]: one unit of 2 000 sites x 100 000 reads through
+    k_expand_planes + k_gram_i8 (int8 tcgen05) + the MI epilogue kernels."""
+    S, R, mc = CFG3["sites"], CFG3["reads"], CFG3["min_common"]
+    pb, _ = synth.make_deep_unit(CFG3["seed"], S, R, CFG3["cov"])
+    batch = lg.Batch(ctx, pb)
+    batch.upload()
+    for _ in range(warmup):
+        batch.run(mc, lg.MODE_ALL_PAIRS)
+    res = batch.sync()
+    assert int(res.n_dense_units) == 1, "cfg3 must take the tensor-core path"
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    gram_ms, dense_ms = [], []
+    for k in range(steps):
+        flush.zero_()
+        ev[k][0].record(stream)
+        batch.run(mc, lg.MODE_ALL_PAIRS)
+        ev[k][1].record(stream)
+        r = batch.sync()
+        gram_ms.append(float(r.gram_kernel_ms))
+        dense_ms.append(float(r.dense_kernel_ms))
+    step_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    pairs = S * (S - 1) // 2
+    algo_ops = 2 * 9 * pairs * R                             # SURVEY 8d: nine count matrices over the upper triangle
+    g_ms = sum(gram_ms) / len(gram_ms)
+    peaks, src = load_peaks()
+    bf16 = float(peaks.get("bf16_tflops", 1590.0))
+    peak = 2.0 * bf16                                        # int8 dense = 2x bf16 dense on sm_100
+    out = {
+        "workload": "cfg3: 1 unit x %d sites x %d reads, cov %g, mi_min_common_read %d" % (S, R, CFG3["cov"], mc),
+        "pairs_per_step": pairs, "surviving_pairs": int(r.n_records), "ms_per_step": step_ms,
+        "value": pairs / (step_ms * 1e-3), "unit": UNIT,
+        "roofline": {"bound": "tensor", "achieved": algo_ops / (g_ms * 1e-3) / 1e12, "peak": peak, "unit": "TOP/s",
+                     "frac": algo_ops / (g_ms * 1e-3) / 1e12 / peak, "traffic": None, "kernel": "k_gram_i8",
+                     "kernel_ms": g_ms, "algorithmic_ops": algo_ops, "issued_ops": 2 * int(r.gram_macs),
+                     "issued_tops": 2 * int(r.gram_macs) / (g_ms * 1e-3) / 1e12,
+                     "peak_source": "2 x bf16_tflops burst, %s" % src,
+                     "library_int8_tops": int8_library_tops(torch),
+                     "kernel_share_of_step": g_ms / step_ms},
+        "expand_plus_gram_ms": sum(dense_ms) / len(dense_ms),
+    }
+    batch.close()
+    return out
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import numpy as np
@@ -209,6 +284,10 @@ def run_gpu(args):
     torch.cuda.set_stream(stream)                            # "library's own stream" to lgmi_set_stream
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)                       # torch.cuda.Event sees the library's launches
+    if args.dense_only:
+        flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        print(json.dumps({"dense": dense_leg(lg, synth, ctx, torch, stream, args.steps, args.warmup, flush)}), flush=True)
+        return 0
 
     # this rank's shard: LPT over the global unit list (equal costs -> equal bins); its data by seed
     G = CFG["units"]
@@ -314,6 +393,9 @@ def run_gpu(args):
             traffic = None
 
     cpu = None if args.no_cpu_baseline else cpu_baseline()
+    dense = None
+    if world == 1 and not args.no_dense:
+        dense = dense_leg(lg, synth, ctx, torch, stream, max(3, min(args.steps, 5)), 3, flush)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -334,6 +416,8 @@ def run_gpu(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if dense is not None:
+        line["dense"] = dense
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -352,6 +436,8 @@ def main():
     ap.add_argument("--impl", choices=["graft", "reference"], default="graft")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
+    ap.add_argument("--no-dense", action="store_true", help="skip the cfg3 deep-unit (tensor-core) leg")
+    ap.add_argument("--dense-only", action="store_true", help="profiling runs: only the cfg3 deep-unit leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
     if args.impl == "reference":

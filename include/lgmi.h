@@ -139,6 +139,9 @@ typedef struct {
                                 /* (plane expansion + int8 Gram kernel)        */
   uint32_t n_dense_units;       /* units that took the tensor-core path        */
   uint64_t dense_macs;          /* int8 multiply-accumulates issued for them   */
+  float gram_kernel_ms;         /* k_gram_i8 of the last such unit, alone      */
+  uint32_t reserved;
+  uint64_t gram_macs;           /* multiply-accumulates of that launch         */
 } lgmi_result;
 
 typedef struct lgmi_ctx lgmi_t;

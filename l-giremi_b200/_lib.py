@@ -58,6 +58,9 @@ class Result(C.Structure):
         ("dense_kernel_ms", C.c_float),
         ("n_dense_units", C.c_uint32),
         ("dense_macs", C.c_uint64),
+        ("gram_kernel_ms", C.c_float),
+        ("reserved", C.c_uint32),
+        ("gram_macs", C.c_uint64),
     ]
 
 

@@ -111,6 +111,8 @@ class StepResult:
         self.dense_kernel_ms = float(res.dense_kernel_ms)
         self.n_dense_units = int(res.n_dense_units)
         self.dense_macs = int(res.dense_macs)
+        self.gram_kernel_ms = float(res.gram_kernel_ms)
+        self.gram_macs = int(res.gram_macs)
         rec = array_at(res.records, PAIR_REC, self.n_records)
         mean = array_at(res.site_mean, np.float64, int(res.n_sites))
         cnt = array_at(res.site_cnt, np.uint32, int(res.n_sites))

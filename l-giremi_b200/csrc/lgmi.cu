@@ -50,7 +50,7 @@ struct lgmi_ctx {
   // tensor-core path: units at least this large build their tables with k_gram_i8
   uint32_t dense_min_sites = 512, dense_min_reads = 8192;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
-  cudaEvent_t ev4 = nullptr, ev5 = nullptr;
+  cudaEvent_t ev4 = nullptr, ev5 = nullptr, ev6 = nullptr, ev7 = nullptr;
 };
 
 // one unit of the tensor-core path
@@ -184,7 +184,8 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
       cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev4) != cudaSuccess || cudaEventCreate(&ctx->ev5) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev4) != cudaSuccess || cudaEventCreate(&ctx->ev5) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev6) != cudaSuccess || cudaEventCreate(&ctx->ev7) != cudaSuccess) {
     int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
     return rc;
@@ -246,6 +247,8 @@ extern "C" void lgmi_destroy(lgmi_t* ctx) {
   if (ctx->ev3) cudaEventDestroy(ctx->ev3);
   if (ctx->ev4) cudaEventDestroy(ctx->ev4);
   if (ctx->ev5) cudaEventDestroy(ctx->ev5);
+  if (ctx->ev6) cudaEventDestroy(ctx->ev6);
+  if (ctx->ev7) cudaEventDestroy(ctx->ev7);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -592,7 +595,10 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     D.gram = b->d_gram + pl.gram_off;
     D.error = reinterpret_cast<uint32_t*>(&b->d_header->pad);
     const unsigned ggrid = (unsigned)std::min<uint32_t>(pl.n_tiles, (uint32_t)ctx->num_sms);
+    const bool last = &pl == &b->dense_plans.back();
+    if (last) CU(ctx, cudaEventRecord(ctx->ev6, ctx->stream));
     k_gram_i8<<<ggrid, kDenseThreads, kDenseSmemBytes, ctx->stream>>>(pl.tmap, D);
+    if (last) CU(ctx, cudaEventRecord(ctx->ev7, ctx->stream));
     ++ctx->launches;
   }
   CU(ctx, cudaEventRecord(ctx->ev5, ctx->stream));
@@ -667,6 +673,12 @@ static int fill_scalars(lgmi_batch* b, lgmi_result* out) {
   out->pairs_kernel_ms = ms;
   CU(ctx, cudaEventElapsedTime(&ms, ctx->ev4, ctx->ev5));
   out->dense_kernel_ms = ms;
+  if (!b->dense_plans.empty()) {
+    CU(ctx, cudaEventElapsedTime(&ms, ctx->ev6, ctx->ev7));
+    out->gram_kernel_ms = ms;
+    const DensePlan& pl = b->dense_plans.back();
+    out->gram_macs = (uint64_t)pl.n_tiles * kDenseBM * kDenseBN * pl.k_blocks * kDenseBK;
+  }
   out->n_dense_units = (uint32_t)b->dense_plans.size();
   out->dense_macs = b->dense_macs;
   if (b->h_header->pad)

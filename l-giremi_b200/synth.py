@@ -226,3 +226,18 @@ def make_heavy_tail(seed, G, cov=0.5, keep_raw=False, **shape_kw):
             raw.append((a[0], k[0]))
     pb = PlaneBatch(units, np.concatenate(chunks), np.concatenate(flags))
     return pb, raw
+
+
+def make_deep_unit(seed, S, R, cov, keep_labels=False):
+    """One deep unit (cfg3: 2 000 sites x 100 000 reads) from the same per-unit model.
+    Returns (PlaneBatch, labels or None)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a, k = draw_alleles(rng, 1, S, R, cov)
+    lab = labels_from_alleles(a[0])
+    del a
+    W = row_words(R)
+    units = np.zeros(1, dtype=UNIT_DESC)
+    units[0] = (0, S, R, W, 0)
+    flags = site_flag_bytes([SITE_TYPE_NAMES[int(x)] for x in k[0]], lab)
+    pb = PlaneBatch(units, pack_labels(lab).reshape(-1), flags)
+    return pb, (lab if keep_labels else None)

@@ -287,6 +287,38 @@ def test_dense_path_deep_unit(lg, gpu_ctx):
     assert full.dense_kernel_ms > 0.0
 
 
+def test_cfg3_full_size_dense_equals_popcount_and_oracle(lg, gpu_ctx):
+    """BASELINE.json configs[2] at full size (2 000 sites x 100 000 reads, 1 999 000 pairs):
+    the tensor-core path and the popcount path give the same records, tables and means
+    bit for bit, and a random sub-unit of 20 sites matches the oracle."""
+    pb, lab = synth.make_deep_unit(20261021, 2000, 100000, 0.6, keep_labels=True)
+    mode = lg.MODE_ALL_PAIRS | lg.MODE_EMIT_COUNTS
+    dense = lg.mi_step_batched(pb, 6, mode, ctx=gpu_ctx)
+    assert dense.n_dense_units == 1 and dense.n_candidates == 1_999_000
+    gpu_ctx.set_dense_threshold(1 << 20, 1 << 30)
+    try:
+        popc = lg.mi_step_batched(pb, 6, mode, ctx=gpu_ctx)
+    finally:
+        gpu_ctx.set_dense_threshold(512, 8192)
+    assert popc.n_dense_units == 0
+    assert np.array_equal(dense.records, popc.records)
+    assert np.array_equal(dense.counts, popc.counts)
+    assert np.array_equal(dense.site_mean, popc.site_mean, equal_nan=True)
+    assert np.array_equal(dense.site_cnt, popc.site_cnt)
+    # every table sums to the pair's common-read count and the marginals are consistent
+    rec = dense.records
+    assert np.all(dense.counts.sum(axis=1) >= 6)
+    key = rec['i'].astype(np.int64) * 65536 + rec['j']
+    assert np.all(np.diff(key) > 0)
+    rng = np.random.default_rng(9)
+    idx = np.sort(rng.choice(2000, 20, replace=False))
+    i, j, mi, tab = c_oracle.unit_pairs_from_labels(signed(lab[idx]), None, 6)
+    at = np.searchsorted(key, idx[i].astype(np.int64) * 65536 + idx[j])
+    assert np.array_equal(key[at], idx[i].astype(np.int64) * 65536 + idx[j])      # same pairs survive
+    assert np.array_equal(dense.counts[at].astype(np.int64), tab)
+    assert_mi_close(rec['mi'][at], mi, 0.9)
+
+
 # --------------------------------------------------------------------------- full-size properties (cfg2)
 @pytest.fixture(scope="module")
 def cfg2(lg):
