@@ -406,7 +406,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
     if (nit > 1) {
       d.dense_off = dense;
       dense += np;
-      for (uint32_t s0 = 0; s0 < u.n_sites; s0 += 128) mean_items.push_back(MeanItem{k, s0});
+      for (uint32_t s0 = 0; s0 < u.n_sites; s0 += (uint32_t)kMeanSites) mean_items.push_back(MeanItem{k, s0});
     }
     for (uint32_t t = 0; t < nit; ++t) {
       Item it;
@@ -647,7 +647,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     ++ctx->launches;
   }
   if (b->n_mean_items) {
-    k_site_mean_dense<<<b->n_mean_items, 128, 0, ctx->stream>>>(b->d_units, b->d_mean_items, b->d_flags, b->d_dense,
+    k_site_mean_dense<<<b->n_mean_items, kMeanSites * 32, 0, ctx->stream>>>(b->d_units, b->d_mean_items, b->d_flags, b->d_dense,
                                                               b->d_site_mean, b->d_site_cnt);
     ++ctx->launches;
   }

@@ -405,35 +405,49 @@ __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
 }
 
 // Per-site mean for units whose pairs span several work items; reads the dense
-// per-unit MI scratch written by k_pairs.  One thread per site.
+// per-unit MI scratch written by k_pairs_generic.  One WARP per site: the lanes
+// fetch 32 partners' MI at a time (coalesced for partners above the site), then
+// the compensated sum runs over them in partner order -- the order is part of
+// the result (mutual_information.py:56-58 is a left-to-right float sum), so the
+// additions stay serial while the loads do not.
+constexpr int kMeanSites = 8;  // sites (= warps) per CTA
 struct MeanItem {
   uint32_t unit;
   uint32_t site_begin;
 };
-__global__ void __launch_bounds__(128) k_site_mean_dense(const DevUnit* __restrict__ units,
-                                                         const MeanItem* __restrict__ items,
-                                                         const uint8_t* __restrict__ site_flags,
-                                                         const double* __restrict__ dense,
-                                                         double* __restrict__ site_mean,
-                                                         uint32_t* __restrict__ site_cnt) {
+__global__ void __launch_bounds__(kMeanSites * 32) k_site_mean_dense(const DevUnit* __restrict__ units,
+                                                                    const MeanItem* __restrict__ items,
+                                                                    const uint8_t* __restrict__ site_flags,
+                                                                    const double* __restrict__ dense,
+                                                                    double* __restrict__ site_mean,
+                                                                    uint32_t* __restrict__ site_cnt) {
   const MeanItem mi = items[blockIdx.x];
   const DevUnit u = units[mi.unit];
-  const uint32_t s = mi.site_begin + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t s = mi.site_begin + (threadIdx.x >> 5);
   if (s >= u.S) return;
-  const uint8_t* flags = site_flags + u.site_off;
-  const double* d = dense + u.dense_off;
+  const uint8_t* __restrict__ flags = site_flags + u.site_off;
+  const double* __restrict__ d = dense + u.dense_off;
   const bool s_het = (flags[s] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
+  const uint64_t row_s = lg_row_off(s, u.S);
   lg_neumaier acc;
   lg_neumaier_init(acc);
-  for (uint32_t t = 0; t < u.S; ++t) {
-    if (t == s) continue;
-    if (!s_het && (flags[t] & LGMI_SITE_TYPE_MASK) != LGMI_SITE_HET_SNP) continue;
-    const uint64_t p = (t < s) ? lg_row_off(t, u.S) + (s - t - 1u) : lg_row_off(s, u.S) + (t - s - 1u);
-    const double v = d[p];
-    if (!isnan(v)) lg_neumaier_add(acc, v);
+  for (uint32_t t0 = 0; t0 < u.S; t0 += 32u) {
+    const uint32_t t = t0 + lane;
+    double v = lg_nan();
+    if (t < u.S && t != s && (s_het || (flags[t] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP))
+      v = d[(t < s) ? lg_row_off(t, u.S) + (s - t - 1u) : row_s + (t - s - 1u)];
+    uint32_t have = __ballot_sync(0xffffffffu, !isnan(v));
+    while (have) {  // ascending partner order; every lane carries the same accumulator
+      const int k = __ffs((int)have) - 1;
+      have &= have - 1u;
+      lg_neumaier_add(acc, __shfl_sync(0xffffffffu, v, k));
+    }
   }
-  site_mean[u.site_off + s] = lg_neumaier_mean(acc);
-  site_cnt[u.site_off + s] = (uint32_t)acc.n;
+  if (lane == 0) {
+    site_mean[u.site_off + s] = lg_neumaier_mean(acc);
+    site_cnt[u.site_off + s] = (uint32_t)acc.n;
+  }
 }
 
 // sites of units without any pair (S < 2): mean = NaN, cnt = 0
