@@ -164,7 +164,7 @@ LGMI_API uint64_t lgmi_launch_count(const lgmi_t* ctx);
 /* Units with n_sites >= min_sites and n_reads >= min_reads build their        *
  * contingency counts as a dense int8 contraction on the tensor cores          *
  * (tcgen05 / TMEM / TMA) instead of AND+popcount; same counts, bit for bit    *
- * (mutual_information.py:15-40).  Default 512 sites x 8192 reads; applies to  *
+ * (mutual_information.py:15-40).  Default 48 sites x 8192 reads; applies to   *
  * batches created afterwards.  Tests lower it to force the path.              */
 LGMI_API int lgmi_set_dense_threshold(lgmi_t* ctx, uint32_t min_sites, uint32_t min_reads);
 

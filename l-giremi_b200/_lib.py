@@ -31,6 +31,7 @@ MODE_EMIT_COUNTS = 0x2
 MODE_SKIP_NONHET = 0x4
 
 ERR_NODEVICE = -5
+DENSE_DEFAULT = (48, 8192)    # lgmi_set_dense_threshold defaults: (min_sites, min_reads)
 
 EXPORTS = (
     "lgmi_version", "lgmi_create", "lgmi_destroy", "lgmi_last_error", "lgmi_set_stream",

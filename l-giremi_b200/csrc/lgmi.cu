@@ -48,7 +48,7 @@ struct lgmi_ctx {
   int num_sms = 0;
   int pairs_ctas_per_sm = 0;
   // tensor-core path: units at least this large build their tables with k_gram_i8
-  uint32_t dense_min_sites = 512, dense_min_reads = 8192;
+  uint32_t dense_min_sites = 48, dense_min_reads = 8192;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
   cudaEvent_t ev4 = nullptr, ev5 = nullptr, ev6 = nullptr, ev7 = nullptr;
 };
@@ -95,6 +95,11 @@ struct lgmi_batch {
   uint32_t* d_gram = nullptr;   // nine count matrices per dense unit
   DenseTile* d_tiles = nullptr;
   uint64_t dense_macs = 0;      // multiply-accumulates the tile lists amount to
+  // tiled popcount path
+  TileItem* d_tile_items = nullptr;
+  uint32_t n_tile_items = 0;
+  uint32_t* d_tile_counts = nullptr;  // EMIT_COUNTS only, allocated on first use
+  uint64_t n_tiled_slots = 0;
   // host (pinned) mirrors
   Header* h_header = nullptr;
   lgmi_pair_rec* h_records = nullptr;
@@ -317,6 +322,8 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   cudaFree(b->d_x);
   cudaFree(b->d_gram);
   cudaFree(b->d_tiles);
+  cudaFree(b->d_tile_items);
+  cudaFree(b->d_tile_counts);
   cudaFreeHost(b->h_header);
   cudaFreeHost(b->h_records);
   cudaFreeHost(b->h_counts);
@@ -343,6 +350,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   std::vector<FastItem> fast_items;
   std::vector<MeanItem> mean_items;
   std::vector<DenseTile> dense_tiles;
+  std::vector<TileItem> tile_items;
+  std::vector<uint32_t> tile_words;  // W of each tile's unit (launch order: longest first)
   uint64_t dense = 0, gram_words = 0, x_bytes = 0;
   for (uint32_t k = 0; k < n_units; ++k) {
     const lgmi_unit_desc& u = units[k];
@@ -373,7 +382,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
     d.dense_off = ~0ull;
     d.gram_off = kNoGram;
     d.S_pad = 0;
-    d.pad = 0;
+    d.tiled = 0;
     if (np && u.n_sites >= ctx->dense_min_sites && u.n_reads >= ctx->dense_min_reads) {
       // tensor-core path: the unit's nine count matrices come from k_gram_i8
       DensePlan pl;
@@ -402,6 +411,19 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       d.gram_off = pl.gram_off;
       d.S_pad = pl.S_pad;
       b->dense_plans.push_back(pl);
+    } else if (np && !(nit == 1 && u.n_sites <= (uint32_t)kFastMaxS && u.n_reads <= (uint32_t)kFastMaxR)) {
+      // tiled popcount path: MI of every pair precomputed by k_tile_mi into the dense scratch
+      d.tiled = 1;
+      if (nit == 1) {
+        d.dense_off = dense;
+        dense += np;
+      }
+      const uint32_t nb = (u.n_sites + (uint32_t)kTileSites - 1u) / (uint32_t)kTileSites;
+      for (uint32_t I = 0; I < nb; ++I)
+        for (uint32_t J = I; J < nb; ++J) {
+          tile_items.push_back(TileItem{k, (uint16_t)I, (uint16_t)J});
+          tile_words.push_back(u.row_words);
+        }
     }
     if (nit > 1) {
       d.dense_off = dense;
@@ -430,6 +452,17 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       b->h_items.push_back(it);
     }
   }
+  {
+    // the deepest tiles first: CTAs are handed out in order, so the long ones do not end up in the tail
+    std::vector<uint32_t> order(tile_items.size());
+    for (uint32_t t = 0; t < order.size(); ++t) order[t] = t;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return tile_words[x] > tile_words[y]; });
+    std::vector<TileItem> sorted(tile_items.size());
+    for (uint32_t t = 0; t < order.size(); ++t) sorted[t] = tile_items[order[t]];
+    tile_items.swap(sorted);
+  }
+  b->n_tile_items = (uint32_t)tile_items.size();
+
   b->n_items = (uint32_t)b->h_items.size();
   b->n_fast = (uint32_t)fast_items.size();
   b->n_mean_items = (uint32_t)mean_items.size();
@@ -465,6 +498,11 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   BCU(cudaMalloc(&b->d_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t)));
   BCU(cudaMalloc(&b->d_dense, std::max<uint64_t>(1, dense) * sizeof(double)));
   BCU(cudaMalloc(&b->d_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long)));
+  if (!tile_items.empty()) {
+    BCU(cudaMalloc(&b->d_tile_items, tile_items.size() * sizeof(TileItem)));
+    BCU(cudaMemcpyAsync(b->d_tile_items, tile_items.data(), tile_items.size() * sizeof(TileItem), cudaMemcpyHostToDevice,
+                        ctx->stream));
+  }
   if (!b->dense_plans.empty()) {
     BCU(cudaMalloc(&b->d_x, x_bytes));
     BCU(cudaMemsetAsync(b->d_x, 0, x_bytes, ctx->stream));  // rows of the site padding stay zero
@@ -545,6 +583,10 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     CU(ctx, cudaMalloc(&b->d_counts, b->rec_cap * 9ull * sizeof(uint32_t)));
     b->counts_cap = b->rec_cap;
   }
+  if ((mode & LGMI_MODE_EMIT_COUNTS) && b->n_tile_items && !b->d_tile_counts) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaMalloc(&b->d_tile_counts, std::max<uint64_t>(1, b->n_dense) * 9ull * sizeof(uint32_t)));
+  }
   RunParams P;
   P.units = b->d_units;
   P.items = b->d_items;
@@ -568,6 +610,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   P.dense = b->d_dense;
   P.unit_rec_off = b->d_unit_rec_off;
   P.gram = b->d_gram;
+  P.tile_counts = b->d_tile_counts;
 
   CU(ctx, cudaMemsetAsync(b->d_header, 0, sizeof(Header), ctx->stream));
   CU(ctx, cudaMemsetAsync(b->d_unit_rec_off, 0, ((size_t)b->n_units + 1) * sizeof(unsigned long long), ctx->stream));
@@ -602,6 +645,12 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     ++ctx->launches;
   }
   CU(ctx, cudaEventRecord(ctx->ev5, ctx->stream));
+  if (b->n_tile_items) {
+    // K1 + K2 of the medium units: counts + MI per 16 x 16 block of site pairs
+    const unsigned tgrid = (unsigned)std::min<uint64_t>(b->n_tile_items, (uint64_t)ctx->num_sms * 3u);
+    k_tile_mi<<<tgrid, kThreads, 0, ctx->stream>>>(P, b->d_tile_items, b->n_tile_items);
+    ++ctx->launches;
+  }
   if (b->n_items) {
     // K0 + scan: every item's place in the ordered output
     const unsigned cgrid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 8u);

@@ -310,14 +310,17 @@ __device__ __forceinline__ void fast_emit_counts(const FastParams& P, FastSmem& 
 struct MeanAcc {
   double s, c;
   uint32_t n;
+  // branch-free so that the loop unrolls and the loads run ahead of the serial sum: a pair
+  // without MI (NaN pattern) adds +0.0, which leaves s and c as they are (s, c >= +0.0)
   __device__ __forceinline__ void add(const double* __restrict__ s_mi, uint32_t p) {
-    const double x = s_mi[p];
-    if (__double2hiint(x) >= 0x7ff00000) return;  // NaN pattern: no MI for this pair
+    const double v = s_mi[p];
+    const bool have = __double2hiint(v) < 0x7ff00000;
+    const double x = have ? v : 0.0;
     const double t = __dadd_rn(s, x);
     const double big = (s >= x) ? s : x, small = (s >= x) ? x : s;
     c = __dadd_rn(c, __dadd_rn(__dsub_rn(big, t), small));
     s = t;
-    ++n;
+    n += have ? 1u : 0u;
   }
 };
 
@@ -331,15 +334,18 @@ __device__ __forceinline__ void fast_means(const FastParams& P, FastSmem& sm, co
   if (tid < n_het) {
     s = sm.het_list[tid];
     uint32_t p = s - 1u;  // pair (t, s) for t = 0; the next one is S - t - 2 further
+#pragma unroll 4
     for (uint32_t t = 0; t < s; ++t) {
       acc.add(s_mi, p);
       p += S - t - 2u;
     }
     p = (s * (2u * S - s - 1u)) >> 1;  // pair (s, s + 1)
+#pragma unroll 4
     for (uint32_t t = s + 1u; t < S; ++t, ++p) acc.add(s_mi, p);
   } else {
     s = sm.nonhet_list[tid - n_het];
     const uint32_t row_s = (s * (2u * S - s - 1u)) >> 1;
+#pragma unroll 4
     for (uint32_t q = 0; q < n_het; ++q) {
       const uint32_t t = sm.het_list[q];
       acc.add(s_mi, (t < s) ? (((t * (2u * S - t - 1u)) >> 1) + (s - t - 1u)) : (row_s + (t - s - 1u)));

@@ -32,7 +32,8 @@ struct DevUnit {
   uint64_t gram_off;   // first word of the unit's nine count matrices (tensor-core path), else ~0
   uint32_t S, R, W, site_off;
   uint32_t first_item, n_items;
-  uint32_t S_pad, pad;
+  uint32_t S_pad;
+  uint32_t tiled;      // 1: MI of every pair is precomputed into the dense scratch by k_tile_mi
 };
 constexpr uint64_t kNoGram = ~0ull;
 
@@ -66,6 +67,7 @@ struct RunParams {
   uint8_t* item_dense;                 // k_count: fast-eligible item with > kOthCap "other" reads at a site
   uint32_t* n_generic;                 // items k_pairs_generic has to process (host count + dense ones)
   const uint32_t* gram;                // count matrices of the tensor-core path (DevUnit::gram_off)
+  uint32_t* tile_counts;               // EMIT_COUNTS: 3x3 tables of the k_tile_mi units, 9 per dense slot
   Header* header;
   lgmi_pair_rec* records;
   uint32_t* counts;
@@ -189,7 +191,9 @@ __global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
       if (skip_nonhet)
         evaluate = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
                    ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
-      if (evaluate && u.gram_off != kNoGram) {
+      if (u.tiled) {
+        mi = P.dense[u.dense_off + it.pair_begin + pl];  // k_tile_mi has been here (NaN: dropped / not evaluated)
+      } else if (evaluate && u.gram_off != kNoGram) {
         uint32_t T[9];
         const uint32_t n_common = gram_table(P.gram + u.gram_off, u.S_pad, i, j, T);
         if ((int)n_common >= P.min_common) {
@@ -252,7 +256,11 @@ __global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
         reinterpret_cast<uint4*>(P.records)[slot] = rec;
         if (P.mode & LGMI_MODE_EMIT_COUNTS) {
           uint32_t T[9];
-          if (u.gram_off != kNoGram) {
+          if (u.tiled) {
+            const uint32_t* src = P.tile_counts + (u.dense_off + it.pair_begin + pl) * 9ull;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) T[k] = src[k];
+          } else if (u.gram_off != kNoGram) {
             gram_table(P.gram + u.gram_off, u.S_pad, ij >> 16, ij & 0xffffu, T);
           } else {
             const uint4* ri = base + (size_t)(ij >> 16) * 3u * W4;
@@ -283,10 +291,180 @@ __global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
         P.site_mean[u.site_off + s] = lg_neumaier_mean(acc);
         P.site_cnt[u.site_off + s] = (uint32_t)acc.n;
       }
-    } else {
+    } else if (!u.tiled) {
       for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) P.dense[u.dense_off + it.pair_begin + pl] = s_mi[pl];
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// K1 + K2, tiled path: units too large for k_pairs_fast and too shallow for the
+// tensor cores.  One CTA per 16 x 16 block of site pairs (upper block triangle),
+// one pair per thread: the three planes of both site blocks are staged in shared
+// memory 1 024 reads at a time; the nine AND+popcount sums of the pair run
+// through a carry-save adder tree (Harley-Seal: 8 words -> 14 LOP3 + ONE POPC,
+// the popcount pipe is a quarter-rate unit), and the fp64 epilogue writes the
+// pair's MI (NaN: dropped by min-common / not evaluated) to the unit's dense
+// scratch in pair order.  k_count / k_pairs_generic then only compact and order
+// what is already there.
+constexpr int kTileSites = 16;   // sites per block
+constexpr int kTileKC = 32;      // words of each plane per staged chunk
+constexpr int kTileStride = 36;  // words per staged row: 16-byte aligned; 8 consecutive rows cover all 32 banks
+
+struct TileItem {
+  uint32_t unit;
+  uint16_t I, J;  // site blocks of 16 sites, I <= J
+};
+
+// running bit-sliced count of one AND+popcount set
+struct CsaAcc {
+  uint32_t ones, twos, fours, eights;  // eights: already popcounted, in units of 8
+  __device__ __forceinline__ void init() { ones = twos = fours = eights = 0u; }
+  __device__ __forceinline__ static void csa(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t s = a ^ b ^ c;
+    carry = (a & b) | (c & (a ^ b));
+    sum = s;
+  }
+  // eight words of x & y
+  __device__ __forceinline__ void add8(const uint4& x0, const uint4& x1, const uint4& y0, const uint4& y1) {
+    uint32_t ta, tb, fa, fb, e;
+    csa(ta, ones, ones, x0.x & y0.x, x0.y & y0.y);
+    csa(tb, ones, ones, x0.z & y0.z, x0.w & y0.w);
+    csa(fa, twos, twos, ta, tb);
+    csa(ta, ones, ones, x1.x & y1.x, x1.y & y1.y);
+    csa(tb, ones, ones, x1.z & y1.z, x1.w & y1.w);
+    csa(fb, twos, twos, ta, tb);
+    csa(e, fours, fours, fa, fb);
+    eights += (uint32_t)__popc(e);
+  }
+  __device__ __forceinline__ uint32_t total() const {
+    return 8u * eights + 4u * (uint32_t)__popc(fours) + 2u * (uint32_t)__popc(twos) + (uint32_t)__popc(ones);
+  }
+};
+
+// fp64 epilogue of one pair, straight from the registers
+__device__ __forceinline__ void tile_epilogue(const RunParams& P, const TileItem& tile, const DevUnit& u,
+                                              const CsaAcc (&acc)[9], uint32_t ty, uint32_t tx) {
+  const uint32_t i = tile.I * (uint32_t)kTileSites + ty, j = tile.J * (uint32_t)kTileSites + tx;
+  if (i >= j || j >= u.S) return;
+  const LnGlobal ln{P.lntab};
+  const uint8_t* __restrict__ flags = P.site_flags + u.site_off;
+  const bool skip_nonhet = (P.mode & LGMI_MODE_HET_ONLY) && (P.mode & LGMI_MODE_SKIP_NONHET);
+  const uint32_t N = acc[0].total();
+  const uint32_t MM = acc[1].total(), Mm = acc[2].total(), mM = acc[3].total(), mm = acc[4].total();
+  uint32_t T[9];
+  T[8] = MM;
+  T[7] = Mm;
+  T[5] = mM;
+  T[4] = mm;
+  T[6] = acc[5].total() - MM - Mm;  // site1 major, site2 other
+  T[3] = acc[6].total() - mM - mm;  // site1 minor, site2 other
+  T[2] = acc[7].total() - MM - mM;  // site1 other, site2 major
+  T[1] = acc[8].total() - Mm - mm;  // site1 other, site2 minor
+  T[0] = N - (MM + Mm + mM + mm) - T[6] - T[3] - T[2] - T[1];
+  double v = lg_nan();
+  bool evaluate = true;
+  if (skip_nonhet)
+    evaluate = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
+               ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+  if (evaluate && (int)N >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
+    if ((T[0] | T[1] | T[2] | T[3] | T[6]) == 0u) v = lg_mi_from_2x2(mm, mM, Mm, MM, ln);
+    else v = lg_mi_from_table(T, ln);
+  }
+  const uint64_t slot = u.dense_off + lg_row_off(i, u.S) + (j - i - 1u);
+  P.dense[slot] = v;
+  if (P.mode & LGMI_MODE_EMIT_COUNTS) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) P.tile_counts[slot * 9ull + k] = T[k];
+  }
+}
+
+// stage one 1 024-read chunk of both site blocks of a tile: [block (i / j)][plane M, m, C][site][word]
+typedef uint32_t TileRows[2][3][kTileSites][kTileStride];
+__device__ __forceinline__ void tile_prefetch(TileRows& rows, const RunParams& P, const TileItem& tile, const DevUnit& u,
+                                              uint32_t k0) {
+  const uint32_t* __restrict__ planes = P.planes + u.plane_off;
+  const uint32_t W = u.W;
+  for (uint32_t e = threadIdx.x; e < 2u * 3u * kTileSites * (kTileKC / 4); e += kThreads) {
+    const uint32_t q = e & 7u, row = e >> 3;  // row = (blk * 3 + plane) * 16 + site
+    const uint32_t site = row & 15u, bp = row >> 4, plane = bp % 3u, blk = bp / 3u;
+    const uint32_t s = (blk ? tile.J : tile.I) * (uint32_t)kTileSites + site;
+    const bool have = s < u.S && k0 + 4u * q < W;  // absent words are zero-filled
+    cp_async16(&rows[blk][plane][site][4u * q],
+               planes + ((size_t)(have ? s : 0u) * 3u + plane) * W + (have ? k0 + 4u * q : 0u), have);
+  }
+}
+
+// persistent: CTA c takes tiles c, c + grid, ...; the next chunk (of this tile or of the
+// CTA's next tile) is in flight while the current one is counted
+__global__ void __launch_bounds__(kThreads, 3) k_tile_mi(const RunParams P, const TileItem* __restrict__ tiles,
+                                                         uint32_t n_tiles) {
+  __shared__ __align__(16) TileRows s_rows[2];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t ty = tid >> 4, tx = tid & 15u;  // pair (site0[0] + ty, site0[1] + tx)
+  uint32_t t = blockIdx.x;
+  if (t >= n_tiles) return;
+  TileItem tile = tiles[t];
+  DevUnit u = P.units[tile.unit];
+  uint32_t buf = 0;
+  tile_prefetch(s_rows[0], P, tile, u, 0u);
+  cp_async_commit();
+
+  while (true) {
+    const uint32_t t_next = t + gridDim.x;
+    TileItem tile_next = tile;
+    DevUnit u_next = u;
+    if (t_next < n_tiles) {
+      tile_next = tiles[t_next];
+      u_next = P.units[tile_next.unit];
+    }
+    const uint32_t W = u.W;
+    CsaAcc acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k].init();
+
+    for (uint32_t k0 = 0; k0 < W; k0 += (uint32_t)kTileKC) {
+      // request what comes next into the other buffer (its last readers passed the barrier below)
+      if (k0 + (uint32_t)kTileKC < W) tile_prefetch(s_rows[buf ^ 1u], P, tile, u, k0 + (uint32_t)kTileKC);
+      else if (t_next < n_tiles) tile_prefetch(s_rows[buf ^ 1u], P, tile_next, u_next, 0u);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      const TileRows& rows = s_rows[buf];
+      const uint32_t kw = min((uint32_t)kTileKC, (W - k0 + 7u) & ~7u);  // whole groups of 8 words (the tail is zeros)
+      for (uint32_t k8 = 0; k8 < kw; k8 += 8u) {
+        const uint4 Mi0 = *reinterpret_cast<const uint4*>(&rows[0][0][ty][k8]);
+        const uint4 Mi1 = *reinterpret_cast<const uint4*>(&rows[0][0][ty][k8 + 4]);
+        const uint4 mi0 = *reinterpret_cast<const uint4*>(&rows[0][1][ty][k8]);
+        const uint4 mi1 = *reinterpret_cast<const uint4*>(&rows[0][1][ty][k8 + 4]);
+        const uint4 Ci0 = *reinterpret_cast<const uint4*>(&rows[0][2][ty][k8]);
+        const uint4 Ci1 = *reinterpret_cast<const uint4*>(&rows[0][2][ty][k8 + 4]);
+        const uint4 Mj0 = *reinterpret_cast<const uint4*>(&rows[1][0][tx][k8]);
+        const uint4 Mj1 = *reinterpret_cast<const uint4*>(&rows[1][0][tx][k8 + 4]);
+        const uint4 mj0 = *reinterpret_cast<const uint4*>(&rows[1][1][tx][k8]);
+        const uint4 mj1 = *reinterpret_cast<const uint4*>(&rows[1][1][tx][k8 + 4]);
+        const uint4 Cj0 = *reinterpret_cast<const uint4*>(&rows[1][2][tx][k8]);
+        const uint4 Cj1 = *reinterpret_cast<const uint4*>(&rows[1][2][tx][k8 + 4]);
+        acc[0].add8(Ci0, Ci1, Cj0, Cj1);  // N
+        acc[1].add8(Mi0, Mi1, Mj0, Mj1);
+        acc[2].add8(Mi0, Mi1, mj0, mj1);
+        acc[3].add8(mi0, mi1, Mj0, Mj1);
+        acc[4].add8(mi0, mi1, mj0, mj1);
+        acc[5].add8(Mi0, Mi1, Cj0, Cj1);
+        acc[6].add8(mi0, mi1, Cj0, Cj1);
+        acc[7].add8(Ci0, Ci1, Mj0, Mj1);
+        acc[8].add8(Ci0, Ci1, mj0, mj1);
+      }
+      __syncthreads();  // this buffer may be refilled by the prefetch of the next iteration
+      buf ^= 1u;
+    }
+    tile_epilogue(P, tile, u, acc, ty, tx);
+    if (t_next >= n_tiles) break;
+    t = t_next;
+    tile = tile_next;
+    u = u_next;
+  }
+  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------
@@ -381,6 +559,10 @@ __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
         const bool het = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
                          ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
         if (!het && (het_only || skip_nonhet)) continue;
+        if (u.tiled) {  // survivors are the pairs k_tile_mi gave an MI
+          mine += isnan(P.dense[u.dense_off + it.pair_begin + pl]) ? 0u : 1u;
+          continue;
+        }
         uint32_t n;
         if (u.gram_off != kNoGram) {
           uint32_t T[9];

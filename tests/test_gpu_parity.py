@@ -249,11 +249,11 @@ def _synth_unit(rng, S, R, cov):
 
 
 @pytest.fixture()
-def dense_everything(gpu_ctx):
+def dense_everything(lg, gpu_ctx):
     """Every unit with a pair goes through k_expand_planes + k_gram_i8."""
     gpu_ctx.set_dense_threshold(2, 1)
     yield gpu_ctx
-    gpu_ctx.set_dense_threshold(512, 8192)
+    gpu_ctx.set_dense_threshold(*lg.DENSE_DEFAULT)
 
 
 def test_dense_path_small_shapes(lg, dense_everything):
@@ -281,9 +281,11 @@ def test_dense_path_deep_unit(lg, gpu_ctx):
     units in one batch: the deep one takes the tensor cores, the others do not."""
     rng = np.random.default_rng(32)
     deep = _synth_unit(rng, 520, 12000, 0.6)
+    narrow = _synth_unit(rng, 60, 9000, 0.5)          # few sites, deep: one padded 256-site block
+    tiled = _synth_unit(rng, 30, 9000, 0.5)           # below the site threshold: 16 x 16 popcount tiles
     small = [_synth_unit(rng, 40, 150, 0.5) for _ in range(3)]
-    full = check_batch(lg, gpu_ctx, [small[0], deep, small[1], small[2]], 6, min_exact=0.9)
-    assert full.n_dense_units == 1
+    full = check_batch(lg, gpu_ctx, [small[0], deep, small[1], narrow, tiled, small[2]], 6, min_exact=0.9)
+    assert full.n_dense_units == 2
     assert full.dense_kernel_ms > 0.0
 
 
@@ -299,7 +301,7 @@ def test_cfg3_full_size_dense_equals_popcount_and_oracle(lg, gpu_ctx):
     try:
         popc = lg.mi_step_batched(pb, 6, mode, ctx=gpu_ctx)
     finally:
-        gpu_ctx.set_dense_threshold(512, 8192)
+        gpu_ctx.set_dense_threshold(*lg.DENSE_DEFAULT)
     assert popc.n_dense_units == 0
     assert np.array_equal(dense.records, popc.records)
     assert np.array_equal(dense.counts, popc.counts)
