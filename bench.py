@@ -345,28 +345,45 @@ def run_gpu(args):
     value = pairs_per_step * world * args.steps / (dev_ms_max * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
+    # lgmi_pipeline_step: pinned host planes in, pinned host rows + per-site means out; H2D, kernels and
+    # D2H of consecutive groups of units overlap inside the call (what lg.mi_step_batched does for big batches)
     mode_e2e = lg.MODE_HET_ONLY                              # what mismatch.py:393-404 hands on
+    pipe = lg.Pipeline(ctx, pb, args.e2e_chunks)
     def e2e_step():
-        batch.upload(pin_planes.array, pin_flags.array)      # H2D from pinned host memory
-        batch.run(mc, mode_e2e)
-        return batch.download(copy=False)                    # D2H of records + per-site means, stream sync
+        return pipe.step(mc, mode_e2e, pin_planes.array, pin_flags.array, copy=False)
     e2e_steps = 0 if args.no_e2e else args.steps
     for _ in range(args.warmup if e2e_steps else 1):
         out = e2e_step()
     h2d = pb.planes.nbytes + pb.site_flags.nbytes
-    d2h = out.n_records * 16 + pb.n_sites * 12 + (pb.n_units + 1) * 8 + 16
+    d2h = out.n_records * 16 + pb.n_sites * 12 + (pb.n_units + args.e2e_chunks) * 8 + 16 * args.e2e_chunks
+    launches_e2e0 = ctx.launch_count
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         out = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    launches_e2e = ctx.launch_count - launches_e2e0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     barrier()
     e2e_value = pairs_per_step * world * e2e_steps / float(t.item()) if e2e_steps else None
     e2e_records = int(out.n_records)
+    # the plain sequence (upload, run, download one after the other), for comparison
+    def serial_step():
+        batch.upload(pin_planes.array, pin_flags.array)
+        batch.run(mc, mode_e2e)
+        return batch.download(copy=False)
+    serial_ms = None
+    if e2e_steps:
+        serial_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            serial_step()
+        torch.cuda.synchronize()
+        serial_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
 
     if rank != 0:
         if world > 1:
@@ -410,7 +427,9 @@ def run_gpu(args):
                      "kernel_share_of_step": k_ms * args.steps / dev_ms if dev_ms else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "mode": "HET_ONLY: all candidates evaluated, het-kept rows (%d) + per-site mean MI returned"
-                        % e2e_records, "ms_per_step": 1e3 * float(t.item()) / e2e_steps if e2e_steps else None},
+                        % e2e_records, "ms_per_step": 1e3 * float(t.item()) / e2e_steps if e2e_steps else None,
+                "api": "lgmi_pipeline_step, %d groups of units on their own streams" % args.e2e_chunks,
+                "serial_upload_run_download_ms": serial_ms, "gpu_launches": launches_e2e * world},
         "gpu_launches": launches * world,
         "clocks": clocks,
     }
@@ -436,6 +455,7 @@ def main():
     ap.add_argument("--impl", choices=["graft", "reference"], default="graft")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="groups of units of the pipelined end-to-end step")
     ap.add_argument("--no-dense", action="store_true", help="skip the cfg3 deep-unit (tensor-core) leg")
     ap.add_argument("--dense-only", action="store_true", help="profiling runs: only the cfg3 deep-unit leg")
     args = ap.parse_args()

@@ -191,6 +191,23 @@ LGMI_API int lgmi_batch_device_ptrs(lgmi_batch_t* b, void** d_planes, void** d_s
  * 16 B per emitted record, 12 B per site.                                     */
 LGMI_API int lgmi_batch_algorithmic_bytes(lgmi_batch_t* b, uint64_t* bytes);
 
+/* ----- pipelined step over HOST buffers ------------------------------------ *
+ * Same result as upload + run + download of one batch (mismatch.py:387-404    *
+ * for every unit), but the units are cut into n_chunks consecutive groups of  *
+ * about equal work, each on its own stream, so that the H2D copy of group     *
+ * k+1, the kernels of group k and the D2H copy of group k-1 overlap.  Units   *
+ * must be laid out back to back in `planes` / `site_flags`, in order (what    *
+ * the encoder produces); otherwise LGMI_ERR_UNSUPPORTED.  `planes` and        *
+ * `site_flags` should be pinned (lgmi_pinned_alloc) for the copies to be      *
+ * asynchronous.  Output pointers stay valid until the next step / destroy.    */
+typedef struct lgmi_pipeline lgmi_pipeline_t;
+LGMI_API int lgmi_pipeline_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units,
+                         uint64_t plane_words, uint64_t n_sites, uint32_t n_chunks,
+                         lgmi_pipeline_t** out);
+LGMI_API int lgmi_pipeline_step(lgmi_pipeline_t* p, const uint32_t* planes, const uint8_t* site_flags,
+                       int min_common, uint32_t mode, lgmi_result* out);
+LGMI_API void lgmi_pipeline_destroy(lgmi_pipeline_t* p);
+
 /* one-shot convenience: create + upload + run + download (+ destroy on wait)  */
 LGMI_API int lgmi_submit(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units,
                 const uint32_t* planes, uint64_t plane_words,

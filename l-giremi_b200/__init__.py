@@ -13,7 +13,7 @@ Public surface (same names as the reference where one exists):
 """
 from ._lib import (DENSE_DEFAULT, LIB_PATH, MODE_ALL_PAIRS, MODE_EMIT_COUNTS, MODE_HET_ONLY, MODE_SKIP_NONHET,
                    PAIR_REC, SITE_HET_SNP, SITE_MISMATCH, SITE_SNP, UNIT_DESC, LgmiError)
-from .api import (Batch, Context, StepResult, ecdf, get_context, mean_mismatch_pair_mutual_info,
+from .api import (Batch, Context, Pipeline, StepResult, ecdf, get_context, mean_mismatch_pair_mutual_info,
                   mi_step_batched, mip_and_calls, mismatch_pair_mutual_info, partition_lpt, unit_costs)
 from .encode import EncodedUnit, PlaneBatch, encode_batch, encode_mismatches, pack_units
 from .patch import install, uninstall

@@ -38,7 +38,8 @@ EXPORTS = (
     "lgmi_pinned_alloc", "lgmi_pinned_free", "lgmi_launch_count", "lgmi_set_dense_threshold",
     "lgmi_batch_create", "lgmi_batch_destroy", "lgmi_batch_upload", "lgmi_batch_run",
     "lgmi_batch_download", "lgmi_batch_sync", "lgmi_batch_device_ptrs",
-    "lgmi_batch_algorithmic_bytes", "lgmi_submit", "lgmi_wait", "lgmi_site_mean_csr",
+    "lgmi_batch_algorithmic_bytes", "lgmi_pipeline_create", "lgmi_pipeline_step", "lgmi_pipeline_destroy",
+    "lgmi_submit", "lgmi_wait", "lgmi_site_mean_csr",
     "lgmi_ecdf", "lgmi_ecdf_eval", "lgmi_unit_cost", "lgmi_partition_lpt",
 )
 
@@ -104,6 +105,9 @@ def load():
         "lgmi_batch_sync": (i32, [vp, C.POINTER(Result)]),
         "lgmi_batch_device_ptrs": (i32, [vp, pvp, pvp, pvp, pvp]),
         "lgmi_batch_algorithmic_bytes": (i32, [vp, C.POINTER(u64)]),
+        "lgmi_pipeline_create": (i32, [vp, vp, u32, u64, u64, u32, pvp]),
+        "lgmi_pipeline_step": (i32, [vp, vp, vp, i32, u32, C.POINTER(Result)]),
+        "lgmi_pipeline_destroy": (None, [vp]),
         "lgmi_submit": (i32, [vp, vp, u32, vp, u64, vp, u64, i32, u32]),
         "lgmi_wait": (i32, [vp, C.POINTER(Result)]),
         "lgmi_site_mean_csr": (i32, [vp, vp, vp, u64, vp]),

@@ -187,11 +187,59 @@ class Batch:
             pass
 
 
-def mi_step_batched(pb: PlaneBatch, min_common_reads=5, mode=MODE_HET_ONLY, ctx=None) -> StepResult:
+class Pipeline:
+    """Host-buffers-in / host-buffers-out step with the H2D copy, the kernels and
+    the D2H copy of consecutive groups of units overlapped (lgmi_pipeline_*).
+    Same result as Batch.upload + run + download."""
+
+    def __init__(self, ctx: Context, pb: PlaneBatch, n_chunks=4):
+        self.ctx, self.pb = ctx, pb
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        check(self._lib.lgmi_pipeline_create(ctx.handle, ptr(pb.units), pb.n_units, pb.planes.size, pb.n_sites,
+                                             int(n_chunks), C.byref(h)), ctx.handle)
+        self.handle = h
+
+    def step(self, min_common, mode=MODE_HET_ONLY, planes=None, site_flags=None, copy=True) -> StepResult:
+        planes = self.pb.planes if planes is None else planes
+        site_flags = self.pb.site_flags if site_flags is None else site_flags
+        assert planes.dtype == np.uint32 and planes.size == self.pb.planes.size
+        assert site_flags.dtype == np.uint8 and site_flags.size == self.pb.n_sites
+        res = Result()
+        check(self._lib.lgmi_pipeline_step(self.handle, ptr(planes), ptr(site_flags), int(min_common), int(mode),
+                                           C.byref(res)), self.ctx.handle)
+        return StepResult(res, self.pb.n_units, copy=copy)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.lgmi_pipeline_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if self.ctx.handle:
+                self.close()
+        except Exception:
+            pass
+
+
+PIPELINE_MIN_CANDIDATES = 2_000_000   # below this one submit is as fast as a pipelined one
+
+
+def mi_step_batched(pb: PlaneBatch, min_common_reads=5, mode=MODE_HET_ONLY, ctx=None, n_chunks=None) -> StepResult:
     """All units of `pb` in one submit: pair MI -> het filter -> per-site mean
     (mismatch.py:387-404 for every unit at once).  Host buffers in, host
-    buffers out."""
+    buffers out.  Large batches go through the pipelined step (copies and
+    kernels overlapped); the result is the same either way."""
     ctx = ctx or get_context()
+    if n_chunks is None:
+        n_chunks = 4 if pb.n_candidates >= PIPELINE_MIN_CANDIDATES and pb.n_units >= 16 else 1
+    if n_chunks > 1:
+        p = Pipeline(ctx, pb, n_chunks)
+        try:
+            return p.step(min_common_reads, mode, copy=True)
+        finally:
+            p.close()
     b = Batch(ctx, pb)
     try:
         b.upload()

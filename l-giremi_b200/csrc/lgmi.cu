@@ -32,7 +32,6 @@ struct lgmi_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   std::string err;
   uint64_t launches = 0;
   // ln table
@@ -50,7 +49,6 @@ struct lgmi_ctx {
   // tensor-core path: units at least this large build their tables with k_gram_i8
   uint32_t dense_min_sites = 48, dense_min_reads = 8192;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
-  cudaEvent_t ev4 = nullptr, ev5 = nullptr, ev6 = nullptr, ev7 = nullptr;
 };
 
 // one unit of the tensor-core path
@@ -62,6 +60,9 @@ struct DensePlan {
 
 struct lgmi_batch {
   lgmi_ctx* ctx = nullptr;
+  cudaStream_t own_stream = nullptr;  // pipeline chunks run on their own stream; otherwise the context's
+  uint32_t unit_base = 0;             // added to the unit field of every record (pipeline chunks)
+  cudaEvent_t ev[8] = {};             // 0-1 whole run, 2-3 k_pairs_fast, 4-5 tensor-core path, 6-7 last k_gram_i8
   uint32_t n_units = 0, n_items = 0, n_mean_items = 0, n_fast = 0;
   uint64_t plane_words = 0, n_sites = 0, n_candidates = 0, n_dense = 0;
   uint32_t max_reads = 0;
@@ -117,6 +118,8 @@ struct lgmi_batch {
 };
 
 // --------------------------------------------------------------------------- helpers
+static inline cudaStream_t bstream(const lgmi_batch* b) { return b->own_stream ? b->own_stream : b->ctx->stream; }
+
 static int fail(lgmi_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -186,11 +189,7 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
   if (!ctx) return fail(nullptr, LGMI_ERR_NOMEM, "lgmi_create: out of host memory");
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev4) != cudaSuccess || cudaEventCreate(&ctx->ev5) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev6) != cudaSuccess || cudaEventCreate(&ctx->ev7) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
     return rc;
@@ -246,14 +245,6 @@ extern "C" void lgmi_destroy(lgmi_t* ctx) {
   if (ctx->d_lntab) cudaFree(ctx->d_lntab);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_ij_tab) cudaFree(ctx->d_ij_tab);
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
-  if (ctx->ev3) cudaEventDestroy(ctx->ev3);
-  if (ctx->ev4) cudaEventDestroy(ctx->ev4);
-  if (ctx->ev5) cudaEventDestroy(ctx->ev5);
-  if (ctx->ev6) cudaEventDestroy(ctx->ev6);
-  if (ctx->ev7) cudaEventDestroy(ctx->ev7);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -298,9 +289,11 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   if (!b) return;
   if (b->ctx) {
     cudaSetDevice(b->ctx->device);
-    cudaStreamSynchronize(b->ctx->stream);
+    cudaStreamSynchronize(bstream(b));
     if (b->ctx->oneshot == b) b->ctx->oneshot = nullptr;
   }
+  for (cudaEvent_t e : b->ev)
+    if (e) cudaEventDestroy(e);
   cudaFree(b->d_units);
   cudaFree(b->d_items);
   cudaFree(b->d_fast_items);
@@ -479,6 +472,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
     }                                                                                \
   } while (0)
 
+  for (cudaEvent_t& e : b->ev) BCU(cudaEventCreate(&e));
   BCU(cudaMalloc(&b->d_units, std::max<size_t>(1, n_units) * sizeof(DevUnit)));
   BCU(cudaMalloc(&b->d_items, std::max<size_t>(1, b->n_items) * sizeof(Item)));
   BCU(cudaMalloc(&b->d_fast_items, std::max<size_t>(1, fast_items.size()) * sizeof(FastItem)));
@@ -490,9 +484,9 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   BCU(cudaMalloc(&b->d_item_cnt, ((size_t)b->n_items + 1) * sizeof(unsigned long long)));
   BCU(cudaMalloc(&b->d_item_off, ((size_t)b->n_items + 1) * sizeof(unsigned long long)));
   BCU(cub::DeviceScan::ExclusiveSum(nullptr, b->scan_tmp_bytes, b->d_item_cnt, b->d_item_off, (int)b->n_items + 1,
-                                    ctx->stream));
+                                    bstream(b)));
   BCU(cudaMalloc(&b->d_scan_tmp, std::max<size_t>(b->scan_tmp_bytes, 16)));
-  BCU(cudaMemsetAsync(b->d_item_cnt, 0, ((size_t)b->n_items + 1) * sizeof(unsigned long long), ctx->stream));
+  BCU(cudaMemsetAsync(b->d_item_cnt, 0, ((size_t)b->n_items + 1) * sizeof(unsigned long long), bstream(b)));
   BCU(cudaMalloc(&b->d_header, sizeof(Header)));
   BCU(cudaMalloc(&b->d_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double)));
   BCU(cudaMalloc(&b->d_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t)));
@@ -501,15 +495,15 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   if (!tile_items.empty()) {
     BCU(cudaMalloc(&b->d_tile_items, tile_items.size() * sizeof(TileItem)));
     BCU(cudaMemcpyAsync(b->d_tile_items, tile_items.data(), tile_items.size() * sizeof(TileItem), cudaMemcpyHostToDevice,
-                        ctx->stream));
+                        bstream(b)));
   }
   if (!b->dense_plans.empty()) {
     BCU(cudaMalloc(&b->d_x, x_bytes));
-    BCU(cudaMemsetAsync(b->d_x, 0, x_bytes, ctx->stream));  // rows of the site padding stay zero
+    BCU(cudaMemsetAsync(b->d_x, 0, x_bytes, bstream(b)));  // rows of the site padding stay zero
     BCU(cudaMalloc(&b->d_gram, gram_words * sizeof(uint32_t)));
     BCU(cudaMalloc(&b->d_tiles, dense_tiles.size() * sizeof(DenseTile)));
     BCU(cudaMemcpyAsync(b->d_tiles, dense_tiles.data(), dense_tiles.size() * sizeof(DenseTile), cudaMemcpyHostToDevice,
-                        ctx->stream));
+                        bstream(b)));
     typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -536,14 +530,14 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   BCU(cudaHostAlloc(&b->h_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double), cudaHostAllocDefault));
   BCU(cudaHostAlloc(&b->h_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t), cudaHostAllocDefault));
   BCU(cudaHostAlloc(&b->h_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
-  if (n_units) BCU(cudaMemcpyAsync(b->d_units, du.data(), n_units * sizeof(DevUnit), cudaMemcpyHostToDevice, ctx->stream));
-  if (b->n_items) BCU(cudaMemcpyAsync(b->d_items, b->h_items.data(), b->n_items * sizeof(Item), cudaMemcpyHostToDevice, ctx->stream));
+  if (n_units) BCU(cudaMemcpyAsync(b->d_units, du.data(), n_units * sizeof(DevUnit), cudaMemcpyHostToDevice, bstream(b)));
+  if (b->n_items) BCU(cudaMemcpyAsync(b->d_items, b->h_items.data(), b->n_items * sizeof(Item), cudaMemcpyHostToDevice, bstream(b)));
   if (!fast_items.empty())
     BCU(cudaMemcpyAsync(b->d_fast_items, fast_items.data(), fast_items.size() * sizeof(FastItem), cudaMemcpyHostToDevice,
-                        ctx->stream));
+                        bstream(b)));
   if (!mean_items.empty())
-    BCU(cudaMemcpyAsync(b->d_mean_items, mean_items.data(), mean_items.size() * sizeof(MeanItem), cudaMemcpyHostToDevice, ctx->stream));
-  BCU(cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope
+    BCU(cudaMemcpyAsync(b->d_mean_items, mean_items.data(), mean_items.size() * sizeof(MeanItem), cudaMemcpyHostToDevice, bstream(b)));
+  BCU(cudaStreamSynchronize(bstream(b)));  // the host vectors above go out of scope
 #undef BCU
   int rc = ensure_lntab(ctx, std::max<uint32_t>(b->max_reads, 1u));
   if (rc) {
@@ -561,9 +555,9 @@ extern "C" int lgmi_batch_upload(lgmi_batch_t* b, const uint32_t* planes, const 
     return fail(ctx, LGMI_ERR_ARG, "lgmi_batch_upload: NULL input");
   CU(ctx, cudaSetDevice(ctx->device));
   if (b->plane_words)
-    CU(ctx, cudaMemcpyAsync(b->d_planes, planes, b->plane_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(b->d_planes, planes, b->plane_words * sizeof(uint32_t), cudaMemcpyHostToDevice, bstream(b)));
   if (b->n_sites)
-    CU(ctx, cudaMemcpyAsync(b->d_flags, site_flags, b->n_sites, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(b->d_flags, site_flags, b->n_sites, cudaMemcpyHostToDevice, bstream(b)));
   b->uploaded = true;
   return LGMI_OK;
 }
@@ -576,7 +570,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     return fail(ctx, LGMI_ERR_ARG, "LGMI_MODE_SKIP_NONHET requires LGMI_MODE_HET_ONLY");
   CU(ctx, cudaSetDevice(ctx->device));
   if ((mode & LGMI_MODE_EMIT_COUNTS) && b->counts_cap < b->rec_cap) {
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaStreamSynchronize(bstream(b)));
     if (b->d_counts) CU(ctx, cudaFree(b->d_counts));
     b->d_counts = nullptr;
     b->counts_cap = 0;
@@ -584,7 +578,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     b->counts_cap = b->rec_cap;
   }
   if ((mode & LGMI_MODE_EMIT_COUNTS) && b->n_tile_items && !b->d_tile_counts) {
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaStreamSynchronize(bstream(b)));
     CU(ctx, cudaMalloc(&b->d_tile_counts, std::max<uint64_t>(1, b->n_dense) * 9ull * sizeof(uint32_t)));
   }
   RunParams P;
@@ -610,25 +604,26 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   P.dense = b->d_dense;
   P.unit_rec_off = b->d_unit_rec_off;
   P.gram = b->d_gram;
+  P.unit_base = b->unit_base;
   P.tile_counts = b->d_tile_counts;
 
-  CU(ctx, cudaMemsetAsync(b->d_header, 0, sizeof(Header), ctx->stream));
-  CU(ctx, cudaMemsetAsync(b->d_unit_rec_off, 0, ((size_t)b->n_units + 1) * sizeof(unsigned long long), ctx->stream));
-  CU(ctx, cudaMemsetAsync(b->d_item_dense, 0, std::max<size_t>(1, b->n_items), ctx->stream));
-  const uint32_t n_generic0 = b->n_items - b->n_fast;  // k_count adds the dense small units
-  CU(ctx, cudaMemcpyAsync(b->d_n_generic, &n_generic0, sizeof n_generic0, cudaMemcpyHostToDevice, ctx->stream));
-  CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  if (b->n_sites) {
-    // sites of pair-less units keep NaN; everything else is overwritten
-    k_fill_nan<<<(unsigned)((b->n_sites + 255) / 256), 256, 0, ctx->stream>>>(b->d_site_mean, b->d_site_cnt, b->n_sites);
+  const bool timing = b->own_stream == nullptr;  // pipeline groups skip the per-kernel events (fewer API calls)
+  if (timing) CU(ctx, cudaEventRecord(b->ev[0], bstream(b)));
+  {
+    // one launch resets the run state: header, offsets, flags, NaN means (sites of pair-less units keep them)
+    const uint64_t n = std::max<uint64_t>(std::max<uint64_t>(b->n_sites, b->n_items), (uint64_t)b->n_units + 1);
+    k_run_init<<<(unsigned)((n + 255) / 256), 256, 0, bstream(b)>>>(b->d_header, b->d_unit_rec_off, b->n_units + 1,
+                                                                  b->d_item_dense, b->n_items, b->d_n_generic,
+                                                                  b->n_items - b->n_fast, b->d_site_mean, b->d_site_cnt,
+                                                                  b->n_sites);
     ++ctx->launches;
   }
-  CU(ctx, cudaEventRecord(ctx->ev4, ctx->stream));
+  if (timing) CU(ctx, cudaEventRecord(b->ev[4], bstream(b)));
   for (const DensePlan& pl : b->dense_plans) {
     // K3: bit-planes -> 0/1 bytes -> nine count matrices on the tensor cores
     const uint64_t groups = 3ull * pl.S * pl.k_blocks * (kDenseBK / 16);
     const unsigned egrid = (unsigned)std::min<uint64_t>((groups + 255) / 256, (uint64_t)ctx->num_sms * 16u);
-    k_expand_planes<<<egrid, 256, 0, ctx->stream>>>(b->d_planes + pl.plane_off, pl.S, pl.W, pl.S_pad, b->d_x);
+    k_expand_planes<<<egrid, 256, 0, bstream(b)>>>(b->d_planes + pl.plane_off, pl.S, pl.W, pl.S_pad, b->d_x);
     ++ctx->launches;
     DenseParams D;
     D.tiles = b->d_tiles + pl.tile_off;
@@ -639,32 +634,30 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     D.error = reinterpret_cast<uint32_t*>(&b->d_header->pad);
     const unsigned ggrid = (unsigned)std::min<uint32_t>(pl.n_tiles, (uint32_t)ctx->num_sms);
     const bool last = &pl == &b->dense_plans.back();
-    if (last) CU(ctx, cudaEventRecord(ctx->ev6, ctx->stream));
-    k_gram_i8<<<ggrid, kDenseThreads, kDenseSmemBytes, ctx->stream>>>(pl.tmap, D);
-    if (last) CU(ctx, cudaEventRecord(ctx->ev7, ctx->stream));
+    if (last && timing) CU(ctx, cudaEventRecord(b->ev[6], bstream(b)));
+    k_gram_i8<<<ggrid, kDenseThreads, kDenseSmemBytes, bstream(b)>>>(pl.tmap, D);
+    if (last && timing) CU(ctx, cudaEventRecord(b->ev[7], bstream(b)));
     ++ctx->launches;
   }
-  CU(ctx, cudaEventRecord(ctx->ev5, ctx->stream));
+  if (timing) CU(ctx, cudaEventRecord(b->ev[5], bstream(b)));
   if (b->n_tile_items) {
     // K1 + K2 of the medium units: counts + MI per 16 x 16 block of site pairs
     const unsigned tgrid = (unsigned)std::min<uint64_t>(b->n_tile_items, (uint64_t)ctx->num_sms * 3u);
-    k_tile_mi<<<tgrid, kThreads, 0, ctx->stream>>>(P, b->d_tile_items, b->n_tile_items);
+    k_tile_mi<<<tgrid, kThreads, 0, bstream(b)>>>(P, b->d_tile_items, b->n_tile_items);
     ++ctx->launches;
   }
   if (b->n_items) {
     // K0 + scan: every item's place in the ordered output
     const unsigned cgrid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 8u);
-    k_count<<<cgrid, kThreads, 0, ctx->stream>>>(P);
+    k_count<<<cgrid, kThreads, 0, bstream(b)>>>(P);
     ++ctx->launches;
     CU(ctx, cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, b->scan_tmp_bytes, b->d_item_cnt, b->d_item_off,
-                                          (int)b->n_items + 1, ctx->stream));
+                                          (int)b->n_items + 1, bstream(b)));
     ++ctx->launches;
-    CU(ctx, cudaMemcpyAsync(&b->d_header->n_records, b->d_item_off + b->n_items, sizeof(unsigned long long),
-                            cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(b->d_unit_rec_off + b->n_units, b->d_item_off + b->n_items, sizeof(unsigned long long),
-                            cudaMemcpyDeviceToDevice, ctx->stream));
+    k_scan_finish<<<1, 32, 0, bstream(b)>>>(b->d_item_off + b->n_items, b->d_header, b->d_unit_rec_off + b->n_units);
+    ++ctx->launches;
   }
-  CU(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+  if (timing) CU(ctx, cudaEventRecord(b->ev[2], bstream(b)));
   if (b->n_fast) {
     FastParams F;
     F.items = b->d_fast_items;
@@ -683,24 +676,25 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     F.site_mean = b->d_site_mean;
     F.site_cnt = b->d_site_cnt;
     F.unit_rec_off = b->d_unit_rec_off;
+    F.unit_base = b->unit_base;
     // persistent CTAs: a whole number of CTAs per SM, never more than there are items
     const unsigned grid = (unsigned)std::min<uint64_t>(b->n_fast, (uint64_t)ctx->num_sms * ctx->pairs_ctas_per_sm);
-    k_pairs_fast<<<grid, kFastThreads, sizeof(FastSmem), ctx->stream>>>(F);
+    k_pairs_fast<<<grid, kFastThreads, sizeof(FastSmem), bstream(b)>>>(F);
     ++ctx->launches;
   }
-  CU(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+  if (timing) CU(ctx, cudaEventRecord(b->ev[3], bstream(b)));
   if (b->n_items) {
     // everything the small-unit kernel does not take; exits at once when there is nothing
     const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
-    k_pairs_generic<<<grid, kThreads, 0, ctx->stream>>>(P);
+    k_pairs_generic<<<grid, kThreads, 0, bstream(b)>>>(P);
     ++ctx->launches;
   }
   if (b->n_mean_items) {
-    k_site_mean_dense<<<b->n_mean_items, kMeanSites * 32, 0, ctx->stream>>>(b->d_units, b->d_mean_items, b->d_flags, b->d_dense,
+    k_site_mean_dense<<<b->n_mean_items, kMeanSites * 32, 0, bstream(b)>>>(b->d_units, b->d_mean_items, b->d_flags, b->d_dense,
                                                               b->d_site_mean, b->d_site_cnt);
     ++ctx->launches;
   }
-  CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  if (timing) CU(ctx, cudaEventRecord(b->ev[1], bstream(b)));
   CU(ctx, cudaGetLastError());
   b->ran = true;
   b->last_mode = mode;
@@ -716,14 +710,17 @@ static int fill_scalars(lgmi_batch* b, lgmi_result* out) {
   out->n_records = b->h_header->n_records;
   out->n_sites = b->n_sites;
   float ms = 0.f;
-  CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-  out->kernel_ms = ms;
-  CU(ctx, cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
-  out->pairs_kernel_ms = ms;
-  CU(ctx, cudaEventElapsedTime(&ms, ctx->ev4, ctx->ev5));
-  out->dense_kernel_ms = ms;
-  if (!b->dense_plans.empty()) {
-    CU(ctx, cudaEventElapsedTime(&ms, ctx->ev6, ctx->ev7));
+  const bool timing = b->own_stream == nullptr;
+  if (timing) {
+    CU(ctx, cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]));
+    out->kernel_ms = ms;
+    CU(ctx, cudaEventElapsedTime(&ms, b->ev[2], b->ev[3]));
+    out->pairs_kernel_ms = ms;
+    CU(ctx, cudaEventElapsedTime(&ms, b->ev[4], b->ev[5]));
+    out->dense_kernel_ms = ms;
+  }
+  if (timing && !b->dense_plans.empty()) {
+    CU(ctx, cudaEventElapsedTime(&ms, b->ev[6], b->ev[7]));
     out->gram_kernel_ms = ms;
     const DensePlan& pl = b->dense_plans.back();
     out->gram_macs = (uint64_t)pl.n_tiles * kDenseBM * kDenseBN * pl.k_blocks * kDenseBK;
@@ -740,8 +737,8 @@ extern "C" int lgmi_batch_sync(lgmi_batch_t* b, lgmi_result* out) {
   lgmi_ctx* ctx = b->ctx;
   if (!b->ran) return fail(ctx, LGMI_ERR_STATE, "lgmi_batch_sync: batch has not been run");
   CU(ctx, cudaSetDevice(ctx->device));
-  CU(ctx, cudaMemcpyAsync(b->h_header, b->d_header, sizeof(Header), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, cudaMemcpyAsync(b->h_header, b->d_header, sizeof(Header), cudaMemcpyDeviceToHost, bstream(b)));
+  CU(ctx, cudaStreamSynchronize(bstream(b)));
   return fill_scalars(b, out);
 }
 
@@ -751,14 +748,14 @@ extern "C" int lgmi_batch_download(lgmi_batch_t* b, lgmi_result* out) {
   if (!b->ran) return fail(ctx, LGMI_ERR_STATE, "lgmi_batch_download: batch has not been run");
   CU(ctx, cudaSetDevice(ctx->device));
   // the small per-site / per-unit outputs can go while we learn the record count
-  CU(ctx, cudaMemcpyAsync(b->h_header, b->d_header, sizeof(Header), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(b->h_header, b->d_header, sizeof(Header), cudaMemcpyDeviceToHost, bstream(b)));
   if (b->n_sites) {
-    CU(ctx, cudaMemcpyAsync(b->h_site_mean, b->d_site_mean, b->n_sites * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(b->h_site_cnt, b->d_site_cnt, b->n_sites * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(b->h_site_mean, b->d_site_mean, b->n_sites * sizeof(double), cudaMemcpyDeviceToHost, bstream(b)));
+    CU(ctx, cudaMemcpyAsync(b->h_site_cnt, b->d_site_cnt, b->n_sites * sizeof(uint32_t), cudaMemcpyDeviceToHost, bstream(b)));
   }
   CU(ctx, cudaMemcpyAsync(b->h_unit_rec_off, b->d_unit_rec_off, ((size_t)b->n_units + 1) * sizeof(unsigned long long),
-                          cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
+                          cudaMemcpyDeviceToHost, bstream(b)));
+  CU(ctx, cudaStreamSynchronize(bstream(b)));
   const uint64_t nrec = b->h_header->n_records;
   if (nrec > b->rec_cap) return fail(ctx, LGMI_ERR_STATE, "record count %llu exceeds capacity", (unsigned long long)nrec);
   if (nrec > b->h_rec_cap) {
@@ -779,10 +776,10 @@ extern "C" int lgmi_batch_download(lgmi_batch_t* b, lgmi_result* out) {
     b->h_counts_cap = cap;
   }
   if (nrec) {
-    CU(ctx, cudaMemcpyAsync(b->h_records, b->d_records, nrec * sizeof(lgmi_pair_rec), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(b->h_records, b->d_records, nrec * sizeof(lgmi_pair_rec), cudaMemcpyDeviceToHost, bstream(b)));
     if (want_counts)
-      CU(ctx, cudaMemcpyAsync(b->h_counts, b->d_counts, nrec * 9ull * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+      CU(ctx, cudaMemcpyAsync(b->h_counts, b->d_counts, nrec * 9ull * sizeof(uint32_t), cudaMemcpyDeviceToHost, bstream(b)));
+    CU(ctx, cudaStreamSynchronize(bstream(b)));
   }
   int rc = fill_scalars(b, out);
   if (rc) return rc;
@@ -811,6 +808,216 @@ extern "C" int lgmi_batch_algorithmic_bytes(lgmi_batch_t* b, uint64_t* bytes) {
   uint64_t in = 0;
   for (const lgmi_unit_desc& u : b->h_units) in += 3ull * u.n_sites * ((u.n_reads + 7ull) / 8ull) + u.n_sites;
   *bytes = in + 16ull * b->h_header->n_records + 12ull * b->n_sites;
+  return LGMI_OK;
+}
+
+// --------------------------------------------------------------------------- pipelined step
+// The batch cut into consecutive groups of units, each a batch of its own on its own
+// stream: H2D of group k+1, kernels of group k and D2H of group k-1 overlap (two copy
+// engines + the SMs).  Outputs are merged into one set of pinned host arrays in the
+// reference's row order, identical to upload + run + download of the whole batch.
+struct lgmi_pipeline {
+  lgmi_ctx* ctx = nullptr;
+  uint32_t n_units = 0;
+  uint64_t plane_words = 0, n_sites = 0, n_candidates = 0;
+  struct Chunk {
+    lgmi_batch* b = nullptr;
+    uint32_t unit0 = 0, n_units = 0;
+    uint64_t plane0 = 0, site0 = 0;
+    cudaEvent_t done = nullptr;
+  };
+  std::vector<Chunk> chunks;
+  lgmi_pair_rec* h_records = nullptr;
+  uint64_t h_rec_cap = 0;
+  uint32_t* h_counts = nullptr;
+  uint64_t h_counts_cap = 0;
+  double* h_site_mean = nullptr;
+  uint32_t* h_site_cnt = nullptr;
+  unsigned long long* h_unit_rec_off = nullptr;
+};
+
+extern "C" void lgmi_pipeline_destroy(lgmi_pipeline_t* p) {
+  if (!p) return;
+  if (p->ctx) cudaSetDevice(p->ctx->device);
+  for (lgmi_pipeline::Chunk& c : p->chunks) {
+    if (c.b) {
+      cudaStream_t st = c.b->own_stream;
+      lgmi_batch_destroy(c.b);
+      if (st) cudaStreamDestroy(st);
+    }
+    if (c.done) cudaEventDestroy(c.done);
+  }
+  cudaFreeHost(p->h_records);
+  cudaFreeHost(p->h_counts);
+  cudaFreeHost(p->h_site_mean);
+  cudaFreeHost(p->h_site_cnt);
+  cudaFreeHost(p->h_unit_rec_off);
+  delete p;
+}
+
+extern "C" int lgmi_pipeline_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units, uint64_t plane_words,
+                                    uint64_t n_sites, uint32_t n_chunks, lgmi_pipeline_t** out) {
+  if (!ctx || !out || (!units && n_units)) return fail(ctx, LGMI_ERR_ARG, "lgmi_pipeline_create: NULL argument");
+  *out = nullptr;
+  if (n_chunks == 0) return fail(ctx, LGMI_ERR_ARG, "lgmi_pipeline_create: n_chunks must be >= 1");
+  CU(ctx, cudaSetDevice(ctx->device));
+  // groups are slices of the input buffers: units must be laid out back to back, in order
+  uint64_t total = 0;
+  for (uint32_t k = 0; k < n_units; ++k) {
+    const lgmi_unit_desc& u = units[k];
+    const uint64_t want_plane = k ? units[k - 1].plane_off + 3ull * units[k - 1].n_sites * units[k - 1].row_words : u.plane_off;
+    const uint64_t want_site = k ? (uint64_t)units[k - 1].site_off + units[k - 1].n_sites : u.site_off;
+    if (u.plane_off != want_plane || u.site_off != want_site)
+      return fail(ctx, LGMI_ERR_UNSUPPORTED, "lgmi_pipeline_create: unit %u is not laid out right after unit %u", k, k - 1);
+    total += u.n_sites >= 2 ? (uint64_t)u.n_sites * (u.n_sites - 1) / 2 : 0;
+  }
+  lgmi_pipeline* p = new (std::nothrow) lgmi_pipeline();
+  if (!p) return fail(ctx, LGMI_ERR_NOMEM, "lgmi_pipeline_create: out of host memory");
+  p->ctx = ctx;
+  p->n_units = n_units;
+  p->plane_words = plane_words;
+  p->n_sites = n_sites;
+  p->n_candidates = total;
+#define PCU(call)                                                                              \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      int rc__ = fail(ctx, (e__ == cudaErrorMemoryAllocation) ? LGMI_ERR_NOMEM : LGMI_ERR_CUDA, \
+                      "%s failed: %s", #call, cudaGetErrorString(e__));                        \
+      lgmi_pipeline_destroy(p);                                                                \
+      return rc__;                                                                             \
+    }                                                                                          \
+  } while (0)
+  // equal shares of the work: candidate pairs plus a term for the bytes to move
+  std::vector<uint64_t> cost(n_units);
+  uint64_t cost_total = 0;
+  for (uint32_t k = 0; k < n_units; ++k) {
+    const lgmi_unit_desc& u = units[k];
+    cost[k] = (u.n_sites >= 2 ? (uint64_t)u.n_sites * (u.n_sites - 1) / 2 : 0) + (uint64_t)u.n_sites * u.row_words / 4 + 1;
+    cost_total += cost[k];
+  }
+  n_chunks = std::min<uint32_t>(n_chunks, std::max<uint32_t>(1, n_units));
+  uint32_t k = 0;
+  uint64_t done_cost = 0;
+  for (uint32_t c = 0; c < n_chunks && (k < n_units || c == 0); ++c) {
+    lgmi_pipeline::Chunk ch;
+    ch.unit0 = k;
+    const uint64_t target = cost_total * (c + 1) / n_chunks;
+    while (k < n_units && (done_cost < target || c + 1 == n_chunks)) done_cost += cost[k++];
+    ch.n_units = k - ch.unit0;
+    if (ch.n_units == 0 && n_units) continue;  // one unit outweighs a whole share
+    ch.plane0 = ch.n_units ? units[ch.unit0].plane_off : 0;
+    ch.site0 = ch.n_units ? units[ch.unit0].site_off : 0;
+    std::vector<lgmi_unit_desc> local(units + ch.unit0, units + k);
+    uint64_t pw = 0, ns = 0;
+    for (lgmi_unit_desc& u : local) {
+      u.plane_off -= ch.plane0;
+      u.site_off -= (uint32_t)ch.site0;
+      pw = u.plane_off + 3ull * u.n_sites * u.row_words;
+      ns = (uint64_t)u.site_off + u.n_sites;
+    }
+    int rc = lgmi_batch_create(ctx, local.data(), ch.n_units, pw, ns, &ch.b);
+    if (rc) {
+      lgmi_pipeline_destroy(p);
+      return rc;
+    }
+    p->chunks.push_back(ch);
+    lgmi_pipeline::Chunk& ref = p->chunks.back();
+    ref.b->unit_base = ref.unit0;  // records carry the unit's index in the whole batch
+    PCU(cudaStreamCreateWithFlags(&ref.b->own_stream, cudaStreamNonBlocking));
+    PCU(cudaEventCreateWithFlags(&ref.done, cudaEventDisableTiming));
+  }
+  PCU(cudaHostAlloc(&p->h_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double), cudaHostAllocDefault));
+  PCU(cudaHostAlloc(&p->h_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t), cudaHostAllocDefault));
+  PCU(cudaHostAlloc(&p->h_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
+#undef PCU
+  *out = p;
+  return LGMI_OK;
+}
+
+// grows a pinned output array, keeping what has already landed in it
+template <class T>
+static int grow_pinned(lgmi_pipeline* p, T*& buf, uint64_t& cap, uint64_t need, uint64_t keep, size_t elem) {
+  if (need <= cap) return LGMI_OK;
+  lgmi_ctx* ctx = p->ctx;
+  for (lgmi_pipeline::Chunk& c : p->chunks) CU(ctx, cudaStreamSynchronize(c.b->own_stream));  // copies into the old array
+  const uint64_t new_cap = std::max<uint64_t>(need + need / 4, 1024);
+  T* fresh = nullptr;
+  CU(ctx, cudaHostAlloc(&fresh, new_cap * elem, cudaHostAllocDefault));
+  if (keep) memcpy(fresh, buf, keep * elem);
+  if (buf) CU(ctx, cudaFreeHost(buf));
+  buf = fresh;
+  cap = new_cap;
+  return LGMI_OK;
+}
+
+extern "C" int lgmi_pipeline_step(lgmi_pipeline_t* p, const uint32_t* planes, const uint8_t* site_flags, int min_common,
+                                  uint32_t mode, lgmi_result* out) {
+  if (!p || !out) return LGMI_ERR_ARG;
+  lgmi_ctx* ctx = p->ctx;
+  if ((!planes && p->plane_words) || (!site_flags && p->n_sites))
+    return fail(ctx, LGMI_ERR_ARG, "lgmi_pipeline_step: NULL input");
+  CU(ctx, cudaSetDevice(ctx->device));
+  const bool want_counts = (mode & LGMI_MODE_EMIT_COUNTS) != 0u;
+  // everything that does not depend on a count is queued up front, group after group
+  for (lgmi_pipeline::Chunk& c : p->chunks) {
+    lgmi_batch* b = c.b;
+    cudaStream_t st = b->own_stream;
+    int rc = lgmi_batch_upload(b, planes + c.plane0, site_flags + c.site0);
+    if (!rc) rc = lgmi_batch_run(b, min_common, mode);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(b->h_header, b->d_header, sizeof(Header), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(b->h_unit_rec_off, b->d_unit_rec_off, ((size_t)b->n_units + 1) * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaEventRecord(c.done, st));
+    if (b->n_sites) {
+      CU(ctx, cudaMemcpyAsync(p->h_site_mean + c.site0, b->d_site_mean, b->n_sites * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CU(ctx, cudaMemcpyAsync(p->h_site_cnt + c.site0, b->d_site_cnt, b->n_sites * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+  }
+  // records: each group's place in the merged array is known once the groups before it have been counted
+  uint64_t base = 0;
+  for (lgmi_pipeline::Chunk& c : p->chunks) {
+    lgmi_batch* b = c.b;
+    CU(ctx, cudaEventSynchronize(c.done));
+    const uint64_t nrec = b->h_header->n_records;
+    if (b->h_header->pad) return fail(ctx, LGMI_ERR_CUDA, "k_gram_i8: a pipeline barrier timed out (tensor-core path)");
+    if (nrec > b->rec_cap) return fail(ctx, LGMI_ERR_STATE, "record count %llu exceeds capacity", (unsigned long long)nrec);
+    int rc = grow_pinned(p, p->h_records, p->h_rec_cap, base + nrec, base, sizeof(lgmi_pair_rec));
+    if (!rc && want_counts) rc = grow_pinned(p, p->h_counts, p->h_counts_cap, base + nrec, base, 9 * sizeof(uint32_t));
+    if (rc) return rc;
+    if (nrec) {
+      CU(ctx, cudaMemcpyAsync(p->h_records + base, b->d_records, nrec * sizeof(lgmi_pair_rec), cudaMemcpyDeviceToHost,
+                              b->own_stream));
+      if (want_counts)
+        CU(ctx, cudaMemcpyAsync(p->h_counts + base * 9ull, b->d_counts, nrec * 9ull * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                b->own_stream));
+    }
+    for (uint32_t u = 0; u < c.n_units; ++u) p->h_unit_rec_off[c.unit0 + u] = base + b->h_unit_rec_off[u];
+    base += nrec;
+  }
+  p->h_unit_rec_off[p->n_units] = base;
+  for (lgmi_pipeline::Chunk& c : p->chunks) CU(ctx, cudaStreamSynchronize(c.b->own_stream));
+  memset(out, 0, sizeof *out);
+  out->n_candidates = p->n_candidates;
+  out->n_evaluated = p->n_candidates;
+  out->n_records = base;
+  out->records = p->h_records;
+  out->counts = want_counts ? p->h_counts : nullptr;
+  out->n_sites = p->n_sites;
+  out->site_mean = p->h_site_mean;
+  out->site_cnt = p->h_site_cnt;
+  out->unit_rec_off = reinterpret_cast<const uint64_t*>(p->h_unit_rec_off);
+  for (lgmi_pipeline::Chunk& c : p->chunks) {
+    lgmi_result r;
+    int rc = fill_scalars(c.b, &r);
+    if (rc) return rc;
+    out->kernel_ms += r.kernel_ms;
+    out->pairs_kernel_ms += r.pairs_kernel_ms;
+    out->dense_kernel_ms += r.dense_kernel_ms;
+    out->n_dense_units += r.n_dense_units;
+    out->dense_macs += r.dense_macs;
+  }
   return LGMI_OK;
 }
 

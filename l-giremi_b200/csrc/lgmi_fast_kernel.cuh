@@ -26,6 +26,7 @@ struct FastParams {
   double* site_mean;
   uint32_t* site_cnt;
   unsigned long long* unit_rec_off;
+  uint32_t unit_base;                  // added to the unit field of every record
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool copy) {
@@ -262,7 +263,7 @@ __device__ __forceinline__ void fast_emit(const FastParams& P, FastSmem& sm, con
       const uint32_t ij = __ldg(ijt + p);
       const unsigned long long bits = sm.val[p];
       uint4 rec;
-      rec.x = it.unit;
+      rec.x = it.unit + P.unit_base;
       rec.y = (ij >> 6) | ((ij & 63u) << 16);
       rec.z = (uint32_t)bits;
       rec.w = (uint32_t)(bits >> 32);

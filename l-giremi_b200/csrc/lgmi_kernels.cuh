@@ -68,6 +68,7 @@ struct RunParams {
   uint32_t* n_generic;                 // items k_pairs_generic has to process (host count + dense ones)
   const uint32_t* gram;                // count matrices of the tensor-core path (DevUnit::gram_off)
   uint32_t* tile_counts;               // EMIT_COUNTS: 3x3 tables of the k_tile_mi units, 9 per dense slot
+  uint32_t unit_base;                  // added to the unit field of every record
   Header* header;
   lgmi_pair_rec* records;
   uint32_t* counts;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
       if (e) {
         const unsigned long long slot = out + __popc(bal & ((1u << lane) - 1u));
         uint4 rec;  // {unit, i | j << 16, mi}
-        rec.x = it.unit;
+        rec.x = it.unit + P.unit_base;
         rec.y = (ij >> 16) | (ij << 16);
         rec.z = (uint32_t)__double2loint(mi);
         rec.w = (uint32_t)__double2hiint(mi);
@@ -632,12 +633,32 @@ __global__ void __launch_bounds__(kMeanSites * 32) k_site_mean_dense(const DevUn
   }
 }
 
-// sites of units without any pair (S < 2): mean = NaN, cnt = 0
-__global__ void k_fill_nan(double* __restrict__ mean, uint32_t* __restrict__ cnt, uint64_t n) {
+// start of a run: header and offsets zeroed, no item flagged, the count of items for
+// k_pairs_generic seeded, every site's mean = NaN / cnt = 0 (sites of units without a
+// pair, S < 2, keep that; everything else is overwritten)
+__global__ void k_run_init(Header* __restrict__ header, unsigned long long* __restrict__ unit_rec_off, uint32_t n_off,
+                           uint8_t* __restrict__ item_dense, uint32_t n_items, uint32_t* __restrict__ n_generic,
+                           uint32_t n_generic0, double* __restrict__ mean, uint32_t* __restrict__ cnt, uint64_t n_sites) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) {
+  if (k == 0) {
+    header->n_records = 0ull;
+    header->pad = 0ull;
+    *n_generic = n_generic0;
+  }
+  if (k < n_off) unit_rec_off[k] = 0ull;
+  if (k < n_items) item_dense[k] = 0;
+  if (k < n_sites) {
     mean[k] = lg_nan();
     cnt[k] = 0u;
+  }
+}
+
+// after the scan: the total goes to the header and closes the per-unit offsets
+__global__ void k_scan_finish(const unsigned long long* __restrict__ total, Header* __restrict__ header,
+                              unsigned long long* __restrict__ unit_rec_off_end) {
+  if (threadIdx.x == 0) {
+    header->n_records = *total;
+    *unit_rec_off_end = *total;
   }
 }
 

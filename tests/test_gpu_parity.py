@@ -321,6 +321,39 @@ def test_cfg3_full_size_dense_equals_popcount_and_oracle(lg, gpu_ctx):
     assert_mi_close(rec['mi'][at], mi, 0.9)
 
 
+# --------------------------------------------------------------------------- pipelined step
+@pytest.mark.parametrize("n_chunks", [1, 2, 5, 64])
+def test_pipelined_step_equals_one_submit(lg, gpu_ctx, n_chunks):
+    """lgmi_pipeline_*: groups of units on their own streams, outputs merged -- bit for bit
+    what upload + run + download of the whole batch gives, in every mode, step after step."""
+    pb, _ = synth.make_heavy_tail(20261024, 90, s_max=200, r_max=3000)
+    pipe = lg.Pipeline(gpu_ctx, pb, n_chunks)
+    b = lg.Batch(gpu_ctx, pb)
+    b.upload()
+    for mode in (lg.MODE_HET_ONLY, lg.MODE_ALL_PAIRS | lg.MODE_EMIT_COUNTS, lg.MODE_HET_ONLY | lg.MODE_SKIP_NONHET):
+        for mc in (6, 3):
+            b.run(mc, mode)
+            want = b.download()
+            got = pipe.step(mc, mode)
+            assert got.n_records == want.n_records and got.n_candidates == want.n_candidates
+            assert np.array_equal(got.records, want.records)
+            assert np.array_equal(got.unit_rec_off, want.unit_rec_off)
+            assert np.array_equal(got.site_mean, want.site_mean, equal_nan=True)
+            assert np.array_equal(got.site_cnt, want.site_cnt)
+            if mode & lg.MODE_EMIT_COUNTS:
+                assert np.array_equal(got.counts, want.counts)
+    pipe.close()
+    b.close()
+
+
+def test_pipeline_needs_back_to_back_units(lg, gpu_ctx):
+    pb = synth.make_uniform_planes(3, 4, 5, 40, 0.5)
+    bad = lg.PlaneBatch(pb.units[::-1].copy(), pb.planes, pb.site_flags)
+    with pytest.raises(lg.LgmiError) as e:
+        lg.Pipeline(gpu_ctx, bad, 2)
+    assert e.value.code == -6
+
+
 # --------------------------------------------------------------------------- full-size properties (cfg2)
 @pytest.fixture(scope="module")
 def cfg2(lg):
