@@ -21,17 +21,30 @@ _TARGETS = (
 )
 
 
-def install():
+# batched seam (SURVEY 8b ii): the per-region analysis and the per-chunk loop of the CLI
+_BATCHED_TARGETS = (
+    ("giremi.mismatch", "region_mismatch_analysis"),
+    ("giremi.script.giremi", "region_mismatch_analysis"),
+    ("giremi.script.giremi", "footprint_bulk_calculation"),
+)
+
+
+def install(batched=False):
     """Replace the reference's bindings in every giremi module already imported.
-    Returns the list of (module, name) actually patched."""
-    from . import api
+    With batched=True also `region_mismatch_analysis` (mismatch.py:345) and the CLI's
+    `footprint_bulk_calculation` (giremi.py:20), so that each chunk of footprints is
+    one GPU submit.  Returns the list of (module, name) actually patched."""
+    from . import api, batched as batched_mod
     done = []
-    for mod_name, attr in _TARGETS:
+    todo = [(m, a, api) for m, a in _TARGETS]
+    if batched:
+        todo += [(m, a, batched_mod) for m, a in _BATCHED_TARGETS]
+    for mod_name, attr, source in todo:
         mod = sys.modules.get(mod_name)
         if mod is None or not hasattr(mod, attr):
             continue
         _saved.setdefault((mod_name, attr), getattr(mod, attr))
-        setattr(mod, attr, getattr(api, attr))
+        setattr(mod, attr, getattr(source, attr))
         done.append((mod_name, attr))
     return done
 

@@ -164,3 +164,16 @@ def gpu_ctx(lg, liblgmi_path):
     if not has_gpu():
         pytest.skip("no CUDA device")
     return lg.get_context(0)
+
+
+@pytest.fixture(scope="session")
+def ref_giremi():
+    """The UNMODIFIED reference, pip-installed into baseline/_ref by __graft_entry__.build()
+    (git-ignored; it travels to the GPU box with the snapshot).  Skips when absent."""
+    path = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(path, "giremi")):
+        pytest.skip("reference not installed under baseline/_ref")
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    import giremi.mismatch
+    return giremi
