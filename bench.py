@@ -71,10 +71,22 @@ def cpu_step(pool, cores, units, min_common):
     import ref_port
     n = max(1, len(units) // cores // 2)
     chunks = [(units[k:k + n], min_common) for k in range(0, len(units), n)]
+    worker = ref_port.reference_chunk if ref_port.reference_functions() else ref_port.port_chunk
     t0 = time.perf_counter()
-    out = pool.map(ref_port.port_chunk, chunks)
+    out = pool.map(worker, chunks)
     dt = time.perf_counter() - t0
     return sum(p for p, _ in out), dt
+
+
+def cpu_kind():
+    """("reference" | "port", description): the unmodified reference installed under baseline/_ref
+    when it is there, else the oracle's port of it."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_port
+    if ref_port.reference_functions():
+        return "reference", ("baseline/_ref = the unmodified reference (giremi 0.2.4, pip-installed): its own "
+                             "mismatch_pair_mutual_info + mean_mismatch_pair_mutual_info, run as mismatch.py:387-404 does")
+    return "port", "oracle/ref_port.py = the reference's per-pair dict rebuild + sklearn mutual_info_score"
 
 
 def make_pool(cores):
@@ -92,10 +104,10 @@ def cpu_baseline(target_seconds=15.0):
         rate = pairs / dt
         n = int(max(2 * cores, min(CHUNK, target_seconds * rate / 1225)))
         pairs, dt = cpu_step(pool, cores, units[:n], CFG["min_common"])
-    return {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "first %d of %d units of the workload (%d candidate pairs, %.1f s wall, mp.Pool(%d)); "
-                      "oracle/ref_port.py = the reference's per-pair dict rebuild + sklearn mutual_info_score"
-                      % (n, CFG["units"], pairs, dt, cores)}
+    kind, what = cpu_kind()
+    return {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "first %d of %d units of the workload (%d candidate pairs, %.1f s wall, mp.Pool(%d)); %s"
+                      % (n, CFG["units"], pairs, dt, cores, what)}
 
 
 def run_reference(args):
@@ -118,14 +130,15 @@ def run_reference(args):
             tot_pairs += p
             tot_dt += d
     value = tot_pairs / tot_dt
+    kind, what = cpu_kind()
     sample = ("each step = first %d of %d units of the workload (%d candidate pairs) through mp.Pool(%d); "
-              "throughput in pairs/s is size-independent for equal-shape units" % (n, CFG["units"], n * 1225, cores))
+              "throughput in pairs/s is size-independent for equal-shape units; %s" % (n, CFG["units"], n * 1225, cores, what))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_dt / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (numpy/sklearn)",
         "data": "synthetic", "config": {"workload": workload_name(), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

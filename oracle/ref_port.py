@@ -70,3 +70,37 @@ def port_chunk(args):
         n_pairs += n * (n - 1) // 2
         out.append((len(rows), len(kept), len(means)))
     return n_pairs, out
+
+
+# --------------------------------------------------------------------------- the real thing, when it is installed
+def reference_functions():
+    """(mismatch_pair_mutual_info, mean_mismatch_pair_mutual_info) of the UNMODIFIED reference,
+    pip-installed under baseline/_ref by __graft_entry__.build(); None when it is absent."""
+    import os
+    import sys
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.isdir(os.path.join(path, "giremi")):
+        return None
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    try:
+        from giremi.mutual_information import mean_mismatch_pair_mutual_info, mismatch_pair_mutual_info
+    except Exception:                                         # noqa: BLE001
+        return None
+    return mismatch_pair_mutual_info, mean_mismatch_pair_mutual_info
+
+
+def reference_chunk(args):
+    """Pool worker running the reference's own two functions the way mismatch.py:387-404 does."""
+    units, min_common = args
+    pair_mi, mean_mi = reference_functions()
+    n_pairs = 0
+    out = []
+    for m in units:
+        rows = pair_mi(m, min_common_reads=min_common) if len(m) > 1 else []
+        kept = [r for r in rows if r[1] == 'het_snp' or r[3] == 'het_snp']
+        means = mean_mi(kept) if kept else []
+        n = len(m)
+        n_pairs += n * (n - 1) // 2
+        out.append((len(rows), len(kept), len(means)))
+    return n_pairs, out
