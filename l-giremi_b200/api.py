@@ -302,8 +302,8 @@ def ecdf(x):
         raise ZeroDivisionError('division by zero')      # 1/n at stat.py:19
 
     def childfunc(sample):
-        s = np.ascontiguousarray(np.asarray(sample, dtype=np.float64))
-        flat = s.reshape(-1)
+        s = np.asarray(sample, dtype=np.float64)
+        flat = np.ascontiguousarray(s).reshape(-1)             # (ascontiguousarray alone would make 0-d into 1-d)
         out = np.empty(flat.size, dtype=np.float64)
         ctx = get_context()
         check(ctx._lib.lgmi_ecdf_eval(ctx.handle, ptr(xs), xs.size, ptr(flat), flat.size, ptr(out)), ctx.handle)

@@ -427,7 +427,9 @@ def test_ecdf_drop_in_matches_reference(lg, gpu_ctx, golden):
         samples = np.array([unhex(v) for v in case["samples"]])
         want = np.array([unhex(v) for v in case["y"]])
         assert np.array_equal(fn(samples), want)              # bit-exact: same linspace arithmetic
-        assert fn(float(samples[0])) == want[0]
+        one = fn(float(samples[0]))
+        assert np.ndim(one) == 0 and isinstance(one, np.floating) and one == want[0]      # scalar in, scalar out
+        assert np.ndim(fn(np.float64(samples[0]))) == 0
     k = golden("kat.json")["ecdf"]
     assert lg.ecdf(k["x"])(np.array(k["samples"])).tolist() == [0, 0, 0.25, 0.75, 0.75, 1.0]
     with pytest.raises(ZeroDivisionError):

@@ -20,7 +20,7 @@ only the calls the reference makes:
 Model: genes 50 kb apart on one contig, 3-6 exons with gt..ag introns, reads
 covering most of the transcript, per-read haplotype, het SNPs that follow the
 haplotype, A>G editing sites (T>C on the minus strand) with Beta(2,5) levels of
-which 30 % are haplotype-linked, 1 % substitution noise.
+which 30 % are haplotype-linked, 0.2 % substitution noise.
 """
 from __future__ import annotations
 
@@ -152,7 +152,7 @@ class Dataset:
     """chrom, genome (str), reads (sorted by start), gtf entries, snp positions, repeats."""
 
     def __init__(self, seed=20261018, n_genes=8, reads_per_gene=120, chrom="chr1", gene_spacing=50000,
-                 n_het=(3, 8), n_edit=(10, 40), noise=0.01):
+                 n_het=(3, 8), n_edit=(10, 40), noise=0.002):
         rng = np.random.Generator(np.random.PCG64(seed))
         self.chrom = chrom
         L = 20000 + gene_spacing * n_genes + 20000
