@@ -19,7 +19,7 @@ import numpy as np
 from . import _lib
 from ._lib import (MODE_ALL_PAIRS, MODE_EMIT_COUNTS, MODE_HET_ONLY, MODE_SKIP_NONHET,
                    PAIR_REC, SITE_TYPE_CODE, LgmiError, Result, array_at, check, ptr)
-from .encode import PlaneBatch, encode_batch, encode_mismatches, pack_units
+from .encode import EncodedUnit, PlaneBatch, encode_batch, encode_mismatches, pack_units
 
 
 class Context:
@@ -327,6 +327,51 @@ def mip_and_calls(mean_mi, site_types, threshold=0.05, ctx=None):
     check(ctx._lib.lgmi_ecdf(ctx.handle, ptr(mean), ptr(flags), mean.size, float(threshold), ptr(mip), ptr(call)),
           ctx.handle)
     return mip, call
+
+
+# --------------------------------------------------------------------------- #
+# site x splice-site MI: the reference's second mutual_info_score call site
+# --------------------------------------------------------------------------- #
+def site_splice_mutual_info(sites, splices, pairs, ctx=None):
+    """The loop of giremi/script/calculate_site_splice_mi.py:106-125 as ONE submit.
+
+    `sites`   {site label: {allele: [read names]}}      (:88-92)
+    `splices` {splice label: [read names]}              (:95-102)
+    `pairs`   iterable of (site label, allele, splice label)   (rows of the pair table)
+
+    Returns the MI of every pair, in order: over all list entries of the site's reads
+    (a read listed twice counts twice, :117-120), labels "carries the allele" x "has the
+    splice site" by read NAME (:121-122).  Each site becomes one unit whose pseudo-sites
+    are the requested alleles and splice sites; every pseudo-site covers every entry, the
+    "with" reads are its major plane, the others its minor plane, so the kernels' 2x2
+    table is the reference's (0/1 sort like minor/major)."""
+    pairs = [tuple(p) for p in pairs]
+    by_site = {}
+    for k, (site_label, seq, splice_label) in enumerate(pairs):
+        by_site.setdefault(site_label, []).append((k, seq, splice_label))
+    units, lookup = [], []                    # lookup[u] = [(pair index, i, j), ...]
+    for site_label, wanted in by_site.items():
+        alleles = sites[site_label]
+        entries = sorted(name for allele in alleles for name in alleles[allele])
+        seqs = list(dict.fromkeys(seq for _k, seq, _s in wanted))
+        spl = list(dict.fromkeys(s for _k, _seq, s in wanted))
+        members = [set(alleles[seq]) for seq in seqs] + [set(splices.get(s, ())) for s in spl]
+        labels = np.empty((len(members), len(entries)), dtype=np.uint8)
+        for row, names in enumerate(members):
+            labels[row] = [2 if name in names else 1 for name in entries]
+        units.append(EncodedUnit(list(range(len(members))), ['mismatch'] * len(members), labels))
+        lookup.append([(k, seqs.index(seq), len(seqs) + spl.index(s)) for k, seq, s in wanted])
+    out = [0.0] * len(pairs)
+    if not units:
+        return out
+    res = mi_step_batched(pack_units(units), 0, MODE_ALL_PAIRS, ctx=ctx)
+    for u, want in enumerate(lookup):
+        rec = res.unit_records(u)
+        S = units[u].n_sites
+        assert len(rec) == S * (S - 1) // 2   # min_common 0: every pair is there, in (i, j) order
+        for k, i, j in want:
+            out[k] = float(rec['mi'][i * (2 * S - i - 1) // 2 + (j - i - 1)])
+    return out
 
 
 # --------------------------------------------------------------------------- #

@@ -283,3 +283,24 @@ def threshold_calls(mean_mi, mip, is_mismatch, threshold=0.05):
         call[valid & (mip <= threshold) & is_mismatch] = CALL_POS
         call[valid & (mip > threshold) & ~is_mismatch] = CALL_NEG
     return call
+
+
+# --------------------------------------------------------------------------- #
+# site x splice-site MI (script/calculate_site_splice_mi.py:106-125)
+# --------------------------------------------------------------------------- #
+def site_splice_mutual_info(sites, splices, pairs):
+    """For every (site label, allele, splice label) of `pairs`: over ALL list entries of the
+    site's reads, sorted (:117-120; a read listed twice counts twice), the 0/1 vectors
+    "read carries the allele" and "read has the splice site" (:121-122, membership by NAME),
+    and their mutual_info_score (:123).  `sites`: {label: {allele: [read names]}},
+    `splices`: {label: [read names]}."""
+    out = []
+    for site_label, seq, splice_label in pairs:
+        with_seq_names = set(sites[site_label][seq])
+        with_splice_names = set(splices.get(splice_label, ()))
+        reads = sorted(name for allele in sites[site_label] for name in sites[site_label][allele])
+        table = [[0, 0], [0, 0]]
+        for name in reads:
+            table[int(name in with_seq_names)][int(name in with_splice_names)] += 1
+        out.append(mi_from_table(table))
+    return out
