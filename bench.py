@@ -249,6 +249,11 @@ def dense_leg(lg, synth, ctx, torch, stream, steps, warmup, flush):
     algo_ops = 2 * 9 * pairs * R                             # nine count matrices over the upper triangle
     g_ms = sum(gram_ms) / len(gram_ms)
     peaks, src = load_peaks()
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_gram_i8_dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     bf16 = float(peaks.get("bf16_tflops", 1590.0))
     peak = 2.0 * bf16                                        # int8 dense = 2x bf16 dense on sm_100
     out = {
@@ -256,7 +261,7 @@ def dense_leg(lg, synth, ctx, torch, stream, steps, warmup, flush):
         "pairs_per_step": pairs, "surviving_pairs": int(r.n_records), "ms_per_step": step_ms,
         "value": pairs / (step_ms * 1e-3), "unit": UNIT,
         "roofline": {"bound": "tensor", "achieved": algo_ops / (g_ms * 1e-3) / 1e12, "peak": peak, "unit": "TOP/s",
-                     "frac": algo_ops / (g_ms * 1e-3) / 1e12 / peak, "traffic": None, "kernel": "k_gram_i8",
+                     "frac": algo_ops / (g_ms * 1e-3) / 1e12 / peak, "traffic": traffic, "kernel": "k_gram_i8",
                      "kernel_ms": g_ms, "algorithmic_ops": algo_ops, "issued_ops": 2 * int(r.gram_macs),
                      "issued_tops": 2 * int(r.gram_macs) / (g_ms * 1e-3) / 1e12,
                      "peak_source": "2 x bf16_tflops burst, %s" % src,
