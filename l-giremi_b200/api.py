@@ -54,6 +54,10 @@ class Context:
         """Units at least this large take the int8 tensor-core path (batches created afterwards)."""
         check(self._lib.lgmi_set_dense_threshold(self.handle, int(min_sites), int(min_reads)), self.handle)
 
+    def set_small_path(self, tensor_cores):
+        """Small units counted on the tensor cores (True, default) or by popcount (False)."""
+        check(self._lib.lgmi_set_small_path(self.handle, 1 if tensor_cores else 0), self.handle)
+
     @property
     def launch_count(self):
         return int(self._lib.lgmi_launch_count(self.handle))

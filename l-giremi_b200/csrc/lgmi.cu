@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <queue>
@@ -46,6 +47,8 @@ struct lgmi_ctx {
   // persistent launch shape of k_pairs
   int num_sms = 0;
   int pairs_ctas_per_sm = 0;
+  int pre_ctas_per_sm = 0;
+  int small_path = 1;  // 1: small units counted on the tensor cores (k_small_gram + k_pairs_pre); 0: popcount (k_pairs_fast)
   // tensor-core path: units at least this large build their tables with k_gram_i8
   uint32_t dense_min_sites = 48, dense_min_reads = 8192;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
@@ -96,6 +99,10 @@ struct lgmi_batch {
   uint32_t* d_gram = nullptr;   // nine count matrices per dense unit
   DenseTile* d_tiles = nullptr;
   uint64_t dense_macs = 0;      // multiply-accumulates the tile lists amount to
+  // small units counted on the tensor cores
+  FastItem* d_pre_items = nullptr;
+  uint32_t n_pre = 0;
+  unsigned long long* d_val = nullptr;  // packed counts, 8 bytes per candidate pair of those units
   // tiled popcount path
   TileItem* d_tile_items = nullptr;
   uint32_t n_tile_items = 0;
@@ -206,6 +213,18 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
     lgmi_destroy(ctx);
     return rc;
   }
+  if (cudaFuncSetAttribute(k_small_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SgSmem) + 1024)) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(k_pairs_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PreSmem)) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pre_ctas_per_sm, k_pairs_pre, kFastThreads, sizeof(PreSmem)) !=
+          cudaSuccess ||
+      ctx->pre_ctas_per_sm < 1) {
+    int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: small-unit tensor path cannot be resident (%s)",
+                  cudaGetErrorString(cudaGetLastError()));
+    lgmi_destroy(ctx);
+    return rc;
+  }
+  if (const char* e = getenv("LGMI_SMALL_PATH")) ctx->small_path = atoi(e) ? 1 : 0;
   {
     cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &q) != cudaSuccess ||
@@ -276,6 +295,12 @@ extern "C" int lgmi_pinned_free(lgmi_t* ctx, void* ptr) {
 
 extern "C" uint64_t lgmi_launch_count(const lgmi_t* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int lgmi_set_small_path(lgmi_t* ctx, int tensor_cores) {
+  if (!ctx) return LGMI_ERR_ARG;
+  ctx->small_path = tensor_cores ? 1 : 0;
+  return LGMI_OK;
+}
+
 extern "C" int lgmi_set_dense_threshold(lgmi_t* ctx, uint32_t min_sites, uint32_t min_reads) {
   if (!ctx) return LGMI_ERR_ARG;
   if (min_sites < 2) return fail(ctx, LGMI_ERR_ARG, "lgmi_set_dense_threshold: min_sites must be >= 2");
@@ -317,6 +342,8 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   cudaFree(b->d_tiles);
   cudaFree(b->d_tile_items);
   cudaFree(b->d_tile_counts);
+  cudaFree(b->d_pre_items);
+  cudaFree(b->d_val);
   cudaFreeHost(b->h_header);
   cudaFreeHost(b->h_records);
   cudaFreeHost(b->h_counts);
@@ -340,7 +367,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   b->h_units.assign(units, units + n_units);
 
   std::vector<DevUnit> du(n_units);
-  std::vector<FastItem> fast_items;
+  std::vector<FastItem> fast_items, pre_items;
+  uint64_t val_slots = 0;
   std::vector<MeanItem> mean_items;
   std::vector<DenseTile> dense_tiles;
   std::vector<TileItem> tile_items;
@@ -440,7 +468,14 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
         f.R = (uint16_t)u.n_reads;
         f.W = u.row_words;
         f.pad = 0;
-        fast_items.push_back(f);
+        if (ctx->small_path && u.n_sites <= (uint32_t)kSgMaxS && val_slots + np + 1 < 0xffffffffull) {
+          it.flags |= ITEM_PRE;
+          f.pad = (uint32_t)val_slots;          // first slot of the unit's packed counts (even: 16-byte aligned)
+          val_slots += (np + 1) & ~1ull;
+          pre_items.push_back(f);
+        } else {
+          fast_items.push_back(f);
+        }
       }
       b->h_items.push_back(it);
     }
@@ -458,6 +493,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
 
   b->n_items = (uint32_t)b->h_items.size();
   b->n_fast = (uint32_t)fast_items.size();
+  b->n_pre = (uint32_t)pre_items.size();
   b->n_mean_items = (uint32_t)mean_items.size();
   b->n_dense = dense;
 
@@ -492,6 +528,12 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   BCU(cudaMalloc(&b->d_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t)));
   BCU(cudaMalloc(&b->d_dense, std::max<uint64_t>(1, dense) * sizeof(double)));
   BCU(cudaMalloc(&b->d_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long)));
+  if (!pre_items.empty()) {
+    BCU(cudaMalloc(&b->d_pre_items, pre_items.size() * sizeof(FastItem)));
+    BCU(cudaMemcpyAsync(b->d_pre_items, pre_items.data(), pre_items.size() * sizeof(FastItem), cudaMemcpyHostToDevice,
+                        bstream(b)));
+    BCU(cudaMalloc(&b->d_val, val_slots * sizeof(unsigned long long)));
+  }
   if (!tile_items.empty()) {
     BCU(cudaMalloc(&b->d_tile_items, tile_items.size() * sizeof(TileItem)));
     BCU(cudaMemcpyAsync(b->d_tile_items, tile_items.data(), tile_items.size() * sizeof(TileItem), cudaMemcpyHostToDevice,
@@ -614,7 +656,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     const uint64_t n = std::max<uint64_t>(std::max<uint64_t>(b->n_sites, b->n_items), (uint64_t)b->n_units + 1);
     k_run_init<<<(unsigned)((n + 255) / 256), 256, 0, bstream(b)>>>(b->d_header, b->d_unit_rec_off, b->n_units + 1,
                                                                   b->d_item_dense, b->n_items, b->d_n_generic,
-                                                                  b->n_items - b->n_fast, b->d_site_mean, b->d_site_cnt,
+                                                                  b->n_items - b->n_fast - b->n_pre, b->d_site_mean, b->d_site_cnt,
                                                                   b->n_sites);
     ++ctx->launches;
   }
@@ -646,6 +688,24 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     k_tile_mi<<<tgrid, kThreads, 0, bstream(b)>>>(P, b->d_tile_items, b->n_tile_items);
     ++ctx->launches;
   }
+  if (b->n_pre) {
+    // small units: counts of every pair on the tensor cores -> packed values + emitted pairs per unit
+    SgParams G;
+    G.items = b->d_pre_items;
+    G.n_items = b->n_pre;
+    G.planes = b->d_planes;
+    G.site_flags = b->d_flags;
+    G.min_common = min_common;
+    G.mode = mode;
+    G.val = b->d_val;
+    G.item_cnt = b->d_item_cnt;
+    G.item_dense = b->d_item_dense;
+    G.n_generic = b->d_n_generic;
+    G.error = reinterpret_cast<uint32_t*>(&b->d_header->pad);
+    const unsigned grid = (unsigned)std::min<uint64_t>(b->n_pre, (uint64_t)ctx->num_sms * 2u);
+    k_small_gram<<<grid, kSgThreads, sizeof(SgSmem) + 1024, bstream(b)>>>(G);
+    ++ctx->launches;
+  }
   if (b->n_items) {
     // K0 + scan: every item's place in the ordered output
     const unsigned cgrid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 8u);
@@ -658,7 +718,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     ++ctx->launches;
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[2], bstream(b)));
-  if (b->n_fast) {
+  if (b->n_fast || b->n_pre) {
     FastParams F;
     F.items = b->d_fast_items;
     F.n_items = b->n_fast;
@@ -677,10 +737,22 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     F.site_cnt = b->d_site_cnt;
     F.unit_rec_off = b->d_unit_rec_off;
     F.unit_base = b->unit_base;
-    // persistent CTAs: a whole number of CTAs per SM, never more than there are items
-    const unsigned grid = (unsigned)std::min<uint64_t>(b->n_fast, (uint64_t)ctx->num_sms * ctx->pairs_ctas_per_sm);
-    k_pairs_fast<<<grid, kFastThreads, sizeof(FastSmem), bstream(b)>>>(F);
-    ++ctx->launches;
+    if (b->n_pre) {
+      PreParams Q;
+      Q.F = F;
+      Q.F.items = b->d_pre_items;
+      Q.F.n_items = b->n_pre;
+      Q.val = b->d_val;
+      const unsigned grid = (unsigned)std::min<uint64_t>(b->n_pre, (uint64_t)ctx->num_sms * ctx->pre_ctas_per_sm);
+      k_pairs_pre<<<grid, kFastThreads, sizeof(PreSmem), bstream(b)>>>(Q);
+      ++ctx->launches;
+    }
+    if (b->n_fast) {
+      // persistent CTAs: a whole number of CTAs per SM, never more than there are items
+      const unsigned grid = (unsigned)std::min<uint64_t>(b->n_fast, (uint64_t)ctx->num_sms * ctx->pairs_ctas_per_sm);
+      k_pairs_fast<<<grid, kFastThreads, sizeof(FastSmem), bstream(b)>>>(F);
+      ++ctx->launches;
+    }
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[3], bstream(b)));
   if (b->n_items) {

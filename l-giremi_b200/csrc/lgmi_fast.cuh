@@ -78,6 +78,9 @@ struct FastSmem {
   uint8_t nonhet_list[kFastMaxS];                        // ... the other sites ascending
   unsigned long long het_mask;
   uint32_t n_list2, n_list3, next_chunk, total;
+  __device__ __forceinline__ uint32_t oth_count(uint32_t s) const {
+    return n_oth[s] < (uint32_t)kOthCap ? n_oth[s] : (uint32_t)kOthCap;
+  }
 };
 
 __device__ __forceinline__ double mi_nan() { return __longlong_as_double(0x7ff8000000000000LL); }

@@ -90,11 +90,11 @@ __device__ __forceinline__ void fast_land(FastSmem& sm, uint32_t* __restrict__ r
 
 // ordered lists of the het sites and of the other sites (for the mean phase), and the
 // per-site byte the counts phase reads: bit 0 het_snp, bits 1-4 number of "other" reads
-__device__ __forceinline__ void fast_site_lists(FastSmem& sm, uint32_t S) {
+template <class SM>
+__device__ __forceinline__ void fast_site_lists(SM& sm, uint32_t S) {
   const uint32_t s = threadIdx.x;
   if (s < S) {
-    sm.info[s] = (uint8_t)(((sm.flags[s] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP ? 1u : 0u) |
-                           (min(sm.n_oth[s], (uint32_t)kOthCap) << 1));
+    sm.info[s] = (uint8_t)(((sm.flags[s] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP ? 1u : 0u) | (sm.oth_count(s) << 1));
     const unsigned long long het = sm.het_mask;
     const uint32_t rank = __popcll(het & ((1ull << s) - 1ull));
     if ((het >> s) & 1ull) sm.het_list[rank] = (uint8_t)s;
@@ -192,7 +192,8 @@ __device__ __forceinline__ void unpack_counts(unsigned long long v, uint32_t& n_
 }
 
 // MI of the listed pairs, in place of their packed counts; warp-sized chunks of both lists
-__device__ __forceinline__ void fast_mi(FastSmem& sm) {
+template <class SM>
+__device__ __forceinline__ void fast_mi(SM& sm, unsigned long long* __restrict__ val) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t n2 = sm.n_list2, n3 = sm.n_list3;
   const uint32_t nc2 = (n2 + 31u) >> 5, nc3 = (n3 + 31u) >> 5;
@@ -202,15 +203,15 @@ __device__ __forceinline__ void fast_mi(FastSmem& sm) {
       if (q < n2) {
         const uint32_t p = sm.list[q];
         uint32_t n_mm, n_mM, n_Mm, n_MM;
-        unpack_counts(sm.val[p], n_mm, n_mM, n_Mm, n_MM);
+        unpack_counts(val[p], n_mm, n_mM, n_Mm, n_MM);
         const double mi = mi_2x2(sm.tab, n_mm, n_mM, n_Mm, n_MM);
-        sm.val[p] = (unsigned long long)__double_as_longlong(mi);
+        val[p] = (unsigned long long)__double_as_longlong(mi);
       }
     } else {
       const uint32_t q = (c - nc2) * 32u + lane;
       if (q < n3) {
         const uint32_t p = sm.list[kFastMaxPairs - 1u - q];
-        const unsigned long long v = sm.val[p];
+        const unsigned long long v = val[p];
         const uint32_t o = (uint32_t)(v >> 36);
         uint32_t T[9];
         unpack_counts(v, T[4], T[5], T[7], T[8]);
@@ -220,14 +221,15 @@ __device__ __forceinline__ void fast_mi(FastSmem& sm) {
         T[3] = (o >> 9) & 7u;
         T[6] = (o >> 12) & 7u;
         const double mi = mi_3x3(sm.tab, T);
-        sm.val[p] = (unsigned long long)__double_as_longlong(mi);
+        val[p] = (unsigned long long)__double_as_longlong(mi);
       }
     }
   }
 }
 
 // exclusive prefix of the chunk emit counts (warp 0)
-__device__ __forceinline__ void fast_chunk_prefix(FastSmem& sm, uint32_t n_chunks) {
+template <class SM>
+__device__ __forceinline__ void fast_chunk_prefix(SM& sm, uint32_t n_chunks) {
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t carry = 0u;
   for (uint32_t c0 = 0; c0 < n_chunks; c0 += 32u) {
@@ -250,8 +252,9 @@ __device__ __forceinline__ void fast_chunk_prefix(FastSmem& sm, uint32_t n_chunk
 
 // ordered write of the surviving pairs: one 16-byte record {unit, i | j << 16, mi} each.
 // Warps [first_warp, 8) share the chunks; the first two warps are busy with the mean phase.
-__device__ __forceinline__ void fast_emit(const FastParams& P, FastSmem& sm, const FastItem& it,
-                                          const uint16_t* __restrict__ ijt, unsigned long long base,
+template <class SM>
+__device__ __forceinline__ void fast_emit(const FastParams& P, SM& sm, const unsigned long long* __restrict__ val,
+                                          const FastItem& it, const uint16_t* __restrict__ ijt, unsigned long long base,
                                           uint32_t n_chunks, uint32_t first_warp) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -261,7 +264,7 @@ __device__ __forceinline__ void fast_emit(const FastParams& P, FastSmem& sm, con
       const uint32_t p = c * 32u + lane;
       const unsigned long long slot = base + sm.chunk_off[c] + __popc(mask & lt);
       const uint32_t ij = __ldg(ijt + p);
-      const unsigned long long bits = sm.val[p];
+      const unsigned long long bits = val[p];
       uint4 rec;
       rec.x = it.unit + P.unit_base;
       rec.y = (ij >> 6) | ((ij & 63u) << 16);
@@ -276,8 +279,9 @@ __device__ __forceinline__ void fast_emit(const FastParams& P, FastSmem& sm, con
 // packed counts and "other" cells the MI epilogue is about to consume (so what is
 // checked bit-for-bit against the oracle is exactly what MI is computed from).
 // Runs between the counts phase and fast_mi.
-__device__ __forceinline__ void fast_emit_counts(const FastParams& P, FastSmem& sm, unsigned long long base,
-                                                 uint32_t n_chunks) {
+template <class SM>
+__device__ __forceinline__ void fast_emit_counts(const FastParams& P, SM& sm, const unsigned long long* __restrict__ val,
+                                                 unsigned long long base, uint32_t n_chunks) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   for (uint32_t c = warp; c < n_chunks; c += kFastWarps) {
@@ -285,7 +289,7 @@ __device__ __forceinline__ void fast_emit_counts(const FastParams& P, FastSmem& 
     if ((mask >> lane) & 1u) {
       const uint32_t p = c * 32u + lane;
       const unsigned long long slot = base + sm.chunk_off[c] + __popc(mask & lt);
-      const unsigned long long v = sm.val[p];
+      const unsigned long long v = val[p];
       const uint32_t o = (uint32_t)(v >> 36);
       uint32_t* out = P.counts + slot * 9ull;
       uint32_t n_mm, n_mM, n_Mm, n_MM;
@@ -325,11 +329,13 @@ struct MeanAcc {
   }
 };
 
-__device__ __forceinline__ void fast_means(const FastParams& P, FastSmem& sm, const FastItem& it) {
+template <class SM>
+__device__ __forceinline__ void fast_means(const FastParams& P, SM& sm, const unsigned long long* __restrict__ val,
+                                           const FastItem& it) {
   const uint32_t tid = threadIdx.x, S = it.S;
   if (tid >= S) return;
   const uint32_t n_het = __popcll(sm.het_mask);
-  const double* s_mi = reinterpret_cast<const double*>(sm.val);
+  const double* s_mi = reinterpret_cast<const double*>(val);
   MeanAcc acc{0.0, 0.0, 0u};
   uint32_t s;
   if (tid < n_het) {
@@ -422,15 +428,15 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
       if (tid < 32u) fast_chunk_prefix(sm, n_chunks);
       if (P.mode & LGMI_MODE_EMIT_COUNTS) {
         __syncthreads();
-        fast_emit_counts(P, sm, base, n_chunks);
+        fast_emit_counts(P, sm, sm.val, base, n_chunks);
       }
-      fast_mi(sm);
+      fast_mi(sm, sm.val);
       __syncthreads();
       if (tid == 0) P.unit_rec_off[it.unit] = base;
       // the serial per-site sums occupy the first one or two warps; the others write the records
       const uint32_t mean_warps = (S + 31u) >> 5;
-      if ((tid >> 5) < mean_warps) fast_means(P, sm, it);
-      else fast_emit(P, sm, it, ijt, base, n_chunks, mean_warps);
+      if ((tid >> 5) < mean_warps) fast_means(P, sm, sm.val, it);
+      else fast_emit(P, sm, sm.val, it, ijt, base, n_chunks, mean_warps);
     } else {
       cp_async_wait<1>();
     }

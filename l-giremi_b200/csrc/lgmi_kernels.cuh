@@ -20,6 +20,7 @@
 #include "lgmi_math.cuh"
 #include "lgmi_fast_kernel.cuh"
 #include "lgmi_dense.cuh"
+#include "lgmi_small.cuh"
 
 namespace lgmi {
 
@@ -37,7 +38,7 @@ struct DevUnit {
 };
 constexpr uint64_t kNoGram = ~0ull;
 
-enum : uint32_t { ITEM_FIRST = 1u, ITEM_SINGLE = 2u, ITEM_FAST = 4u };
+enum : uint32_t { ITEM_FIRST = 1u, ITEM_SINGLE = 2u, ITEM_FAST = 4u, ITEM_PRE = 8u /* counted by k_small_gram */ };
 
 struct Item {
   uint32_t unit;
@@ -517,6 +518,7 @@ __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
   const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
   for (uint32_t item_idx = blockIdx.x; item_idx < P.n_items; item_idx += gridDim.x) {
     const Item it = P.items[item_idx];
+    if (it.flags & ITEM_PRE) continue;  // k_small_gram has written this item's count
     const DevUnit u = P.units[it.unit];
     const uint8_t* __restrict__ flags = P.site_flags + u.site_off;
     uint32_t mine = 0;

@@ -321,6 +321,51 @@ def test_cfg3_full_size_dense_equals_popcount_and_oracle(lg, gpu_ctx):
     assert_mi_close(rec['mi'][at], mi, 0.9)
 
 
+def test_small_units_popcount_and_tensor_paths_agree(lg, gpu_ctx):
+    """Small units (<= 60 sites, <= 256 reads) counted by k_small_gram (int8 Gram matrix per
+    unit, default) and by k_pairs_fast's AND+popcount: same records, 3x3 tables and means bit
+    for bit, both against the oracle; sizes around every block boundary of the tensor layout
+    (10 sites per 32-lane group, 40 per M block, 128 reads per k-block)."""
+    rng = np.random.default_rng(41)
+    shapes = [(2, 6), (3, 40), (9, 128), (10, 129), (11, 200), (20, 256), (30, 31), (31, 255), (39, 100), (40, 128),
+              (41, 129), (50, 200), (59, 256), (60, 200), (61, 200), (64, 256)]
+    eus = [_synth_unit(rng, S, R, float(rng.uniform(0.3, 0.95))) for S, R in shapes]
+    eus += [lg.encode_mismatches(random_mismatches(rng)) for _ in range(60)]
+    eus = [e for e in eus if not e.bad_sites]
+    mode = lg.MODE_ALL_PAIRS | lg.MODE_EMIT_COUNTS
+    try:
+        gpu_ctx.set_small_path(False)
+        popc = check_batch(lg, gpu_ctx, eus, 6)
+        gpu_ctx.set_small_path(True)
+        tens = check_batch(lg, gpu_ctx, eus, 6)
+        for mc in (1, 20):
+            gpu_ctx.set_small_path(False)
+            a = lg.mi_step_batched(lg.pack_units(eus), mc, mode, ctx=gpu_ctx)
+            gpu_ctx.set_small_path(True)
+            b = lg.mi_step_batched(lg.pack_units(eus), mc, mode, ctx=gpu_ctx)
+            assert np.array_equal(a.records, b.records) and np.array_equal(a.counts, b.counts)
+            assert np.array_equal(a.site_mean, b.site_mean, equal_nan=True)
+    finally:
+        gpu_ctx.set_small_path(True)
+    assert np.array_equal(popc.records, tens.records) and np.array_equal(popc.counts, tens.counts)
+    assert np.array_equal(popc.site_mean, tens.site_mean, equal_nan=True)
+
+
+def test_small_units_many_others_fall_back(lg, gpu_ctx):
+    """More than 7 'other' reads in a cell does not fit the packed form: the unit is flagged and
+    the generic kernel takes it, on either small-unit path."""
+    rng = np.random.default_rng(42)
+    lab = rng.choice(np.array([0, 1, 2, 255], np.uint8), size=(12, 150), p=[0.3, 0.3, 0.3, 0.1])
+    eu = enc.EncodedUnit(list(range(12)), ['het_snp', 'mismatch'] * 6, lab)
+    ok = _synth_unit(rng, 20, 100, 0.6)
+    for tensor in (True, False):
+        gpu_ctx.set_small_path(tensor)
+        try:
+            check_batch(lg, gpu_ctx, [ok, eu, ok], 6)
+        finally:
+            gpu_ctx.set_small_path(True)
+
+
 # --------------------------------------------------------------------------- pipelined step
 @pytest.mark.parametrize("n_chunks", [1, 2, 5, 64])
 def test_pipelined_step_equals_one_submit(lg, gpu_ctx, n_chunks):
