@@ -167,10 +167,11 @@ LGMI_API uint64_t lgmi_launch_count(const lgmi_t* ctx);
  * (mutual_information.py:15-40).  Default 48 sites x 8192 reads; applies to   *
  * batches created afterwards.  Tests lower it to force the path.              */
 LGMI_API int lgmi_set_dense_threshold(lgmi_t* ctx, uint32_t min_sites, uint32_t min_reads);
-/* Small units (<= 60 sites, <= 256 reads) have their counts built as one small *
- * int8 Gram matrix per unit on the tensor cores (tensor_cores != 0, default)  *
- * or by AND+popcount (0).  Same integers either way; applies to batches       *
- * created afterwards.  Environment LGMI_SMALL_PATH=0/1 sets the default.      */
+/* Small units (<= 60 sites, <= 256 reads) have their counts built by          *
+ * AND+popcount (0, default) or as one small int8 Gram matrix per unit on the  *
+ * tensor cores (tensor_cores != 0: k_small_gram + k_pairs_pre).  Same         *
+ * integers either way; applies to batches created afterwards.  Environment    *
+ * LGMI_SMALL_PATH=0/1 sets the default.                                       */
 LGMI_API int lgmi_set_small_path(lgmi_t* ctx, int tensor_cores);
 
 /* ----- batched MI step: replaces the per-unit loop                           *

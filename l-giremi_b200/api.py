@@ -55,7 +55,7 @@ class Context:
         check(self._lib.lgmi_set_dense_threshold(self.handle, int(min_sites), int(min_reads)), self.handle)
 
     def set_small_path(self, tensor_cores):
-        """Small units counted on the tensor cores (True, default) or by popcount (False)."""
+        """Small units counted by popcount (False, default) or on the tensor cores (True)."""
         check(self._lib.lgmi_set_small_path(self.handle, 1 if tensor_cores else 0), self.handle)
 
     @property

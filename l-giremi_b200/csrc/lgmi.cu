@@ -48,7 +48,7 @@ struct lgmi_ctx {
   int num_sms = 0;
   int pairs_ctas_per_sm = 0;
   int pre_ctas_per_sm = 0;
-  int small_path = 1;  // 1: small units counted on the tensor cores (k_small_gram + k_pairs_pre); 0: popcount (k_pairs_fast)
+  int small_path = 0;  // 0: popcount (k_pairs_fast, default: faster); 1: counted on the tensor cores
   // tensor-core path: units at least this large build their tables with k_gram_i8
   uint32_t dense_min_sites = 48, dense_min_reads = 8192;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)

@@ -63,6 +63,7 @@ struct SgSmem {
   uint8_t X[2][kSgKbBytes];                 // 64 KB, 1024-byte aligned
   uint32_t planes[2][kSgMaxS * 24];         // landed rows [M 8 | m 8 | C 8], double-buffered
   uint8_t flags[2][64];
+  uint32_t het[2];                          // het_snp sites of the current unit, bit s
   uint64_t mma_bar;
   uint32_t tmem_slot;
   uint32_t n_emit, overflow;
@@ -143,6 +144,12 @@ __global__ void __launch_bounds__(kSgThreads, 2) k_small_gram(const SgParams P) 
     cp_async_wait<0>();
     __syncthreads();  // planes + flags of this unit landed; the previous unit's readout is over (X, TMEM free)
 
+    if (warp < 2u) {
+      const uint32_t s = warp * 32u + lane;
+      const bool h = s < S && (sm.flags[buf][s] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
+      const uint32_t m = __ballot_sync(0xffffffffu, h);
+      if (lane == 0) sm.het[warp] = m;
+    }
     // ---- expand: one thread per (site, 16-read chunk), the three label rows at once
     {
       const uint32_t* __restrict__ pl = sm.planes[buf];
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(kSgThreads, 2) k_small_gram(const SgParams P) 
     {
       const uint32_t lq = warp & 3u, half = warp >> 2;
       const uint32_t si = lane / 3u, a = lane - 3u * si;  // lanes 30, 31 carry the padding rows
-      const uint8_t* __restrict__ fl = sm.flags[buf];
+      const unsigned long long het_mask = (unsigned long long)sm.het[0] | ((unsigned long long)sm.het[1] << 32);
       unsigned long long* __restrict__ vout = P.val + it.pad;
       uint32_t n_emit = 0u;
       bool overflow = false;
@@ -208,7 +215,8 @@ __global__ void __launch_bounds__(kSgThreads, 2) k_small_gram(const SgParams P) 
         if (g >= ng) continue;
         const uint32_t i = kSgSitesPerGroup * g + si;
         const bool row_ok = lane < 30u && i < S;
-        const bool het_i = row_ok && (fl[row_ok ? i : 0u] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
+        const bool het_i = ((het_mask >> (i & 63u)) & 1ull) != 0ull;
+        unsigned long long* __restrict__ vrow = vout + ((long long)((i * (2u * S - i - 1u)) / 2u) - (long long)i - 1ll);  // + j
         for (uint32_t q = g + half; q < ng; q += 2u) {
           uint32_t r[32];
           const uint32_t col = mb ? (32u * ng + 32u * (q - 4u)) : 32u * q;
@@ -226,28 +234,33 @@ __global__ void __launch_bounds__(kSgThreads, 2) k_small_gram(const SgParams P) 
               k2[sj / 3] = w2;
             }
           }
+          const uint32_t j0 = kSgSitesPerGroup * q + a;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const uint32_t sj = 3u * t + a;
-            const uint32_t j = kSgSitesPerGroup * q + sj;
-            const bool ok = row_ok && sj < (uint32_t)kSgSitesPerGroup && j < S && i < j;
-            unsigned long long v = kNoMi;
+            const uint32_t j = j0 + 3u * t;
+            const bool ok = row_ok && 3u * t + a < (uint32_t)kSgSitesPerGroup && j < S && i < j;
             bool emit = false;
             if (ok) {
-              const uint32_t T00 = k0[t] & 1023u, T01 = (k0[t] >> 10) & 1023u, T02 = k0[t] >> 20;
-              const uint32_t T10 = k1[t] & 1023u, T11 = (k1[t] >> 10) & 1023u, T12 = k1[t] >> 20;
-              const uint32_t T20 = k2[t] & 1023u, T21 = (k2[t] >> 10) & 1023u, T22 = k2[t] >> 20;
+              unsigned long long v = kNoMi;
+              const uint32_t T11 = (k1[t] >> 10) & 1023u, T12 = k1[t] >> 20;
+              const uint32_t T21 = (k2[t] >> 10) & 1023u, T22 = k2[t] >> 20;
               const uint32_t nMP = T21 + T22, nPM = T12 + T22, nPP = T11 + T12 + nMP;
-              const uint32_t n_common = nPP + T00 + T01 + T02 + T10 + T20;
-              const bool het = het_i || (fl[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
-              if ((het || !skip_nonhet) && (int)n_common >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
+              const uint32_t oth = k0[t] | ((k1[t] | k2[t]) & 1023u);  // any cell with an "other" label
+              uint32_t n_common = nPP, o = 0u;
+              if (oth) {
+                const uint32_t T00 = k0[t] & 1023u, T01 = (k0[t] >> 10) & 1023u, T02 = k0[t] >> 20;
+                const uint32_t T10 = k1[t] & 1023u, T20 = k2[t] & 1023u;
+                n_common += T00 + T01 + T02 + T10 + T20;
                 overflow |= ((T00 | T01 | T02 | T10 | T20) > 7u);
-                const uint32_t o = (T00 & 7u) | ((T01 & 7u) << 3) | ((T02 & 7u) << 6) | ((T10 & 7u) << 9) | ((T20 & 7u) << 12);
+                o = (T00 & 7u) | ((T01 & 7u) << 3) | ((T02 & 7u) << 6) | ((T10 & 7u) << 9) | ((T20 & 7u) << 12);
+              }
+              const bool het = het_i || ((het_mask >> j) & 1ull) != 0ull;
+              if ((het || !skip_nonhet) && (int)n_common >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
                 emit = het || !het_only;
                 v = (unsigned long long)(nPP | (nMP << 9) | (nPM << 18)) | ((unsigned long long)T22 << 27) |
-                    ((unsigned long long)o << 36) | (emit ? kValEmit : 0ull);
+                    ((unsigned long long)(o | (emit ? 1u << 16 : 0u)) << 36);
               }
-              vout[(i * (2u * S - i - 1u)) / 2u + (j - i - 1u)] = v;
+              vrow[j] = v;
             }
             n_emit += __popc(__ballot_sync(0xffffffffu, emit));
           }

@@ -322,8 +322,8 @@ def test_cfg3_full_size_dense_equals_popcount_and_oracle(lg, gpu_ctx):
 
 
 def test_small_units_popcount_and_tensor_paths_agree(lg, gpu_ctx):
-    """Small units (<= 60 sites, <= 256 reads) counted by k_small_gram (int8 Gram matrix per
-    unit, default) and by k_pairs_fast's AND+popcount: same records, 3x3 tables and means bit
+    """Small units (<= 60 sites, <= 256 reads) counted by k_pairs_fast's AND+popcount (default) and
+    by k_small_gram (int8 Gram matrix per unit): same records, 3x3 tables and means bit
     for bit, both against the oracle; sizes around every block boundary of the tensor layout
     (10 sites per 32-lane group, 40 per M block, 128 reads per k-block)."""
     rng = np.random.default_rng(41)
@@ -346,7 +346,7 @@ def test_small_units_popcount_and_tensor_paths_agree(lg, gpu_ctx):
             assert np.array_equal(a.records, b.records) and np.array_equal(a.counts, b.counts)
             assert np.array_equal(a.site_mean, b.site_mean, equal_nan=True)
     finally:
-        gpu_ctx.set_small_path(True)
+        gpu_ctx.set_small_path(False)
     assert np.array_equal(popc.records, tens.records) and np.array_equal(popc.counts, tens.counts)
     assert np.array_equal(popc.site_mean, tens.site_mean, equal_nan=True)
 
@@ -363,7 +363,7 @@ def test_small_units_many_others_fall_back(lg, gpu_ctx):
         try:
             check_batch(lg, gpu_ctx, [ok, eu, ok], 6)
         finally:
-            gpu_ctx.set_small_path(True)
+            gpu_ctx.set_small_path(False)
 
 
 # --------------------------------------------------------------------------- pipelined step
