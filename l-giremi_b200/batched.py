@@ -87,6 +87,29 @@ def _site_frame_rows(chromosome, strand, sites, mean_of):
     return rows
 
 
+def pair_frame(chromosome, strand, eu, rec):
+    """The `.mi.txt` rows of one unit (mismatch.py:407-418, written at giremi.py:400-404) straight
+    from the record array: no per-row Python.  Same columns, order and dtypes as the reference's
+    DataFrame.from_records over [chromosome, strand, p1, type1, p2, type2, mi] lists."""
+    pos = np.asarray(eu.positions, dtype=np.int64)
+    typ = np.asarray(eu.types, dtype=object)
+    i, j = rec['i'].astype(np.int64), rec['j'].astype(np.int64)
+    n = len(rec)
+    return pd.DataFrame({
+        'chromosome': np.full(n, chromosome, dtype=object), 'strand': np.full(n, strand, dtype=object),
+        'site1_pos': pos[i], 'site1_type': typ[i], 'site2_pos': pos[j], 'site2_type': typ[j],
+        'mi': rec['mi'].astype(np.float64)}, columns=_PAIR_COLUMNS)
+
+
+def write_mi_table(path, frames):
+    """`.mi.txt` exactly as the CLI writes it (giremi.py:400-404): the pair frames of all regions
+    concatenated, tab-separated, no index."""
+    frames = [f for f in frames if len(f)]
+    df = pd.concat(frames, axis=0) if frames else pd.DataFrame.from_records([], columns=_PAIR_COLUMNS)
+    df.to_csv(path, sep='\t', index=False)
+    return len(df)
+
+
 def analyse_extracted(regions, min_common_reads=5, ctx=None):
     """[(df_mismatches, df_mismatch_pair_mi, df_removed_mismatches), ...] for the extracted
     regions, with ONE GPU submit for all of their (footprint, strand) units."""
@@ -97,7 +120,7 @@ def analyse_extracted(regions, min_common_reads=5, ctx=None):
                 units.append(reg.encoded[s])
                 owner.append((r, s))
     res = api.mi_step_batched(pack_units(units), min_common_reads, api.MODE_HET_ONLY, ctx=ctx) if units else None
-    pair_rows = [{'+': [], '-': []} for _ in regions]
+    pair_rows = [{'+': None, '-': None} for _ in regions]
     mean_of = [{'+': {}, '-': {}} for _ in regions]
     site_off = 0
     for u, (r, s) in enumerate(owner):
@@ -107,16 +130,18 @@ def analyse_extracted(regions, min_common_reads=5, ctx=None):
             bad = np.fromiter(eu.bad_sites, dtype=np.int64)
             if np.isin(rec['i'], bad).any() or np.isin(rec['j'], bad).any():
                 raise IndexError('list index out of range')          # mutual_information.py:30/32
-        pos, typ = eu.positions, eu.types
-        chrom = regions[r].chromosome
-        pair_rows[r][s] = [[chrom, s, pos[i], typ[i], pos[j], typ[j], mi]
-                           for i, j, mi in zip(rec['i'].tolist(), rec['j'].tolist(), rec['mi'].tolist())]
+        pos = eu.positions
+        pair_rows[r][s] = pair_frame(regions[r].chromosome, s, eu, rec)
         mean = res.site_mean[site_off:site_off + eu.n_sites]
         mean_of[r][s] = {p: float(m) for p, m in zip(pos, mean.tolist()) if m == m}   # NaN: in no kept pair
         site_off += eu.n_sites
     out = []
     for r, reg in enumerate(regions):
-        df_pairs = pd.DataFrame.from_records(pair_rows[r]['+'] + pair_rows[r]['-'], columns=_PAIR_COLUMNS)
+        parts = [f for f in (pair_rows[r]['+'], pair_rows[r]['-']) if f is not None and len(f)]
+        if not parts:
+            df_pairs = pd.DataFrame.from_records([], columns=_PAIR_COLUMNS)     # what the reference builds from no rows
+        else:
+            df_pairs = parts[0] if len(parts) == 1 else pd.concat(parts, axis=0, ignore_index=True)
         site_rows = []
         for s in _STRANDS:
             site_rows += _site_frame_rows(reg.chromosome, s, reg.mismatches[s], mean_of[r][s])
