@@ -706,11 +706,28 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     k_small_gram<<<grid, kSgThreads, sizeof(SgSmem) + 1024, bstream(b)>>>(G);
     ++ctx->launches;
   }
-  if (b->n_items) {
-    // K0 + scan: every item's place in the ordered output
-    const unsigned cgrid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 8u);
-    k_count<<<cgrid, kThreads, 0, bstream(b)>>>(P);
+  if (b->n_fast) {
+    // K0 of the small units: emitted pairs per unit from the C planes alone
+    CountFastParams C;
+    C.items = b->d_fast_items;
+    C.n_items = b->n_fast;
+    C.planes = b->d_planes;
+    C.site_flags = b->d_flags;
+    C.ij_tab = ctx->d_ij_tab;
+    C.min_common = min_common;
+    C.mode = mode;
+    C.item_cnt = b->d_item_cnt;
+    const unsigned grid = (unsigned)std::min<uint64_t>(b->n_fast, (uint64_t)ctx->num_sms * 8u);
+    k_count_fast<<<grid, kThreads, 0, bstream(b)>>>(C);
     ++ctx->launches;
+  }
+  if (b->n_items) {
+    // K0 of everything else + scan: every item's place in the ordered output
+    if (b->n_items > b->n_fast + b->n_pre) {
+      const unsigned cgrid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 8u);
+      k_count<<<cgrid, kThreads, 0, bstream(b)>>>(P);
+      ++ctx->launches;
+    }
     CU(ctx, cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, b->scan_tmp_bytes, b->d_item_cnt, b->d_item_off,
                                           (int)b->n_items + 1, bstream(b)));
     ++ctx->launches;
@@ -731,6 +748,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     F.mode = mode;
     F.item_off = b->d_item_off;
     F.item_dense = b->d_item_dense;
+    F.n_generic = b->d_n_generic;
     F.records = b->d_records;
     F.counts = b->d_counts;
     F.site_mean = b->d_site_mean;

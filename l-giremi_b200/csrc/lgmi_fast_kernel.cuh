@@ -20,7 +20,8 @@ struct FastParams {
   int min_common;
   uint32_t mode;
   const unsigned long long* item_off;  // exclusive scan of the per-item emit counts
-  const uint8_t* item_dense;           // 1: some site has more than kOthCap "other" reads -> generic kernel
+  uint8_t* item_dense;                 // 1: some site has more than kOthCap "other" reads -> generic kernel
+  uint32_t* n_generic;                 // items the generic kernel has to take (incremented with item_dense)
   lgmi_pair_rec* records;
   uint32_t* counts;                    // EMIT_COUNTS: 9 per record
   double* site_mean;
@@ -403,22 +404,28 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
     const uint32_t S = it.S;
     const uint32_t n_pairs = S * (S - 1u) / 2u;
     const uint32_t n_chunks = (n_pairs + 31u) >> 5;
-    const bool dense = P.item_dense[it.item] != 0u;  // handled by the generic kernel
     const unsigned long long base = P.item_off[it.item];
-    if (!dense) {
-      uint32_t* rows = sm.rows[buf];
-      const uint16_t* __restrict__ ijt = P.ij_tab + lg_ij_tab_off(S);
-      if (tid < (uint32_t)kFastMaxS) sm.n_oth[tid] = 0u;
+    uint32_t* rows = sm.rows[buf];
+    const uint16_t* __restrict__ ijt = P.ij_tab + lg_ij_tab_off(S);
+    if (tid < (uint32_t)kFastMaxS) sm.n_oth[tid] = 0u;
+    if (tid == 0) {
+      sm.n_list2 = 0u;
+      sm.n_list3 = 0u;
+    }
+    cp_async_wait<1>();  // this item's rows have landed (the next item's may still be in flight)
+    __syncthreads();
+    fast_land(sm, rows, it, P.site_flags + it.site_off);
+    __syncthreads();
+    // a site with more than kOthCap "other" reads does not fit the sparse lists: the generic kernel takes the unit
+    const bool over = tid < S && sm.n_oth[tid] > (uint32_t)kOthCap;
+    fast_site_lists(sm, S);
+    const bool dense = __syncthreads_or(over) != 0;  // (also: sm.info is read by every thread of the counts phase)
+    if (dense) {
       if (tid == 0) {
-        sm.n_list2 = 0u;
-        sm.n_list3 = 0u;
+        P.item_dense[it.item] = 1;
+        atomicAdd(P.n_generic, 1u);
       }
-      cp_async_wait<1>();  // this item's rows have landed (the next item's may still be in flight)
-      __syncthreads();
-      fast_land(sm, rows, it, P.site_flags + it.site_off);
-      __syncthreads();
-      fast_site_lists(sm, S);
-      __syncthreads();  // sm.info is read by every thread of the counts phase
+    } else {
       const uint32_t nw = ((uint32_t)it.R + 31u) >> 5;
       if (nw <= 2u) fast_counts<2>(P, sm, rows, ijt, n_pairs);
       else if (nw <= 4u) fast_counts<4>(P, sm, rows, ijt, n_pairs);
@@ -437,8 +444,6 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
       const uint32_t mean_warps = (S + 31u) >> 5;
       if ((tid >> 5) < mean_warps) fast_means(P, sm, sm.val, it);
       else fast_emit(P, sm, sm.val, it, ijt, base, n_chunks, mean_warps);
-    } else {
-      cp_async_wait<1>();
     }
     __syncthreads();  // everything of this item consumed before its buffers are reused
     it = it_next;

@@ -475,21 +475,28 @@ __global__ void __launch_bounds__(kThreads, 3) k_tile_mi(const RunParams P, cons
 // the ordered output, so k_pairs needs no inter-CTA communication.
 constexpr int kCountStride = 12;  // words per staged C row (48 B: conflict-free LDS.128)
 
+// pairs a small unit will emit: |Ci & Cj| >= min_common (and the het filter of the mode) over the
+// unit's C planes only.  Persistent CTAs over the fast items, the next unit's C rows in flight
+// (cp.async) while the current one is counted; (i, j) from the per-S pair table.
+struct CountFastParams {
+  const FastItem* items;
+  uint32_t n_items;
+  const uint32_t* planes;
+  const uint8_t* site_flags;
+  const uint16_t* ij_tab;
+  int min_common;
+  uint32_t mode;
+  unsigned long long* item_cnt;
+};
+
 template <int NW>
-__device__ __forceinline__ uint32_t count_fast_item(const uint32_t* __restrict__ s_c, const uint8_t* __restrict__ s_flags,
-                                                    uint32_t S, int min_common, bool het_only, bool skip_nonhet) {
-  const uint32_t n_pairs = S * (S - 1u) / 2u;
+__device__ __forceinline__ uint32_t count_fast_item(const uint32_t* __restrict__ s_c, unsigned long long het_mask,
+                                                    const uint16_t* __restrict__ ijt, uint32_t n_pairs, int min_common,
+                                                    bool need_het) {
   uint32_t mine = 0;
-  // walk the triangle row by row: thread -> (i, k), advanced by blockDim
-  uint32_t i = 0, k = threadIdx.x;
-  uint32_t len = S - 1u;
   for (uint32_t p = threadIdx.x; p < n_pairs; p += kThreads) {
-    while (k >= len) {
-      k -= len;
-      ++i;
-      --len;
-    }
-    const uint32_t j = i + 1u + k;
+    const uint32_t ij = __ldg(ijt + p);
+    const uint32_t i = ij >> 6, j = ij & 63u;
     uint32_t a[8], b[8];
 #pragma unroll
     for (int q = 0; q < (NW + 3) / 4; ++q) {
@@ -499,61 +506,98 @@ __device__ __forceinline__ uint32_t count_fast_item(const uint32_t* __restrict__
       b[4 * q] = y.x; b[4 * q + 1] = y.y; b[4 * q + 2] = y.z; b[4 * q + 3] = y.w;
     }
     const uint32_t n = and_popc<NW>(a, b);
-    const bool het = ((s_flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
-                     ((s_flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
-    const bool emit = ((int)n >= min_common) && (het || !(het_only || skip_nonhet));
-    mine += emit ? 1u : 0u;
-    k += kThreads;
+    const bool het = (((het_mask >> i) | (het_mask >> j)) & 1ull) != 0ull;
+    mine += ((int)n >= min_common && (het || !need_het)) ? 1u : 0u;
   }
   return mine;
 }
 
+__global__ void __launch_bounds__(kThreads) k_count_fast(const CountFastParams P) {
+  __shared__ __align__(16) uint32_t s_c[2][kFastMaxS * kCountStride];
+  __shared__ uint32_t s_het[2][2];
+  __shared__ uint32_t s_warp[kThreads / 32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const bool need_het = (P.mode & LGMI_MODE_HET_ONLY) != 0u;  // (SKIP_NONHET implies HET_ONLY)
+
+  auto request_rows = [&](uint32_t b, const FastItem& it) {  // C rows of a unit by cp.async
+    const uint32_t W = it.W, W4 = W >> 2;
+    const uint32_t* __restrict__ src = P.planes + it.plane_off + 2u * W;
+    for (uint32_t e = tid; e < (uint32_t)it.S * 2u; e += kThreads) {
+      const uint32_t s = e >> 1, half = e & 1u;
+      const bool have = half < W4;
+      cp_async16(&s_c[b][s * kCountStride + half * 4u], src + (size_t)s * 3u * W + (have ? half * 4u : 0u), have);
+    }
+  };
+  auto load_flag = [&](const FastItem& it) -> uint32_t {  // one site's flag byte per thread of the first two warps
+    return (tid < it.S) ? (uint32_t)P.site_flags[it.site_off + tid] : 0u;
+  };
+  auto store_het = [&](uint32_t b, uint32_t f) {
+    if (warp < 2u) {
+      const uint32_t m = __ballot_sync(0xffffffffu, (f & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+      if (lane == 0) s_het[b][warp] = m;
+    }
+  };
+
+  uint32_t idx = blockIdx.x, buf = 0;
+  FastItem it;
+  if (idx < P.n_items) {
+    it = P.items[idx];
+    request_rows(0, it);
+    store_het(0, load_flag(it) | (tid < it.S ? 0u : 3u));
+  }
+  cp_async_commit();
+  while (idx < P.n_items) {
+    const uint32_t idx_next = idx + gridDim.x;
+    FastItem it_next = it;
+    uint32_t f_next = 3u;  // not a site type: never het
+    if (idx_next < P.n_items) {
+      it_next = P.items[idx_next];
+      request_rows(buf ^ 1u, it_next);
+      if (tid < it_next.S) f_next = load_flag(it_next);  // consumed after this unit's pairs: the latency is hidden
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const uint32_t S = it.S, n_pairs = S * (S - 1u) / 2u;
+    const uint16_t* __restrict__ ijt = P.ij_tab + lg_ij_tab_off(S);
+    const unsigned long long het_mask = (unsigned long long)s_het[buf][0] | ((unsigned long long)s_het[buf][1] << 32);
+    const uint32_t nw = ((uint32_t)it.R + 31u) >> 5;
+    uint32_t mine;
+    if (nw <= 2u) mine = count_fast_item<2>(s_c[buf], het_mask, ijt, n_pairs, P.min_common, need_het);
+    else if (nw <= 4u) mine = count_fast_item<4>(s_c[buf], het_mask, ijt, n_pairs, P.min_common, need_het);
+    else if (nw <= 7u) mine = count_fast_item<7>(s_c[buf], het_mask, ijt, n_pairs, P.min_common, need_het);
+    else mine = count_fast_item<8>(s_c[buf], het_mask, ijt, n_pairs, P.min_common, need_het);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) s_warp[warp] = mine;
+    store_het(buf ^ 1u, f_next);
+    __syncthreads();  // also: this unit's rows are consumed, the buffer may be refilled two iterations on
+    if (tid == 0) {
+      uint32_t tot = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) tot += s_warp[w];
+      P.item_cnt[it.item] = tot;
+    }
+    it = it_next;
+    idx = idx_next;
+    buf ^= 1u;
+  }
+  cp_async_wait<0>();
+}
+
 __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
-  __shared__ __align__(16) uint32_t s_c[kFastMaxS * kCountStride];
-  __shared__ uint8_t s_flags[kFastMaxS];
-  __shared__ uint32_t s_noth[kFastMaxS];
   __shared__ uint32_t s_warp[kThreads / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const bool het_only = (P.mode & LGMI_MODE_HET_ONLY) != 0u;
   const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
   for (uint32_t item_idx = blockIdx.x; item_idx < P.n_items; item_idx += gridDim.x) {
     const Item it = P.items[item_idx];
-    if (it.flags & ITEM_PRE) continue;  // k_small_gram has written this item's count
+    if (it.flags & (ITEM_PRE | ITEM_FAST)) continue;  // counted by k_small_gram / k_count_fast
     const DevUnit u = P.units[it.unit];
     const uint8_t* __restrict__ flags = P.site_flags + u.site_off;
     uint32_t mine = 0;
     __syncthreads();
-    if (it.flags & ITEM_FAST) {
-      const uint32_t W = u.W;
-      const uint32_t* __restrict__ planes = P.planes + u.plane_off;
-      if (tid < (uint32_t)kFastMaxS) s_noth[tid] = 0u;
-      __syncthreads();
-      for (uint32_t e = tid; e < u.S * 8u; e += kThreads) {
-        const uint32_t s = e >> 3, k = e & 7u;
-        uint32_t C = 0u;
-        if (k < W) {
-          const uint32_t* row = planes + (size_t)s * 3u * W;
-          C = __ldg(row + 2u * W + k);
-          const uint32_t n_other = __popc(C & ~(__ldg(row + k) | __ldg(row + W + k)));
-          if (n_other) atomicAdd(&s_noth[s], n_other);
-        }
-        s_c[s * kCountStride + k] = C;
-      }
-      if (tid < u.S) s_flags[tid] = flags[tid];
-      __syncthreads();
-      {
-        const bool over = tid < u.S && s_noth[tid] > (uint32_t)kOthCap;
-        if (__syncthreads_or(over) && tid == 0) {
-          P.item_dense[item_idx] = 1;
-          atomicAdd(P.n_generic, 1u);
-        }
-      }
-      const uint32_t nw = (u.R + 31u) >> 5;
-      if (nw <= 2u) mine = count_fast_item<2>(s_c, s_flags, u.S, P.min_common, het_only, skip_nonhet);
-      else if (nw <= 4u) mine = count_fast_item<4>(s_c, s_flags, u.S, P.min_common, het_only, skip_nonhet);
-      else if (nw <= 7u) mine = count_fast_item<7>(s_c, s_flags, u.S, P.min_common, het_only, skip_nonhet);
-      else mine = count_fast_item<8>(s_c, s_flags, u.S, P.min_common, het_only, skip_nonhet);
-    } else {
+    {
       const uint32_t W4 = u.W >> 2;
       const uint4* __restrict__ base = reinterpret_cast<const uint4*>(P.planes + u.plane_off);
       for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
