@@ -273,6 +273,32 @@ def dense_leg(lg, synth, ctx, torch, stream, steps, warmup, flush):
     return out
 
 
+def bind_near_gpu(torch, local):
+    """Pin this rank's threads to the CPUs of the NUMA node its GPU hangs off, so that the pinned
+    staging buffers (first touched below) and the copy threads sit next to the PCIe root.  Returns
+    the previous affinity (restored before the CPU baseline) and a note for the JSON line."""
+    try:
+        prev = os.sched_getaffinity(0)
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return prev, "numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= prev
+        if not cpus:
+            return prev, "numa node %d has none of this process's cpus" % node
+        os.sched_setaffinity(0, cpus)
+        return prev, "bound to numa node %d (%d cpus)" % (node, len(cpus))
+    except (OSError, ValueError, AttributeError) as exc:
+        return None, "not bound (%s)" % type(exc).__name__
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import numpy as np
@@ -287,6 +313,7 @@ def run_gpu(args):
     if world != args.gpus:
         raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world))
     torch.cuda.set_device(local)
+    prev_affinity, numa_note = bind_near_gpu(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -427,6 +454,8 @@ def run_gpu(args):
         except (OSError, ValueError):
             traffic = None
 
+    if prev_affinity:
+        os.sched_setaffinity(0, prev_affinity)               # the CPU baseline gets every host core again
     cpu = None if args.no_cpu_baseline else cpu_baseline()
     dense = None
     if world == 1 and not args.no_dense:
@@ -447,7 +476,8 @@ def run_gpu(args):
                 "mode": "HET_ONLY: all candidates evaluated, het-kept rows (%d) + per-site mean MI returned"
                         % e2e_records, "ms_per_step": 1e3 * float(t.item()) / e2e_steps if e2e_steps else None,
                 "api": "lgmi_pipeline_step, %d groups of units on their own streams" % args.e2e_chunks,
-                "serial_upload_run_download_ms": serial_ms, "gpu_launches": launches_e2e * world},
+                "serial_upload_run_download_ms": serial_ms, "gpu_launches": launches_e2e * world,
+                "host_affinity": numa_note},
         "gpu_launches": launches * world,
         "clocks": clocks,
     }

@@ -239,6 +239,40 @@ LGMI_API int lgmi_ecdf(lgmi_t* ctx, const double* mean, const uint8_t* site_flag
 LGMI_API int lgmi_ecdf_eval(lgmi_t* ctx, const double* x, uint64_t n, const double* samples,
                    uint64_t n_samples, double* out);
 
+/* ----- host-side native pieces either side of the step (no device needed) --- *
+ * One read's short-form cs tag (minimap2 --cs): its substitutions in contig    *
+ * coordinates (0-based) with the splice-distance filter applied, and its       *
+ * introns.  Replaces, per read, CS.from_cs_tag_string + get_mismatches +       *
+ * get_introns (giremi/cs.py:8-41, :573-613) and FILTER 1 of                    *
+ * giremi/mismatch.py:99-141 (merged +-min_dist intervals around every intron   *
+ * start and end, membership start <= pos < end as in utils.py:4-31).           *
+ * mm_ref / mm_alt are upper-case bases.  Returns LGMI_ERR_ARG for a mark the   *
+ * reference does not know, LGMI_ERR_NOMEM (counts still set) when a capacity   *
+ * is too small.                                                                */
+LGMI_API int lgmi_cs_scan(const char* cs, uint64_t cs_len, int64_t ref_start, int min_dist_from_splice,
+                 uint32_t cap_mismatch, int64_t* mm_pos, char* mm_ref, char* mm_alt,
+                 uint32_t* n_mismatch, uint32_t cap_intron, int64_t* intron_lo, int64_t* intron_hi,
+                 uint32_t* n_intron);
+/* One unit from its flattened `mismatches[strand]` dict to bit-planes + flag   *
+ * bytes (the layout above), with the dict semantics the kernels cannot see:    *
+ * a read listed twice at a site keeps its last allele                          *
+ * (mutual_information.py:15-16), major / minor by `depth` descending with the  *
+ * stable tie-break (:25-32), every other allele -> "other" (:33-38).           *
+ * Sites in ascending position order.  Per site s: n_depth_entries[s] pairs     *
+ * (depth_allele, depth_value) in the depth dict's order, n_nt_entries[s] pairs *
+ * (nt_allele, nt_n_names) in the nt dict's order; allele ids are any integers  *
+ * consistent within a site; the read names of all lists, in order, are one     *
+ * newline-separated blob.  Outputs: planes (3 * n_sites * W words, W returned  *
+ * in row_words_out), site_flags, bad_site (1: fewer than two alleles in        *
+ * `depth`), the number of distinct reads.  LGMI_ERR_NOMEM if plane_cap_words   *
+ * is too small (n_reads_out / row_words_out are set: call again).              */
+LGMI_API int lgmi_encode_unit(uint32_t n_sites, const uint8_t* site_type, const uint32_t* n_depth_entries,
+                     const uint32_t* depth_allele, const int64_t* depth_value,
+                     const uint32_t* n_nt_entries, const uint32_t* nt_allele,
+                     const uint32_t* nt_n_names, const char* names_blob, uint64_t blob_len,
+                     uint64_t plane_cap_words, uint32_t* planes, uint8_t* site_flags,
+                     uint8_t* bad_site, uint32_t* n_reads_out, uint32_t* row_words_out);
+
 /* ----- multi-GPU partitioning (no collective) ------------------- *
  * cost(unit) = S(S-1)/2 * ceil(R/64).  Longest-processing-time greedy into    *
  * n_bins; bin_of[u] receives the bin.  Deterministic (ties: lower index).     */

@@ -16,7 +16,8 @@ from ._lib import (DENSE_DEFAULT, LIB_PATH, MODE_ALL_PAIRS, MODE_EMIT_COUNTS, MO
 from .api import (Batch, Context, Pipeline, StepResult, ecdf, get_context, mean_mismatch_pair_mutual_info,
                   mi_step_batched, mip_and_calls, mismatch_pair_mutual_info, partition_lpt, site_splice_mutual_info,
                   unit_costs)
-from .encode import EncodedUnit, PlaneBatch, encode_batch, encode_mismatches, pack_units
+from .encode import (EncodedUnit, PlaneBatch, concat_plane_batches, cs_read_mismatches, encode_batch, encode_mismatches,
+                     encode_mismatches_native, pack_units)
 from .batched import analyse_extracted, extract_region, footprint_bulk_calculation, region_mismatch_analysis
 from .patch import install, uninstall
 

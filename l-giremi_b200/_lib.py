@@ -41,7 +41,7 @@ EXPORTS = (
     "lgmi_batch_download", "lgmi_batch_sync", "lgmi_batch_device_ptrs",
     "lgmi_batch_algorithmic_bytes", "lgmi_pipeline_create", "lgmi_pipeline_step", "lgmi_pipeline_destroy",
     "lgmi_submit", "lgmi_wait", "lgmi_site_mean_csr",
-    "lgmi_ecdf", "lgmi_ecdf_eval", "lgmi_unit_cost", "lgmi_partition_lpt",
+    "lgmi_ecdf", "lgmi_ecdf_eval", "lgmi_cs_scan", "lgmi_encode_unit", "lgmi_unit_cost", "lgmi_partition_lpt",
 )
 
 
@@ -115,6 +115,10 @@ def load():
         "lgmi_site_mean_csr": (i32, [vp, vp, vp, u64, vp]),
         "lgmi_ecdf": (i32, [vp, vp, vp, u64, C.c_double, vp, vp]),
         "lgmi_ecdf_eval": (i32, [vp, vp, u64, vp, u64, vp]),
+        "lgmi_cs_scan": (i32, [C.c_char_p, u64, C.c_int64, i32, u32, vp, vp, vp, C.POINTER(u32), u32, vp, vp,
+                               C.POINTER(u32)]),
+        "lgmi_encode_unit": (i32, [u32, vp, vp, vp, vp, vp, vp, vp, C.c_char_p, u64, u64, vp, vp, vp,
+                                   C.POINTER(u32), C.POINTER(u32)]),
         "lgmi_unit_cost": (u64, [u32, u32]),
         "lgmi_partition_lpt": (i32, [vp, u32, u32, vp, vp]),
     }

@@ -25,7 +25,7 @@ import numpy as np
 import pandas as pd
 
 from . import api
-from .encode import encode_mismatches, pack_units
+from .encode import concat_plane_batches, encode_mismatches_native
 
 _PAIR_COLUMNS = ['chromosome', 'strand', 'site1_pos', 'site1_type', 'site2_pos', 'site2_type', 'mi']
 _SITE_COLUMNS = ['type', 'chromosome', 'strand', 'pos', 'ref', 'change_type', 'ratio', 'allelic_ratio_diff',
@@ -45,7 +45,9 @@ class RegionExtract:
         self.mismatches = mismatches            # {'+': {pos: site}, '-': {...}}  (reference objects, untouched)
         self.removed = removed
         # a strand enters the MI step only with at least two sites (mismatch.py:388)
-        self.encoded = {s: (encode_mismatches(mismatches[s]) if len(mismatches[s]) > 1 else None) for s in _STRANDS}
+        # (native encoder, csrc/lgmi_host.inl: one PlaneBatch of one unit per strand)
+        self.encoded = {s: (encode_mismatches_native(mismatches[s]) if len(mismatches[s]) > 1 else None)
+                        for s in _STRANDS}
 
 
 def extract_region(chromosome, start_pos, end_pos, sam, genome, **filters) -> RegionExtract:
@@ -87,6 +89,16 @@ def _site_frame_rows(chromosome, strand, sites, mean_of):
     return rows
 
 
+class _UnitMeta:
+    """positions / types / bad sites of a one-unit PlaneBatch."""
+
+    __slots__ = ("positions", "types", "bad_sites", "n_sites")
+
+    def __init__(self, pb):
+        self.positions, self.types, self.bad_sites = pb.positions[0], pb.types[0], pb.bad_sites[0]
+        self.n_sites = len(self.positions)
+
+
 def pair_frame(chromosome, strand, eu, rec):
     """The `.mi.txt` rows of one unit (mismatch.py:407-418, written at giremi.py:400-404) straight
     from the record array: no per-row Python.  Same columns, order and dtypes as the reference's
@@ -119,12 +131,12 @@ def analyse_extracted(regions, min_common_reads=5, ctx=None):
             if reg.encoded[s] is not None:
                 units.append(reg.encoded[s])
                 owner.append((r, s))
-    res = api.mi_step_batched(pack_units(units), min_common_reads, api.MODE_HET_ONLY, ctx=ctx) if units else None
+    res = api.mi_step_batched(concat_plane_batches(units), min_common_reads, api.MODE_HET_ONLY, ctx=ctx) if units else None
     pair_rows = [{'+': None, '-': None} for _ in regions]
     mean_of = [{'+': {}, '-': {}} for _ in regions]
     site_off = 0
     for u, (r, s) in enumerate(owner):
-        eu = units[u]
+        eu = _UnitMeta(units[u])
         rec = res.unit_records(u)
         if eu.bad_sites and len(rec):
             bad = np.fromiter(eu.bad_sites, dtype=np.int64)

@@ -1268,3 +1268,5 @@ extern "C" int lgmi_partition_lpt(const uint64_t* cost, uint32_t n_units, uint32
   if (bin_load) memcpy(bin_load, load.data(), n_bins * sizeof(uint64_t));
   return LGMI_OK;
 }
+
+#include "lgmi_host.inl"

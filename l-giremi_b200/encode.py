@@ -174,3 +174,104 @@ def pack_units(encoded_units) -> PlaneBatch:
 
 def encode_batch(list_of_mismatches) -> PlaneBatch:
     return pack_units([encode_mismatches(m) for m in list_of_mismatches])
+
+
+# --------------------------------------------------------------------------- #
+# native host pieces (csrc/lgmi_host.inl): no device needed
+# --------------------------------------------------------------------------- #
+def cs_read_mismatches(cs_tag, reference_start, min_dist_from_splice=4):
+    """One read's cs tag -> (mismatches, introns): ``[[pos, 'AG'], ...]`` after the
+    splice-distance filter of mismatch.py:99-141 (``'AG'`` = reference base, read base, upper
+    case, as stored at :143-147) and ``[[start, end], ...]`` of its introns in contig
+    coordinates (cs.py:603-607).  Raises ValueError for a mark the reference's parser does
+    not know (it raises KeyError there)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    raw = cs_tag.encode() if isinstance(cs_tag, str) else bytes(cs_tag)
+    cap = max(1, raw.count(b"*"))
+    cap_i = max(1, raw.count(b"~"))
+    pos = np.empty(cap, np.int64)
+    ref = np.empty(cap, "S1")
+    alt = np.empty(cap, "S1")
+    lo = np.empty(cap_i, np.int64)
+    hi = np.empty(cap_i, np.int64)
+    n, ni = C.c_uint32(), C.c_uint32()
+    rc = lib.lgmi_cs_scan(raw, len(raw), int(reference_start), int(min_dist_from_splice), cap, _lib.ptr(pos),
+                          _lib.ptr(ref), _lib.ptr(alt), C.byref(n), cap_i, _lib.ptr(lo), _lib.ptr(hi), C.byref(ni))
+    if rc != 0:
+        raise ValueError("cs tag not understood (liblgmi error %d): %r" % (rc, cs_tag[:60]))
+    mm = [[int(p), (r + a).decode()] for p, r, a in zip(pos[:n.value].tolist(), ref[:n.value].tolist(),
+                                                         alt[:n.value].tolist())]
+    return mm, [[int(a), int(b)] for a, b in zip(lo[:ni.value].tolist(), hi[:ni.value].tolist())]
+
+
+def encode_mismatches_native(mismatches):
+    """dict -> (PlaneBatch of one unit, positions, types, bad_sites) through lgmi_encode_unit:
+    the same planes and flags as pack_units([encode_mismatches(m)]), without the label matrix."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    positions = sorted(mismatches)
+    S = len(positions)
+    site_type = np.empty(S, np.uint8)
+    n_depth = np.empty(S, np.uint32)
+    n_nt = np.empty(S, np.uint32)
+    d_allele, d_value, nt_allele, nt_count, names, types = [], [], [], [], [], []
+    for s, pos in enumerate(positions):
+        site = mismatches[pos]
+        types.append(site['type'])
+        site_type[s] = SITE_TYPE_CODE[site['type']]
+        ids = {}
+        n_depth[s] = len(site['depth'])
+        for allele, depth in site['depth'].items():
+            d_allele.append(ids.setdefault(allele, len(ids)))
+            d_value.append(int(depth))
+        n_nt[s] = len(site['nt'])
+        for allele, lst in site['nt'].items():
+            nt_allele.append(ids.setdefault(allele, len(ids)))
+            nt_count.append(len(lst))
+            names.extend(lst)
+    blob = "\n".join(names).encode()
+    d_allele = np.asarray(d_allele, np.uint32)
+    d_value = np.asarray(d_value, np.int64)
+    nt_allele = np.asarray(nt_allele, np.uint32)
+    nt_count = np.asarray(nt_count, np.uint32)
+    cap = 3 * S * row_words(len(names))
+    planes = np.empty(max(1, cap), np.uint32)
+    flags = np.empty(max(1, S), np.uint8)
+    bad = np.empty(max(1, S), np.uint8)
+    R, W = C.c_uint32(), C.c_uint32()
+    rc = lib.lgmi_encode_unit(S, _lib.ptr(site_type), _lib.ptr(n_depth), _lib.ptr(d_allele), _lib.ptr(d_value),
+                              _lib.ptr(n_nt), _lib.ptr(nt_allele), _lib.ptr(nt_count), blob, len(blob), cap,
+                              _lib.ptr(planes), _lib.ptr(flags), _lib.ptr(bad), C.byref(R), C.byref(W))
+    if rc != 0:
+        raise RuntimeError("lgmi_encode_unit failed (%d)" % rc)
+    units = np.zeros(1, dtype=UNIT_DESC)
+    units[0] = (0, S, R.value, W.value, 0)
+    pb = PlaneBatch(units, planes[:3 * S * W.value].copy(), flags[:S].copy(), [positions], [types],
+                    [frozenset(np.flatnonzero(bad[:S]).tolist())])
+    return pb
+
+
+def concat_plane_batches(batches) -> PlaneBatch:
+    """Several PlaneBatches -> one, units back to back in the given order (what the pipelined
+    step wants)."""
+    units, planes, flags, pos, typ, bad = [], [], [], [], [], []
+    plane_off = site_off = 0
+    for pb in batches:
+        u = pb.units.copy()
+        u['plane_off'] += plane_off - (int(pb.units['plane_off'][0]) if len(pb.units) else 0)
+        u['site_off'] += site_off - (int(pb.units['site_off'][0]) if len(pb.units) else 0)
+        units.append(u)
+        planes.append(pb.planes)
+        flags.append(pb.site_flags)
+        plane_off += pb.planes.size
+        site_off += pb.site_flags.size
+        n = len(pb.units)
+        pos += pb.positions if pb.positions is not None else [None] * n
+        typ += pb.types if pb.types is not None else [None] * n
+        bad += pb.bad_sites if pb.bad_sites is not None else [frozenset()] * n
+    return PlaneBatch(np.concatenate(units) if units else np.zeros(0, UNIT_DESC),
+                      np.concatenate(planes) if planes else np.zeros(0, np.uint32),
+                      np.concatenate(flags) if flags else np.zeros(0, np.uint8), pos, typ, bad)
