@@ -70,8 +70,10 @@ struct FastSmem {
                                                          //       pairs with "other" cells from the back
   uint32_t emit_mask[kFastChunks];                       // ballot of each 32-pair chunk
   uint32_t chunk_off[kFastChunks];
-  uint16_t oth_list[kFastMaxS * 8];                      // 1 KB
+  uint32_t ocell[kFastMaxPairs / 2];                     // 4 KB: per pair, 15 bits: the five 3-bit "other" cells
+  uint16_t oth_flat[kFastMaxS * kOthCap];                // every (site << 8 | read) with label "other", any order
   uint32_t n_oth[kFastMaxS];
+  uint32_t n_oth_total;
   uint8_t flags[kFastMaxS];
   uint8_t info[kFastMaxS];                               // bit 0 het_snp, bits 1-4 number of "other" reads
   uint8_t het_list[kFastMaxS];                           // het sites ascending, then ...

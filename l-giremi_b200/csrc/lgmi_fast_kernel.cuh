@@ -73,7 +73,7 @@ __device__ __forceinline__ void fast_land(FastSmem& sm, uint32_t* __restrict__ r
       const uint32_t b = __ffs((int)O) - 1u;
       O &= O - 1u;
       const uint32_t idx = atomicAdd(&sm.n_oth[s], 1u);
-      if (idx < (uint32_t)kOthCap) sm.oth_list[s * 8u + idx] = (uint16_t)(k * 32u + b);
+      if (idx < (uint32_t)kOthCap) sm.oth_flat[atomicAdd(&sm.n_oth_total, 1u)] = (uint16_t)((s << 8) | (k * 32u + b));
     }
   }
   // het mask (sites ascending) by the first two warps
@@ -103,31 +103,34 @@ __device__ __forceinline__ void fast_site_lists(SM& sm, uint32_t S) {
   }
 }
 
-// the table cells that involve an "other" label of pair (i, j), from the sparse per-site
-// lists: five 3-bit cells T[0][0], T[0][1], T[0][2], T[1][0], T[2][0]
-__device__ __forceinline__ uint32_t other_cells(const FastSmem& sm, const uint32_t* __restrict__ rows, uint32_t i,
-                                                uint32_t j, uint32_t ni, uint32_t nj, uint32_t& n_cells) {
-  uint32_t o = 0u, n = 0u;
-  const uint32_t* ri = rows + i * kRowStride;
-  const uint32_t* rj = rows + j * kRowStride;
-  for (uint32_t q = 0; q < ni; ++q) {  // "other" at i: row 0 of the table
-    const uint32_t r = sm.oth_list[i * 8u + q];
-    const uint32_t w = r >> 5, bit = r & 31u;
-    const uint32_t covered = (rj[16u + w] >> bit) & 1u;
-    n += covered;
-    if ((rj[8u + w] >> bit) & 1u) o += 8u << (3u * ((rj[w] >> bit) & 1u));  // j minor -> cell 1, major -> cell 2
-    else o += covered;                                                      // "other" at both
-  }
-  for (uint32_t q = 0; q < nj; ++q) {  // "other" at j, not at i: column 0
-    const uint32_t r = sm.oth_list[j * 8u + q];
-    const uint32_t w = r >> 5, bit = r & 31u;
-    if ((ri[8u + w] >> bit) & 1u) {
-      o += 512u << (3u * ((ri[w] >> bit) & 1u));  // i minor -> cell 3, major -> cell 4
-      ++n;
+// The table cells that involve an "other" label, scattered from the reads that carry one:
+// for every listed (site s, read r) and every partner site t that covers r, one 3-bit cell of
+// the pair gets +1 -- T[0][0], T[0][1], T[0][2] when s is the pair's first site (by t's label
+// at r), T[1][0], T[2][0] when it is the second (a read "other" at both sites is counted from
+// the first site only).  One warp per entry, lanes over the partners.
+__device__ __forceinline__ void fast_other_cells(FastSmem& sm, const uint32_t* __restrict__ rows, uint32_t S) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t E = sm.n_oth_total;
+  for (uint32_t e = warp; e < E; e += kFastWarps) {
+    const uint32_t v = sm.oth_flat[e];
+    const uint32_t s = v >> 8, w = (v & 255u) >> 5, bit = v & 31u;
+    for (uint32_t t = lane; t < S; t += 32u) {
+      if (t == s) continue;
+      const uint32_t* rt = rows + t * kRowStride;
+      if (!((rt[16u + w] >> bit) & 1u)) continue;  // t does not cover the read
+      const uint32_t Pt = (rt[8u + w] >> bit) & 1u, Mt = (rt[w] >> bit) & 1u;
+      uint32_t cell, p;
+      if (s < t) {
+        cell = Pt ? 1u + Mt : 0u;
+        p = ((s * (2u * S - s - 1u)) >> 1) + (t - s - 1u);
+      } else {
+        if (!Pt) continue;
+        cell = 3u + Mt;
+        p = ((t * (2u * S - t - 1u)) >> 1) + (s - t - 1u);
+      }
+      atomicAdd(&sm.ocell[p >> 1], 1u << (3u * cell + 16u * (p & 1u)));
     }
   }
-  n_cells = n;
-  return o;
 }
 
 // the four AND+popcount sets of every pair, "other" cells, min-common filter, emit masks, lists
@@ -151,12 +154,8 @@ __device__ __forceinline__ void fast_counts(const FastParams& P, FastSmem& sm, c
       if (het || !skip_nonhet) {
         const unsigned long long cnt = pair_counts<NW>(rows + i * kRowStride, rows + j * kRowStride);
         uint32_t n_common = (uint32_t)cnt & 511u;
-        uint32_t o = 0u;
-        if ((fi | fj) >> 1) {
-          uint32_t n_o = 0u;
-          o = other_cells(sm, rows, i, j, fi >> 1, fj >> 1, n_o);
-          n_common += n_o;
-        }
+        const uint32_t o = (sm.ocell[p >> 1] >> (16u * (p & 1u))) & 0x7fffu;
+        if (o) n_common += (o & 7u) + ((o >> 3) & 7u) + ((o >> 6) & 7u) + ((o >> 9) & 7u) + (o >> 12);
         if ((int)n_common >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
           v = cnt | ((unsigned long long)o << 36);
           cls = o ? 3u : 2u;
@@ -408,9 +407,11 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
     uint32_t* rows = sm.rows[buf];
     const uint16_t* __restrict__ ijt = P.ij_tab + lg_ij_tab_off(S);
     if (tid < (uint32_t)kFastMaxS) sm.n_oth[tid] = 0u;
+    for (uint32_t q = tid; q < (n_pairs + 1u) >> 1; q += kFastThreads) sm.ocell[q] = 0u;
     if (tid == 0) {
       sm.n_list2 = 0u;
       sm.n_list3 = 0u;
+      sm.n_oth_total = 0u;
     }
     cp_async_wait<1>();  // this item's rows have landed (the next item's may still be in flight)
     __syncthreads();
@@ -419,6 +420,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
     // a site with more than kOthCap "other" reads does not fit the sparse lists: the generic kernel takes the unit
     const bool over = tid < S && sm.n_oth[tid] > (uint32_t)kOthCap;
     fast_site_lists(sm, S);
+    fast_other_cells(sm, rows, S);
     const bool dense = __syncthreads_or(over) != 0;  // (also: sm.info is read by every thread of the counts phase)
     if (dense) {
       if (tid == 0) {
