@@ -4,6 +4,7 @@
 TAG=${1:-r1}
 O=gpurun_out
 mkdir -p $O
+timeout 300 python __graft_entry__.py --smoke > $O/smoke_$TAG.log 2>&1; tail -1 $O/smoke_$TAG.log
 timeout 1200 python -m pytest tests -x -q -m gpu > $O/pytest_gpu_$TAG.log 2>&1; tail -3 $O/pytest_gpu_$TAG.log
 timeout 600 python bench.py --steps 10 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; cut -c1-300 $O/bench_$TAG.json
 timeout 400 python bench.py --impl reference --steps 1 --warmup 0 > $O/bench_ref_$TAG.json 2> $O/bench_ref_$TAG.err; cut -c1-200 $O/bench_ref_$TAG.json
