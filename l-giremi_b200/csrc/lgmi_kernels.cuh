@@ -184,9 +184,10 @@ __global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
     __syncthreads();  // previous item fully consumed
 
     // ---- counts + MI for every candidate pair of the item
+    uint32_t i = 0, j = 0;
+    if (tid < it.pair_cnt) lg_pair_ij(it.pair_begin + tid, u.S, i, j);  // one square root per thread, then steps
     for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
-      uint32_t i, j;
-      lg_pair_ij(it.pair_begin + pl, u.S, i, j);
+      if (pl != tid) lg_pair_advance(i, j, u.S, kThreads);
       s_ij[pl] = (i << 16) | j;
       double mi = lg_nan();
       bool evaluate = true;
@@ -600,12 +601,16 @@ __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
     {
       const uint32_t W4 = u.W >> 2;
       const uint4* __restrict__ base = reinterpret_cast<const uint4*>(P.planes + u.plane_off);
+      const bool need_ij = het_only || skip_nonhet || !u.tiled;
+      uint32_t i = 0, j = 0;
+      if (need_ij && tid < it.pair_cnt) lg_pair_ij(it.pair_begin + tid, u.S, i, j);
       for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
-        uint32_t i, j;
-        lg_pair_ij(it.pair_begin + pl, u.S, i, j);
-        const bool het = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
-                         ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
-        if (!het && (het_only || skip_nonhet)) continue;
+        if (need_ij && pl != tid) lg_pair_advance(i, j, u.S, kThreads);
+        if (het_only || skip_nonhet) {
+          const bool het = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
+                           ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+          if (!het) continue;
+        }
         if (u.tiled) {  // survivors are the pairs k_tile_mi gave an MI
           mine += isnan(P.dense[u.dense_off + it.pair_begin + pl]) ? 0u : 1u;
           continue;

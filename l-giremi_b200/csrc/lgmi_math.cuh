@@ -173,6 +173,14 @@ LG_HD double lg_neumaier_mean(const lg_neumaier& a) {
 LG_HD uint64_t lg_row_off(uint32_t i, uint32_t S) {
   return ((uint64_t)i * (2ull * S - i - 1ull)) >> 1;
 }
+// (i, j) of pair p + step from the (i, j) of pair p, without the square root
+LG_HD void lg_pair_advance(uint32_t& i, uint32_t& j, uint32_t S, uint32_t step) {
+  j += step;
+  while (j >= S) {  // past the end of row i by j - S pairs: row i + 1 starts at column i + 2
+    ++i;
+    j = j - S + i + 1u;
+  }
+}
 LG_HD void lg_pair_ij(uint32_t p, uint32_t S, uint32_t& i, uint32_t& j) {
   const double b = 2.0 * (double)S - 1.0;
   double disc = b * b - 8.0 * (double)p;

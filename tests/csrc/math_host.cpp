@@ -30,6 +30,7 @@ double t_neumaier_mean(const double* v, int64_t n) {
   return lg_neumaier_mean(acc);
 }
 void t_pair_ij(uint32_t p, uint32_t S, uint32_t* i, uint32_t* j) { lg_pair_ij(p, S, *i, *j); }
+void t_pair_advance(uint32_t* i, uint32_t* j, uint32_t S, uint32_t step) { lg_pair_advance(*i, *j, S, step); }
 uint64_t t_row_off(uint32_t i, uint32_t S) { return lg_row_off(i, S); }
 double t_ecdf_y(uint64_t idx, uint64_t n) { return lg_ecdf_y(idx, n); }
 void t_build_lntab(double* out, uint64_t k0, uint64_t k1) { lgmi_build_lntab(out, k0, k1); }

@@ -131,6 +131,19 @@ def test_pair_index_roundtrip(math_host):
         math_host.t_pair_ij(p, S, ctypes.byref(i), ctypes.byref(j))
         got.append((i.value, j.value))
     assert got == want
+    # stepping through the triangle without the square root (k_pairs_generic / k_count: stride 256)
+    for S in (2, 3, 24, 65, 700):
+        pairs = [(a, b) for a in range(S) for b in range(a + 1, S)]
+        for start in (0, 1, 7, len(pairs) // 2):
+            for step in (1, 32, 256):
+                if start >= len(pairs):
+                    continue
+                i.value, j.value = pairs[start]
+                p = start
+                while p + step < len(pairs):
+                    math_host.t_pair_advance(ctypes.byref(i), ctypes.byref(j), S, step)
+                    p += step
+                    assert (i.value, j.value) == pairs[p]
 
 
 def test_ecdf_y_is_numpy_linspace(math_host):
