@@ -106,6 +106,7 @@ struct lgmi_batch {
   // tiled popcount path
   TileItem* d_tile_items = nullptr;
   uint32_t n_tile_items = 0;
+  uint32_t n_tiled_work_items = 0;     // work items (Item) of the k_tile_mi units: k_pairs_generic<true>'s
   uint32_t* d_tile_counts = nullptr;  // EMIT_COUNTS only, allocated on first use
   uint64_t n_tiled_slots = 0;
   // host (pinned) mirrors
@@ -456,7 +457,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       it.unit = k;
       it.pair_begin = t * (uint32_t)kPairsMax;
       it.pair_cnt = (uint32_t)std::min<uint64_t>(kPairsMax, np - (uint64_t)t * kPairsMax);
-      it.flags = (t == 0 ? ITEM_FIRST : 0u) | (nit == 1 ? ITEM_SINGLE : 0u);
+      it.flags = (t == 0 ? ITEM_FIRST : 0u) | (nit == 1 ? ITEM_SINGLE : 0u) | (d.tiled ? ITEM_TILED : 0u);
+      if (d.tiled) ++b->n_tiled_work_items;
       if (nit == 1 && np >= 1 && u.n_sites <= (uint32_t)kFastMaxS && u.n_reads <= (uint32_t)kFastMaxR) {
         it.flags |= ITEM_FAST;
         FastItem f;
@@ -656,7 +658,8 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     const uint64_t n = std::max<uint64_t>(std::max<uint64_t>(b->n_sites, b->n_items), (uint64_t)b->n_units + 1);
     k_run_init<<<(unsigned)((n + 255) / 256), 256, 0, bstream(b)>>>(b->d_header, b->d_unit_rec_off, b->n_units + 1,
                                                                   b->d_item_dense, b->n_items, b->d_n_generic,
-                                                                  b->n_items - b->n_fast - b->n_pre, b->d_site_mean, b->d_site_cnt,
+                                                                  b->n_items - b->n_fast - b->n_pre - b->n_tiled_work_items, b->d_site_mean,
+                                                                  b->d_site_cnt,
                                                                   b->n_sites);
     ++ctx->launches;
   }
@@ -775,8 +778,13 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   if (timing) CU(ctx, cudaEventRecord(b->ev[3], bstream(b)));
   if (b->n_items) {
     // everything the small-unit kernel does not take; exits at once when there is nothing
+    if (b->n_tile_items) {  // ordering + emission of what k_tile_mi computed
+      const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
+      k_pairs_generic<true><<<grid, kThreads, 0, bstream(b)>>>(P);
+      ++ctx->launches;
+    }
     const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
-    k_pairs_generic<<<grid, kThreads, 0, bstream(b)>>>(P);
+    k_pairs_generic<false><<<grid, kThreads, 0, bstream(b)>>>(P);
     ++ctx->launches;
   }
   if (b->n_mean_items) {

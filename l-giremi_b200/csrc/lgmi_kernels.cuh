@@ -38,7 +38,10 @@ struct DevUnit {
 };
 constexpr uint64_t kNoGram = ~0ull;
 
-enum : uint32_t { ITEM_FIRST = 1u, ITEM_SINGLE = 2u, ITEM_FAST = 4u, ITEM_PRE = 8u /* counted by k_small_gram */ };
+enum : uint32_t {
+  ITEM_FIRST = 1u, ITEM_SINGLE = 2u, ITEM_FAST = 4u, ITEM_PRE = 8u /* counted by k_small_gram */,
+  ITEM_TILED = 16u /* MI precomputed by k_tile_mi */
+};
 
 struct Item {
   uint32_t unit;
@@ -164,7 +167,10 @@ __device__ __forceinline__ uint32_t gram_table(const uint32_t* __restrict__ g, u
 // sites or 256 reads, pair-less units, and small units with dense third alleles.
 // The output offset of every item is known before the kernel starts (k_count +
 // exclusive scan), so no CTA ever waits on another.
-__global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
+// kTiled: only the items whose MI k_tile_mi has already computed (pure ordering and emission: few
+// registers, four CTAs per SM to hide the loads); !kTiled: everything else.
+template <bool kTiled>
+__global__ void __launch_bounds__(kThreads, kTiled ? 4 : 2) k_pairs_generic(const RunParams P) {
   __shared__ double s_mi[kPairsMax];    // MI of each pair of the item, NaN = no MI
   __shared__ uint32_t s_ij[kPairsMax];  // (i << 16) | j
   __shared__ uint32_t s_warp[kThreads / 32];
@@ -172,10 +178,11 @@ __global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
   const LnGlobal ln{P.lntab};
   const bool het_only = (P.mode & LGMI_MODE_HET_ONLY) != 0u;
   const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
-  if (*P.n_generic == 0u) return;  // every item was a small unit taken by k_pairs_fast
+  if (!kTiled && *P.n_generic == 0u) return;  // every item was a small unit taken by k_pairs_fast
 
   for (uint32_t item_idx = blockIdx.x; item_idx < P.n_items; item_idx += gridDim.x) {
     const Item it = P.items[item_idx];
+    if (kTiled != ((it.flags & ITEM_TILED) != 0u)) continue;          // the other instantiation's
     if ((it.flags & ITEM_FAST) && !P.item_dense[item_idx]) continue;  // k_pairs_fast's
     const DevUnit u = P.units[it.unit];
     const uint32_t W4 = u.W >> 2;
@@ -186,36 +193,45 @@ __global__ void __launch_bounds__(kThreads) k_pairs_generic(const RunParams P) {
     // ---- counts + MI for every candidate pair of the item
     uint32_t i = 0, j = 0;
     if (tid < it.pair_cnt) lg_pair_ij(it.pair_begin + tid, u.S, i, j);  // one square root per thread, then steps
-    for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
-      if (pl != tid) lg_pair_advance(i, j, u.S, kThreads);
-      s_ij[pl] = (i << 16) | j;
-      double mi = lg_nan();
-      bool evaluate = true;
-      if (skip_nonhet)
-        evaluate = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
-                   ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
-      if (u.tiled) {
-        mi = P.dense[u.dense_off + it.pair_begin + pl];  // k_tile_mi has been here (NaN: dropped / not evaluated)
-      } else if (evaluate && u.gram_off != kNoGram) {
-        uint32_t T[9];
-        const uint32_t n_common = gram_table(P.gram + u.gram_off, u.S_pad, i, j, T);
-        if ((int)n_common >= P.min_common) {
-          if ((T[0] | T[1] | T[2] | T[3] | T[6]) == 0u) mi = lg_mi_from_2x2(T[4], T[5], T[7], T[8], ln);
-          else mi = lg_mi_from_table(T, ln);
-        }
-      } else if (evaluate) {
-        const uint4* ri = base + (size_t)i * 3u * W4;
-        const uint4* rj = base + (size_t)j * 3u * W4;
-        const uint32_t n_common = pair_common(ri, rj, W4);
-        if ((int)n_common >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
-          uint32_t T[9];
-          if (pair_table(ri, rj, W4, n_common, T))
-            mi = lg_mi_from_2x2(T[4], T[5], T[7], T[8], ln);
-          else
-            mi = lg_mi_from_table(T, ln);
-        }
+    if constexpr (kTiled) {
+      // k_tile_mi has been here (NaN: dropped / not evaluated): the loads first, all in flight together
+      const double* __restrict__ src = P.dense + u.dense_off + it.pair_begin;
+#pragma unroll 8
+      for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) s_mi[pl] = src[pl];
+      for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
+        if (pl != tid) lg_pair_advance(i, j, u.S, kThreads);
+        s_ij[pl] = (i << 16) | j;
       }
-      s_mi[pl] = mi;
+    } else {
+      for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
+        if (pl != tid) lg_pair_advance(i, j, u.S, kThreads);
+        s_ij[pl] = (i << 16) | j;
+        double mi = lg_nan();
+        bool evaluate = true;
+        if (skip_nonhet)
+          evaluate = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
+                     ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+        if (evaluate && u.gram_off != kNoGram) {
+          uint32_t T[9];
+          const uint32_t n_common = gram_table(P.gram + u.gram_off, u.S_pad, i, j, T);
+          if ((int)n_common >= P.min_common) {
+            if ((T[0] | T[1] | T[2] | T[3] | T[6]) == 0u) mi = lg_mi_from_2x2(T[4], T[5], T[7], T[8], ln);
+            else mi = lg_mi_from_table(T, ln);
+          }
+        } else if (evaluate) {
+          const uint4* ri = base + (size_t)i * 3u * W4;
+          const uint4* rj = base + (size_t)j * 3u * W4;
+          const uint32_t n_common = pair_common(ri, rj, W4);
+          if ((int)n_common >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
+            uint32_t T[9];
+            if (pair_table(ri, rj, W4, n_common, T))
+              mi = lg_mi_from_2x2(T[4], T[5], T[7], T[8], ln);
+            else
+              mi = lg_mi_from_table(T, ln);
+          }
+        }
+        s_mi[pl] = mi;
+      }
     }
     __syncthreads();
 
