@@ -13,12 +13,18 @@ N-times larger transcriptome (units are independent: no collective on the data
 path; torch.distributed is used only for the barrier and the max-over-ranks
 time), so scaling is "weak".
 
-Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM;
-`e2e` goes through the C-ABI calls with pinned HOST buffers, H2D and D2H inside
-the timed region.  `roofline` is for the dominant kernel (k_pairs_fast), timed live
-with CUDA events on the launching stream.  `cpu_baseline` times the oracle's
-port of the reference step on the host cores on a bounded sample of the same
-units.
+Prints ONE JSON line (rank 0):
+  value         inputs resident in HBM, CUDA events around K steps, max over ranks
+  e2e           lgmi_pipeline_step through the C ABI: pinned HOST planes in, pinned HOST
+                rows + per-site means out, H2D / kernels / D2H of four groups of units
+                overlapped inside the call (the plain upload-run-download time is
+                reported next to it)
+  roofline      the dominant kernel (k_pairs_fast) against the measured HBM bandwidth,
+                timed live with CUDA events on the launching stream
+  cpu_baseline  the unmodified reference (baseline/_ref; the oracle's port if that is
+                absent) on the host cores over a bounded sample of the same units (N=1)
+  dense         N=1 only: BASELINE.json configs[2], one unit of 2 000 sites x 100 000
+                reads through the int8 tcgen05 path, with a tensor roofline for k_gram_i8
 """
 from __future__ import annotations
 
@@ -456,7 +462,7 @@ def run_gpu(args):
 
     if prev_affinity:
         os.sched_setaffinity(0, prev_affinity)               # the CPU baseline gets every host core again
-    cpu = None if args.no_cpu_baseline else cpu_baseline()
+    cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline()      # rank 0 at N=1 only
     dense = None
     if world == 1 and not args.no_dense:
         dense = dense_leg(lg, synth, ctx, torch, stream, max(3, min(args.steps, 5)), 3, flush)
