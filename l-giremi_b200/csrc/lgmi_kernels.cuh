@@ -654,18 +654,102 @@ __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
   }
 }
 
-// Per-site mean for units whose pairs span several work items; reads the dense
-// per-unit MI scratch written by k_pairs_generic.  One WARP per site: the lanes
-// fetch 32 partners' MI at a time (coalesced for partners above the site), then
-// the compensated sum runs over them in partner order -- the order is part of
-// the result (mutual_information.py:56-58 is a left-to-right float sum), so the
-// additions stay serial while the loads do not.
-constexpr int kMeanSites = 8;  // sites (= warps) per CTA
+// Per-site mean for units whose pairs span several work items; reads the dense per-unit MI
+// scratch (pair order = upper triangle of the symmetric site x site matrix).  One CTA per 32
+// consecutive sites: 32 x 32 tiles of the matrix are staged in shared memory with coalesced
+// loads -- partners below the site block come from the partners' rows, partners above from the
+// sites' rows, stored transposed -- double-buffered, and warp 0 runs the 32 compensated sums
+// side by side, one site per lane, partners ascending.  The order of the additions is part of
+// the result (mutual_information.py:56-58 is a left-to-right float sum), so each site's sum is
+// serial; the 32 sites of a block are not.
+constexpr int kMeanSites = 32;    // sites per CTA (= lanes of the consuming warp)
+constexpr int kMeanThreads = 128;
+constexpr uint32_t kMeanWideMinSites = 512;  // from here on the warp-per-site form (k_site_mean_wide) is used
 struct MeanItem {
   uint32_t unit;
   uint32_t site_begin;
 };
-__global__ void __launch_bounds__(kMeanSites * 32) k_site_mean_dense(const DevUnit* __restrict__ units,
+__global__ void __launch_bounds__(kMeanThreads) k_site_mean_dense(const DevUnit* __restrict__ units,
+                                                                 const MeanItem* __restrict__ items,
+                                                                 const uint8_t* __restrict__ site_flags,
+                                                                 const double* __restrict__ dense,
+                                                                 double* __restrict__ site_mean,
+                                                                 uint32_t* __restrict__ site_cnt) {
+  __shared__ double s_tile[2][32][33];  // [buffer][partner][site]; NaN: no MI / not a pair
+  __shared__ uint8_t s_phet[2][32];     // partner is a het_snp
+  const MeanItem mi = items[blockIdx.x];
+  const DevUnit u = units[mi.unit];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t S = u.S, s0 = mi.site_begin;
+  const uint8_t* __restrict__ flags = site_flags + u.site_off;
+  const double* __restrict__ d = dense + u.dense_off;
+  const uint32_t n_blocks = (S + 31u) >> 5;
+
+  auto load_tile = [&](uint32_t b, uint32_t tb) {  // partners t0 .. t0 + 31 against sites s0 .. s0 + 31
+    const uint32_t t0 = tb << 5;
+    for (uint32_t e = tid; e < 1024u; e += kMeanThreads) {
+      // below the diagonal block the fast index runs over the sites (row of the partner), above it over
+      // the partners (row of the site); inside it either way
+      const uint32_t hi = e >> 5, lo = e & 31u;
+      const uint32_t tl = (t0 < s0) ? hi : lo, sl = (t0 < s0) ? lo : hi;
+      const uint32_t t = t0 + tl, s = s0 + sl;
+      double v = lg_nan();
+      if (t < S && s < S && t != s)
+        v = d[(t < s) ? lg_row_off(t, S) + (s - t - 1u) : lg_row_off(s, S) + (t - s - 1u)];
+      s_tile[b][tl][sl] = v;
+    }
+    if (tid < 32u) s_phet[b][tid] = (t0 + tid < S) && (flags[t0 + tid] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
+  };
+
+  const uint32_t s = s0 + lane;
+  const bool s_ok = s < S;
+  const bool s_het = s_ok && (flags[s_ok ? s : 0u] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
+  lg_neumaier acc;
+  lg_neumaier_init(acc);
+  load_tile(0, 0);
+  __syncthreads();
+  for (uint32_t tb = 0; tb < n_blocks; ++tb) {
+    const uint32_t b = tb & 1u;
+    if (warp == 0) {  // consume this tile: one site per lane, partners ascending
+      if (s_ok) {
+        for (uint32_t tl = 0; tl < 32u; ++tl) {
+          const double v = s_tile[b][tl][lane];
+          if (!isnan(v) && (s_het || s_phet[b][tl])) lg_neumaier_add(acc, v);
+        }
+      }
+    } else if (tb + 1u < n_blocks) {  // the other warps fetch the next tile meanwhile
+      const uint32_t t0 = (tb + 1u) << 5;
+      for (uint32_t e = tid - 32u; e < 1024u; e += kMeanThreads - 32u) {
+        const uint32_t hi = e >> 5, lo = e & 31u;
+        const uint32_t tl = (t0 < s0) ? hi : lo, sl = (t0 < s0) ? lo : hi;
+        const uint32_t t = t0 + tl, ss = s0 + sl;
+        double v = lg_nan();
+        if (t < S && ss < S && t != ss)
+          v = d[(t < ss) ? lg_row_off(t, S) + (ss - t - 1u) : lg_row_off(ss, S) + (t - ss - 1u)];
+        s_tile[b ^ 1u][tl][sl] = v;
+      }
+      if (tid >= 32u && tid < 64u) {
+        const uint32_t t = t0 + (tid - 32u);
+        s_phet[b ^ 1u][tid - 32u] = (t < S) && (flags[t < S ? t : 0u] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0 && s_ok) {
+    site_mean[u.site_off + s] = lg_neumaier_mean(acc);
+    site_cnt[u.site_off + s] = (uint32_t)acc.n;
+  }
+}
+
+
+// The same for units with many sites (few of them, long sums): one WARP per site, so that a
+// single deep unit still fills the machine: the lanes
+// fetch 32 partners' MI at a time (coalesced for partners above the site), then
+// the compensated sum runs over them in partner order -- the order is part of
+// the result (mutual_information.py:56-58 is a left-to-right float sum), so the
+// additions stay serial while the loads do not.
+constexpr int kMeanWideSites = 8;  // sites (= warps) per CTA of the warp-per-site form
+__global__ void __launch_bounds__(kMeanWideSites * 32) k_site_mean_wide(const DevUnit* __restrict__ units,
                                                                     const MeanItem* __restrict__ items,
                                                                     const uint8_t* __restrict__ site_flags,
                                                                     const double* __restrict__ dense,
