@@ -15,10 +15,10 @@ time), so scaling is "weak".
 
 Prints ONE JSON line (rank 0):
   value         inputs resident in HBM, CUDA events around K steps, max over ranks
-  e2e           lgmi_pipeline_step through the C ABI: pinned HOST planes in, pinned HOST
-                rows + per-site means out, H2D / kernels / D2H of four groups of units
-                overlapped inside the call (the plain upload-run-download time is
-                reported next to it)
+  e2e           lgmi_pipeline_step_packed through the C ABI: pinned HOST planes in (packed
+                two-plane form), pinned HOST rows (MI + (i, j) arrays) + per-site means
+                out, H2D / kernels / D2H of four groups of units overlapped inside the
+                call (the plain three-plane upload-run-download time is reported next to it)
   roofline      the dominant kernel (k_pairs_fast) against the measured HBM bandwidth,
                 timed live with CUDA events on the launching stream
   cpu_baseline  the unmodified reference (baseline/_ref; the oracle's port if that is
@@ -400,13 +400,17 @@ def run_gpu(args):
     # D2H of consecutive groups of units overlap inside the call (what lg.mi_step_batched does for big batches)
     mode_e2e = lg.MODE_HET_ONLY                              # what mismatch.py:393-404 hands on
     pipe = lg.Pipeline(ctx, pb, args.e2e_chunks)
+    # the library's compact host formats: two-plane input (2 bits per site and read), rows as MI + (i, j) arrays
+    packed = pb.packed2()
+    pin_packed = ctx.pinned_empty(packed.shape, np.uint32)
+    pin_packed.array[...] = packed
     def e2e_step():
-        return pipe.step(mc, mode_e2e, pin_planes.array, pin_flags.array, copy=False)
+        return pipe.step(mc, mode_e2e | lg.MODE_SPLIT_RECORDS, pin_packed.array, pin_flags.array, copy=False, packed=True)
     e2e_steps = 0 if args.no_e2e else args.steps
     for _ in range(args.warmup if e2e_steps else 1):
         out = e2e_step()
-    h2d = pb.planes.nbytes + pb.site_flags.nbytes
-    d2h = out.n_records * 16 + pb.n_sites * 12 + (pb.n_units + args.e2e_chunks) * 8 + 16 * args.e2e_chunks
+    h2d = packed.nbytes + pb.site_flags.nbytes
+    d2h = out.n_records * 12 + pb.n_sites * 12 + (pb.n_units + args.e2e_chunks) * 8 + 16 * args.e2e_chunks
     launches_e2e0 = ctx.launch_count
     barrier()
     t0 = time.perf_counter()
@@ -481,7 +485,8 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "mode": "HET_ONLY: all candidates evaluated, het-kept rows (%d) + per-site mean MI returned"
                         % e2e_records, "ms_per_step": 1e3 * float(t.item()) / e2e_steps if e2e_steps else None,
-                "api": "lgmi_pipeline_step, %d groups of units on their own streams" % args.e2e_chunks,
+                "api": "lgmi_pipeline_step_packed (two-plane input, split rows), %d groups of units on their own "
+                       "streams" % args.e2e_chunks,
                 "serial_upload_run_download_ms": serial_ms, "gpu_launches": launches_e2e * world,
                 "host_affinity": numa_note},
         "gpu_launches": launches * world,
@@ -509,7 +514,7 @@ def main():
     ap.add_argument("--impl", choices=["graft", "reference"], default="graft")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="groups of units of the pipelined end-to-end step")
+    ap.add_argument("--e2e-chunks", type=int, default=6, help="groups of units of the pipelined end-to-end step")
     ap.add_argument("--no-dense", action="store_true", help="skip the cfg3 deep-unit (tensor-core) leg")
     ap.add_argument("--dense-only", action="store_true", help="profiling runs: only the cfg3 deep-unit leg")
     args = ap.parse_args()

@@ -104,6 +104,11 @@ typedef struct {
                                    /* pairs without a het partner (dead work   */
                                    /* in the reference); reported   */
                                    /* separately, never in the headline        */
+#define LGMI_MODE_SPLIT_RECORDS 0x8u /* lgmi_pipeline_step*: deliver the rows as  */
+                                   /* two arrays rec_mi / rec_ij (12 bytes per  */
+                                   /* row over PCIe instead of 16) and leave    */
+                                   /* `records` NULL; the unit of a row follows */
+                                   /* from unit_rec_off                         */
 
 /* one emitted pair == one row [p1,type1,p2,type2,mi] of                       *
  * mutual_information.py:42-44; i<j index the unit's sorted positions.         */
@@ -142,6 +147,8 @@ typedef struct {
   float gram_kernel_ms;         /* k_gram_i8 of the last such unit, alone      */
   uint32_t reserved;
   uint64_t gram_macs;           /* multiply-accumulates of that launch         */
+  const double* rec_mi;         /* LGMI_MODE_SPLIT_RECORDS: MI of every row    */
+  const uint32_t* rec_ij;       /* ... and its i | j << 16                     */
 } lgmi_result;
 
 typedef struct lgmi_ctx lgmi_t;
@@ -212,6 +219,13 @@ LGMI_API int lgmi_pipeline_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint
                          lgmi_pipeline_t** out);
 LGMI_API int lgmi_pipeline_step(lgmi_pipeline_t* p, const uint32_t* planes, const uint8_t* site_flags,
                        int min_common, uint32_t mode, lgmi_result* out);
+/* The same with the input in the packed two-plane form: 2 bits per site and  *
+ * read (00 not covered, 01 major, 10 minor, 11 other), row of site s =        *
+ * [b0 | b1] with W words each, units back to back (unit k starts at 2/3 of    *
+ * its plane_off): a third fewer bytes over PCIe; expanded on the device.      */
+LGMI_API int lgmi_pipeline_step_packed(lgmi_pipeline_t* p, const uint32_t* planes2,
+                              const uint8_t* site_flags, int min_common, uint32_t mode,
+                              lgmi_result* out);
 LGMI_API void lgmi_pipeline_destroy(lgmi_pipeline_t* p);
 
 /* one-shot convenience: create + upload + run + download (+ destroy on wait)  */

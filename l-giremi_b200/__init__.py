@@ -12,6 +12,7 @@ Public surface (same names as the reference where one exists):
     install / uninstall                                                -- patch a loaded `giremi`
 """
 from ._lib import (DENSE_DEFAULT, LIB_PATH, MODE_ALL_PAIRS, MODE_EMIT_COUNTS, MODE_HET_ONLY, MODE_SKIP_NONHET,
+                   MODE_SPLIT_RECORDS,
                    PAIR_REC, SITE_HET_SNP, SITE_MISMATCH, SITE_SNP, UNIT_DESC, LgmiError)
 from .api import (Batch, Context, Pipeline, StepResult, ecdf, get_context, mean_mismatch_pair_mutual_info,
                   mi_step_batched, mip_and_calls, mismatch_pair_mutual_info, partition_lpt, site_splice_mutual_info,

@@ -29,6 +29,7 @@ MODE_ALL_PAIRS = 0x0
 MODE_HET_ONLY = 0x1
 MODE_EMIT_COUNTS = 0x2
 MODE_SKIP_NONHET = 0x4
+MODE_SPLIT_RECORDS = 0x8
 
 ERR_NODEVICE = -5
 DENSE_DEFAULT = (48, 8192)    # lgmi_set_dense_threshold defaults: (min_sites, min_reads)
@@ -39,7 +40,8 @@ EXPORTS = (
     "lgmi_set_small_path",
     "lgmi_batch_create", "lgmi_batch_destroy", "lgmi_batch_upload", "lgmi_batch_run",
     "lgmi_batch_download", "lgmi_batch_sync", "lgmi_batch_device_ptrs",
-    "lgmi_batch_algorithmic_bytes", "lgmi_pipeline_create", "lgmi_pipeline_step", "lgmi_pipeline_destroy",
+    "lgmi_batch_algorithmic_bytes", "lgmi_pipeline_create", "lgmi_pipeline_step", "lgmi_pipeline_step_packed",
+    "lgmi_pipeline_destroy",
     "lgmi_submit", "lgmi_wait", "lgmi_site_mean_csr",
     "lgmi_ecdf", "lgmi_ecdf_eval", "lgmi_cs_scan", "lgmi_encode_unit", "lgmi_unit_cost", "lgmi_partition_lpt",
 )
@@ -64,6 +66,8 @@ class Result(C.Structure):
         ("gram_kernel_ms", C.c_float),
         ("reserved", C.c_uint32),
         ("gram_macs", C.c_uint64),
+        ("rec_mi", C.c_void_p),
+        ("rec_ij", C.c_void_p),
     ]
 
 
@@ -109,6 +113,7 @@ def load():
         "lgmi_batch_algorithmic_bytes": (i32, [vp, C.POINTER(u64)]),
         "lgmi_pipeline_create": (i32, [vp, vp, u32, u64, u64, u32, pvp]),
         "lgmi_pipeline_step": (i32, [vp, vp, vp, i32, u32, C.POINTER(Result)]),
+        "lgmi_pipeline_step_packed": (i32, [vp, vp, vp, i32, u32, C.POINTER(Result)]),
         "lgmi_pipeline_destroy": (None, [vp]),
         "lgmi_submit": (i32, [vp, vp, u32, vp, u64, vp, u64, i32, u32]),
         "lgmi_wait": (i32, [vp, C.POINTER(Result)]),

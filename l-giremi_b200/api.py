@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (MODE_ALL_PAIRS, MODE_EMIT_COUNTS, MODE_HET_ONLY, MODE_SKIP_NONHET,
+from ._lib import (MODE_ALL_PAIRS, MODE_EMIT_COUNTS, MODE_HET_ONLY, MODE_SKIP_NONHET, MODE_SPLIT_RECORDS,
                    PAIR_REC, SITE_TYPE_CODE, LgmiError, Result, array_at, check, ptr)
 from .encode import EncodedUnit, PlaneBatch, encode_batch, encode_mismatches, pack_units
 
@@ -117,15 +117,38 @@ class StepResult:
         self.dense_macs = int(res.dense_macs)
         self.gram_kernel_ms = float(res.gram_kernel_ms)
         self.gram_macs = int(res.gram_macs)
-        rec = array_at(res.records, PAIR_REC, self.n_records)
+        off = array_at(res.unit_rec_off, np.uint64, n_units + 1)
+        self.rec_mi = self.rec_ij = None
+        if not res.records and res.rec_mi:                   # MODE_SPLIT_RECORDS: two arrays instead of 16-byte rows
+            self.rec_mi = array_at(res.rec_mi, np.float64, self.n_records)
+            self.rec_ij = array_at(res.rec_ij, np.uint32, self.n_records)
+            if copy:
+                self.rec_mi, self.rec_ij = self.rec_mi.copy(), self.rec_ij.copy()
+            rec = None
+        else:
+            rec = array_at(res.records, PAIR_REC, self.n_records)
         mean = array_at(res.site_mean, np.float64, int(res.n_sites))
         cnt = array_at(res.site_cnt, np.uint32, int(res.n_sites))
-        off = array_at(res.unit_rec_off, np.uint64, n_units + 1)
         counts = array_at(res.counts, np.uint32, self.n_records * 9).reshape(-1, 9) if res.counts else None
         if copy:
-            rec, mean, cnt, off = rec.copy(), mean.copy(), cnt.copy(), off.copy()
+            rec = rec.copy() if rec is not None else None
+            mean, cnt, off = mean.copy(), cnt.copy(), off.copy()
             counts = counts.copy() if counts is not None else None
-        self.records, self.site_mean, self.site_cnt, self.unit_rec_off, self.counts = rec, mean, cnt, off, counts
+        self._records, self.site_mean, self.site_cnt, self.unit_rec_off, self.counts = rec, mean, cnt, off, counts
+
+    @property
+    def records(self):
+        """Rows as (unit, i, j, mi); assembled on the host from the split arrays when the step
+        ran with MODE_SPLIT_RECORDS."""
+        if self._records is None:
+            rec = np.empty(self.n_records, dtype=PAIR_REC)
+            rec['mi'] = self.rec_mi
+            rec['i'] = self.rec_ij & 0xffff
+            rec['j'] = self.rec_ij >> 16
+            n = np.diff(self.unit_rec_off.astype(np.int64))
+            rec['unit'] = np.repeat(np.arange(len(n), dtype=np.uint32), n)
+            self._records = rec
+        return self._records
 
     def unit_records(self, unit):
         a, b = int(self.unit_rec_off[unit]), int(self.unit_rec_off[unit + 1])
@@ -204,14 +227,17 @@ class Pipeline:
                                              int(n_chunks), C.byref(h)), ctx.handle)
         self.handle = h
 
-    def step(self, min_common, mode=MODE_HET_ONLY, planes=None, site_flags=None, copy=True) -> StepResult:
-        planes = self.pb.planes if planes is None else planes
+    def step(self, min_common, mode=MODE_HET_ONLY, planes=None, site_flags=None, copy=True, packed=False) -> StepResult:
+        """One pipelined step.  packed=True: `planes` is the two-plane form (PlaneBatch.packed2(),
+        two thirds of the bytes); mode | MODE_SPLIT_RECORDS: rows come back as rec_mi / rec_ij."""
+        if planes is None:
+            planes = self.pb.packed2() if packed else self.pb.planes
         site_flags = self.pb.site_flags if site_flags is None else site_flags
-        assert planes.dtype == np.uint32 and planes.size == self.pb.planes.size
+        assert planes.dtype == np.uint32 and planes.size == (self.pb.planes.size // 3 * 2 if packed else self.pb.planes.size)
         assert site_flags.dtype == np.uint8 and site_flags.size == self.pb.n_sites
         res = Result()
-        check(self._lib.lgmi_pipeline_step(self.handle, ptr(planes), ptr(site_flags), int(min_common), int(mode),
-                                           C.byref(res)), self.ctx.handle)
+        fn = self._lib.lgmi_pipeline_step_packed if packed else self._lib.lgmi_pipeline_step
+        check(fn(self.handle, ptr(planes), ptr(site_flags), int(min_common), int(mode), C.byref(res)), self.ctx.handle)
         return StepResult(res, self.pb.n_units, copy=copy)
 
     def close(self):

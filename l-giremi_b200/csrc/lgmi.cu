@@ -934,12 +934,19 @@ struct lgmi_pipeline {
     uint32_t unit0 = 0, n_units = 0;
     uint64_t plane0 = 0, site0 = 0;
     cudaEvent_t done = nullptr;
+    uint32_t* d_packed = nullptr;   // two-plane input staging (lgmi_pipeline_step_packed)
+    double* d_rec_mi = nullptr;     // split output (LGMI_MODE_SPLIT_RECORDS)
+    uint32_t* d_rec_ij = nullptr;
   };
   std::vector<Chunk> chunks;
   lgmi_pair_rec* h_records = nullptr;
   uint64_t h_rec_cap = 0;
   uint32_t* h_counts = nullptr;
   uint64_t h_counts_cap = 0;
+  double* h_rec_mi = nullptr;
+  uint64_t h_rec_mi_cap = 0;
+  uint32_t* h_rec_ij = nullptr;
+  uint64_t h_rec_ij_cap = 0;
   double* h_site_mean = nullptr;
   uint32_t* h_site_cnt = nullptr;
   unsigned long long* h_unit_rec_off = nullptr;
@@ -955,7 +962,12 @@ extern "C" void lgmi_pipeline_destroy(lgmi_pipeline_t* p) {
       if (st) cudaStreamDestroy(st);
     }
     if (c.done) cudaEventDestroy(c.done);
+    cudaFree(c.d_packed);
+    cudaFree(c.d_rec_mi);
+    cudaFree(c.d_rec_ij);
   }
+  cudaFreeHost(p->h_rec_mi);
+  cudaFreeHost(p->h_rec_ij);
   cudaFreeHost(p->h_records);
   cudaFreeHost(p->h_counts);
   cudaFreeHost(p->h_site_mean);
@@ -1060,21 +1072,46 @@ static int grow_pinned(lgmi_pipeline* p, T*& buf, uint64_t& cap, uint64_t need, 
   return LGMI_OK;
 }
 
-extern "C" int lgmi_pipeline_step(lgmi_pipeline_t* p, const uint32_t* planes, const uint8_t* site_flags, int min_common,
-                                  uint32_t mode, lgmi_result* out) {
+static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, const uint8_t* site_flags, int min_common,
+                         uint32_t mode, lgmi_result* out) {
   if (!p || !out) return LGMI_ERR_ARG;
   lgmi_ctx* ctx = p->ctx;
   if ((!planes && p->plane_words) || (!site_flags && p->n_sites))
     return fail(ctx, LGMI_ERR_ARG, "lgmi_pipeline_step: NULL input");
   CU(ctx, cudaSetDevice(ctx->device));
   const bool want_counts = (mode & LGMI_MODE_EMIT_COUNTS) != 0u;
+  const bool split = (mode & LGMI_MODE_SPLIT_RECORDS) != 0u;
+  mode &= ~LGMI_MODE_SPLIT_RECORDS;  // a matter of the output copies, not of the kernels
   // everything that does not depend on a count is queued up front, group after group
   for (lgmi_pipeline::Chunk& c : p->chunks) {
     lgmi_batch* b = c.b;
     cudaStream_t st = b->own_stream;
-    int rc = lgmi_batch_upload(b, planes + c.plane0, site_flags + c.site0);
+    int rc = LGMI_OK;
+    if (packed) {
+      // two planes per site over PCIe, expanded on the device
+      const uint64_t words2 = b->plane_words / 3u * 2u;
+      if (!c.d_packed && words2) CU(ctx, cudaMalloc(&c.d_packed, words2 * sizeof(uint32_t)));
+      if (words2) {
+        CU(ctx, cudaMemcpyAsync(c.d_packed, planes + c.plane0 / 3u * 2u, words2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        k_unpack2<<<std::min<uint32_t>(b->n_units, (uint32_t)ctx->num_sms * 16u), 256, 0, st>>>(b->d_units, b->n_units,
+                                                                                              c.d_packed, b->d_planes);
+        ++ctx->launches;
+      }
+      if (b->n_sites) CU(ctx, cudaMemcpyAsync(b->d_flags, site_flags + c.site0, b->n_sites, cudaMemcpyHostToDevice, st));
+      b->uploaded = true;
+    } else {
+      rc = lgmi_batch_upload(b, planes + c.plane0, site_flags + c.site0);
+    }
     if (!rc) rc = lgmi_batch_run(b, min_common, mode);
     if (rc) return rc;
+    if (split) {
+      if (!c.d_rec_mi) {
+        CU(ctx, cudaMalloc(&c.d_rec_mi, b->rec_cap * sizeof(double)));
+        CU(ctx, cudaMalloc(&c.d_rec_ij, b->rec_cap * sizeof(uint32_t)));
+      }
+      k_split_records<<<(unsigned)ctx->num_sms * 8u, 256, 0, st>>>(b->d_header, b->d_records, c.d_rec_mi, c.d_rec_ij);
+      ++ctx->launches;
+    }
     CU(ctx, cudaMemcpyAsync(b->h_header, b->d_header, sizeof(Header), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaMemcpyAsync(b->h_unit_rec_off, b->d_unit_rec_off, ((size_t)b->n_units + 1) * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, st));
@@ -1092,12 +1129,23 @@ extern "C" int lgmi_pipeline_step(lgmi_pipeline_t* p, const uint32_t* planes, co
     const uint64_t nrec = b->h_header->n_records;
     if (b->h_header->pad) return fail(ctx, LGMI_ERR_CUDA, "k_gram_i8: a pipeline barrier timed out (tensor-core path)");
     if (nrec > b->rec_cap) return fail(ctx, LGMI_ERR_STATE, "record count %llu exceeds capacity", (unsigned long long)nrec);
-    int rc = grow_pinned(p, p->h_records, p->h_rec_cap, base + nrec, base, sizeof(lgmi_pair_rec));
+    int rc = LGMI_OK;
+    if (split) {
+      rc = grow_pinned(p, p->h_rec_mi, p->h_rec_mi_cap, base + nrec, base, sizeof(double));
+      if (!rc) rc = grow_pinned(p, p->h_rec_ij, p->h_rec_ij_cap, base + nrec, base, sizeof(uint32_t));
+    } else {
+      rc = grow_pinned(p, p->h_records, p->h_rec_cap, base + nrec, base, sizeof(lgmi_pair_rec));
+    }
     if (!rc && want_counts) rc = grow_pinned(p, p->h_counts, p->h_counts_cap, base + nrec, base, 9 * sizeof(uint32_t));
     if (rc) return rc;
     if (nrec) {
-      CU(ctx, cudaMemcpyAsync(p->h_records + base, b->d_records, nrec * sizeof(lgmi_pair_rec), cudaMemcpyDeviceToHost,
-                              b->own_stream));
+      if (split) {
+        CU(ctx, cudaMemcpyAsync(p->h_rec_mi + base, c.d_rec_mi, nrec * sizeof(double), cudaMemcpyDeviceToHost, b->own_stream));
+        CU(ctx, cudaMemcpyAsync(p->h_rec_ij + base, c.d_rec_ij, nrec * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->own_stream));
+      } else {
+        CU(ctx, cudaMemcpyAsync(p->h_records + base, b->d_records, nrec * sizeof(lgmi_pair_rec), cudaMemcpyDeviceToHost,
+                                b->own_stream));
+      }
       if (want_counts)
         CU(ctx, cudaMemcpyAsync(p->h_counts + base * 9ull, b->d_counts, nrec * 9ull * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                 b->own_stream));
@@ -1111,7 +1159,9 @@ extern "C" int lgmi_pipeline_step(lgmi_pipeline_t* p, const uint32_t* planes, co
   out->n_candidates = p->n_candidates;
   out->n_evaluated = p->n_candidates;
   out->n_records = base;
-  out->records = p->h_records;
+  out->records = split ? nullptr : p->h_records;
+  out->rec_mi = split ? p->h_rec_mi : nullptr;
+  out->rec_ij = split ? p->h_rec_ij : nullptr;
   out->counts = want_counts ? p->h_counts : nullptr;
   out->n_sites = p->n_sites;
   out->site_mean = p->h_site_mean;
@@ -1128,6 +1178,16 @@ extern "C" int lgmi_pipeline_step(lgmi_pipeline_t* p, const uint32_t* planes, co
     out->dense_macs += r.dense_macs;
   }
   return LGMI_OK;
+}
+
+extern "C" int lgmi_pipeline_step(lgmi_pipeline_t* p, const uint32_t* planes, const uint8_t* site_flags, int min_common,
+                                  uint32_t mode, lgmi_result* out) {
+  return pipeline_step(p, planes, false, site_flags, min_common, mode, out);
+}
+
+extern "C" int lgmi_pipeline_step_packed(lgmi_pipeline_t* p, const uint32_t* planes2, const uint8_t* site_flags,
+                                         int min_common, uint32_t mode, lgmi_result* out) {
+  return pipeline_step(p, planes2, true, site_flags, min_common, mode, out);
 }
 
 // --------------------------------------------------------------------------- one-shot

@@ -119,6 +119,26 @@ class PlaneBatch:
         s = self.units['n_sites'].astype(np.int64)
         return int((s * (s - 1) // 2).sum())
 
+    def packed2(self) -> np.ndarray:
+        """The planes in the two-plane form of lgmi_pipeline_step_packed: per site row [b0 | b1]
+        with b0 = major | other, b1 = minor | other (2 bits per read: 00 not covered, 01 major,
+        10 minor, 11 other).  Two thirds of the bytes of the [M | m | C] form."""
+        out = np.empty(self.planes.size // 3 * 2, dtype=np.uint32)
+        S = self.units['n_sites'].astype(np.int64)
+        W = self.units['row_words'].astype(np.int64)
+        off = self.units['plane_off'].astype(np.int64)
+        for w in np.unique(W[S > 0]):                         # all units of one row width at once
+            sel = np.flatnonzero((W == w) & (S > 0))
+            rows = np.concatenate([off[k] + 3 * w * np.arange(S[k]) for k in sel])
+            idx = rows[:, None] + np.arange(w)[None, :]
+            M, m, C = self.planes[idx], self.planes[idx + w], self.planes[idx + 2 * w]
+            other = C & ~M & ~m
+            dst = rows // 3 * 2
+            didx = dst[:, None] + np.arange(w)[None, :]
+            out[didx] = M | other
+            out[didx + w] = m | other
+        return out
+
     def site_types(self, unit):
         off = int(self.units['site_off'][unit])
         n = int(self.units['n_sites'][unit])
