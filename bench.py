@@ -514,7 +514,7 @@ def main():
     ap.add_argument("--impl", choices=["graft", "reference"], default="graft")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
-    ap.add_argument("--e2e-chunks", type=int, default=6, help="groups of units of the pipelined end-to-end step")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="groups of units of the pipelined end-to-end step")
     ap.add_argument("--no-dense", action="store_true", help="skip the cfg3 deep-unit (tensor-core) leg")
     ap.add_argument("--dense-only", action="store_true", help="profiling runs: only the cfg3 deep-unit leg")
     args = ap.parse_args()

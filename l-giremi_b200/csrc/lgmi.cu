@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -662,7 +663,8 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   {
     // one launch resets the run state: header, offsets, flags, NaN means (sites of pair-less units keep them)
     const uint64_t n = std::max<uint64_t>(std::max<uint64_t>(b->n_sites, b->n_items), (uint64_t)b->n_units + 1);
-    k_run_init<<<(unsigned)((n + 255) / 256), 256, 0, bstream(b)>>>(b->d_header, b->d_unit_rec_off, b->n_units + 1,
+    k_run_init<<<(unsigned)((n + 255) / 256), 256, 0, bstream(b)>>>(b->d_header, b->own_stream ? b->h_header : nullptr,
+                                                                  b->d_unit_rec_off, b->n_units + 1,
                                                                   b->d_item_dense, b->n_items, b->d_n_generic,
                                                                   b->n_items - b->n_fast - b->n_pre - b->n_tiled_work_items, b->d_site_mean,
                                                                   b->d_site_cnt,
@@ -740,7 +742,8 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     CU(ctx, cub::DeviceScan::ExclusiveSum(b->d_scan_tmp, b->scan_tmp_bytes, b->d_item_cnt, b->d_item_off,
                                           (int)b->n_items + 1, bstream(b)));
     ++ctx->launches;
-    k_scan_finish<<<1, 32, 0, bstream(b)>>>(b->d_item_off + b->n_items, b->d_header, b->d_unit_rec_off + b->n_units);
+    k_scan_finish<<<1, 32, 0, bstream(b)>>>(b->d_item_off + b->n_items, b->d_header,
+                                            b->own_stream ? b->h_header : nullptr, b->d_unit_rec_off + b->n_units);
     ++ctx->launches;
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[2], bstream(b)));
@@ -933,12 +936,17 @@ struct lgmi_pipeline {
     lgmi_batch* b = nullptr;
     uint32_t unit0 = 0, n_units = 0;
     uint64_t plane0 = 0, site0 = 0;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr;     // the group's kernels have finished
+    cudaEvent_t landed = nullptr;   // the group's input is in device memory
     uint32_t* d_packed = nullptr;   // two-plane input staging (lgmi_pipeline_step_packed)
     double* d_rec_mi = nullptr;     // split output (LGMI_MODE_SPLIT_RECORDS)
     uint32_t* d_rec_ij = nullptr;
+    uint64_t base = 0;              // first row of the group in the merged output of the current step
   };
   std::vector<Chunk> chunks;
+  // one stream per copy direction: copies of a direction run one after the other anyway, and a stream that
+  // copies both ways can land on one engine with another stream's uploads in front of its downloads
+  cudaStream_t h2d = nullptr, d2h = nullptr;
   lgmi_pair_rec* h_records = nullptr;
   uint64_t h_rec_cap = 0;
   uint32_t* h_counts = nullptr;
@@ -962,10 +970,13 @@ extern "C" void lgmi_pipeline_destroy(lgmi_pipeline_t* p) {
       if (st) cudaStreamDestroy(st);
     }
     if (c.done) cudaEventDestroy(c.done);
+    if (c.landed) cudaEventDestroy(c.landed);
     cudaFree(c.d_packed);
     cudaFree(c.d_rec_mi);
     cudaFree(c.d_rec_ij);
   }
+  if (p->h2d) cudaStreamDestroy(p->h2d);
+  if (p->d2h) cudaStreamDestroy(p->d2h);
   cudaFreeHost(p->h_rec_mi);
   cudaFreeHost(p->h_rec_ij);
   cudaFreeHost(p->h_records);
@@ -1047,7 +1058,10 @@ extern "C" int lgmi_pipeline_create(lgmi_t* ctx, const lgmi_unit_desc* units, ui
     ref.b->unit_base = ref.unit0;  // records carry the unit's index in the whole batch
     PCU(cudaStreamCreateWithFlags(&ref.b->own_stream, cudaStreamNonBlocking));
     PCU(cudaEventCreateWithFlags(&ref.done, cudaEventDisableTiming));
+    PCU(cudaEventCreateWithFlags(&ref.landed, cudaEventDisableTiming));
   }
+  PCU(cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking));
+  PCU(cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking));
   PCU(cudaHostAlloc(&p->h_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double), cudaHostAllocDefault));
   PCU(cudaHostAlloc(&p->h_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t), cudaHostAllocDefault));
   PCU(cudaHostAlloc(&p->h_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -1061,7 +1075,7 @@ template <class T>
 static int grow_pinned(lgmi_pipeline* p, T*& buf, uint64_t& cap, uint64_t need, uint64_t keep, size_t elem) {
   if (need <= cap) return LGMI_OK;
   lgmi_ctx* ctx = p->ctx;
-  for (lgmi_pipeline::Chunk& c : p->chunks) CU(ctx, cudaStreamSynchronize(c.b->own_stream));  // copies into the old array
+  CU(ctx, cudaStreamSynchronize(p->d2h));  // copies into the old array
   const uint64_t new_cap = std::max<uint64_t>(need + need / 4, 1024);
   T* fresh = nullptr;
   CU(ctx, cudaHostAlloc(&fresh, new_cap * elem, cudaHostAllocDefault));
@@ -1082,26 +1096,36 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
   const bool want_counts = (mode & LGMI_MODE_EMIT_COUNTS) != 0u;
   const bool split = (mode & LGMI_MODE_SPLIT_RECORDS) != 0u;
   mode &= ~LGMI_MODE_SPLIT_RECORDS;  // a matter of the output copies, not of the kernels
+  static const bool debug = getenv("LGMI_PIPE_DEBUG") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  double t_enqueued = 0.0;
+  std::vector<double> t_done, t_copy, t_issue;
   // everything that does not depend on a count is queued up front, group after group
   for (lgmi_pipeline::Chunk& c : p->chunks) {
     lgmi_batch* b = c.b;
     cudaStream_t st = b->own_stream;
     int rc = LGMI_OK;
-    if (packed) {
-      // two planes per site over PCIe, expanded on the device
-      const uint64_t words2 = b->plane_words / 3u * 2u;
+    // input on the upload stream, in group order; the group's own stream picks up when it has landed
+    if (b->n_sites) CU(ctx, cudaMemcpyAsync(b->d_flags, site_flags + c.site0, b->n_sites, cudaMemcpyHostToDevice, p->h2d));
+    const uint64_t words2 = b->plane_words / 3u * 2u;
+    if (packed) {  // two planes per site over PCIe, expanded on the device
       if (!c.d_packed && words2) CU(ctx, cudaMalloc(&c.d_packed, words2 * sizeof(uint32_t)));
-      if (words2) {
-        CU(ctx, cudaMemcpyAsync(c.d_packed, planes + c.plane0 / 3u * 2u, words2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        k_unpack2<<<std::min<uint32_t>(b->n_units, (uint32_t)ctx->num_sms * 16u), 256, 0, st>>>(b->d_units, b->n_units,
-                                                                                              c.d_packed, b->d_planes);
-        ++ctx->launches;
-      }
-      if (b->n_sites) CU(ctx, cudaMemcpyAsync(b->d_flags, site_flags + c.site0, b->n_sites, cudaMemcpyHostToDevice, st));
-      b->uploaded = true;
-    } else {
-      rc = lgmi_batch_upload(b, planes + c.plane0, site_flags + c.site0);
+      if (words2)
+        CU(ctx, cudaMemcpyAsync(c.d_packed, planes + c.plane0 / 3u * 2u, words2 * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                p->h2d));
+    } else if (b->plane_words) {
+      CU(ctx, cudaMemcpyAsync(b->d_planes, planes + c.plane0, b->plane_words * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                              p->h2d));
     }
+    CU(ctx, cudaEventRecord(c.landed, p->h2d));
+    CU(ctx, cudaStreamWaitEvent(st, c.landed, 0));
+    if (packed && words2) {
+      k_unpack2<<<std::min<uint32_t>(b->n_units, (uint32_t)ctx->num_sms * 16u), 256, 0, st>>>(b->d_units, b->n_units,
+                                                                                            c.d_packed, b->d_planes);
+      ++ctx->launches;
+    }
+    b->uploaded = true;
     if (!rc) rc = lgmi_batch_run(b, min_common, mode);
     if (rc) return rc;
     if (split) {
@@ -1112,22 +1136,16 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
       k_split_records<<<(unsigned)ctx->num_sms * 8u, 256, 0, st>>>(b->d_header, b->d_records, c.d_rec_mi, c.d_rec_ij);
       ++ctx->launches;
     }
-    CU(ctx, cudaMemcpyAsync(b->h_header, b->d_header, sizeof(Header), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaMemcpyAsync(b->h_unit_rec_off, b->d_unit_rec_off, ((size_t)b->n_units + 1) * sizeof(unsigned long long),
-                            cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaEventRecord(c.done, st));
-    if (b->n_sites) {
-      CU(ctx, cudaMemcpyAsync(p->h_site_mean + c.site0, b->d_site_mean, b->n_sites * sizeof(double), cudaMemcpyDeviceToHost, st));
-      CU(ctx, cudaMemcpyAsync(p->h_site_cnt + c.site0, b->d_site_cnt, b->n_sites * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    }
+    CU(ctx, cudaEventRecord(c.done, st));  // the group's record count is in its (host-resident) header by then
   }
+  t_enqueued = since();
   // records: each group's place in the merged array is known once the groups before it have been counted
   uint64_t base = 0;
   for (lgmi_pipeline::Chunk& c : p->chunks) {
     lgmi_batch* b = c.b;
     CU(ctx, cudaEventSynchronize(c.done));
+    if (debug) t_done.push_back(since());
     const uint64_t nrec = b->h_header->n_records;
-    if (b->h_header->pad) return fail(ctx, LGMI_ERR_CUDA, "k_gram_i8: a pipeline barrier timed out (tensor-core path)");
     if (nrec > b->rec_cap) return fail(ctx, LGMI_ERR_STATE, "record count %llu exceeds capacity", (unsigned long long)nrec);
     int rc = LGMI_OK;
     if (split) {
@@ -1138,23 +1156,42 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
     }
     if (!rc && want_counts) rc = grow_pinned(p, p->h_counts, p->h_counts_cap, base + nrec, base, 9 * sizeof(uint32_t));
     if (rc) return rc;
+    cudaStream_t st = p->d2h;  // the group is complete (event above): nothing here waits on a kernel
     if (nrec) {
       if (split) {
-        CU(ctx, cudaMemcpyAsync(p->h_rec_mi + base, c.d_rec_mi, nrec * sizeof(double), cudaMemcpyDeviceToHost, b->own_stream));
-        CU(ctx, cudaMemcpyAsync(p->h_rec_ij + base, c.d_rec_ij, nrec * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->own_stream));
+        CU(ctx, cudaMemcpyAsync(p->h_rec_mi + base, c.d_rec_mi, nrec * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(p->h_rec_ij + base, c.d_rec_ij, nrec * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       } else {
-        CU(ctx, cudaMemcpyAsync(p->h_records + base, b->d_records, nrec * sizeof(lgmi_pair_rec), cudaMemcpyDeviceToHost,
-                                b->own_stream));
+        CU(ctx, cudaMemcpyAsync(p->h_records + base, b->d_records, nrec * sizeof(lgmi_pair_rec), cudaMemcpyDeviceToHost, st));
       }
       if (want_counts)
-        CU(ctx, cudaMemcpyAsync(p->h_counts + base * 9ull, b->d_counts, nrec * 9ull * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                b->own_stream));
+        CU(ctx, cudaMemcpyAsync(p->h_counts + base * 9ull, b->d_counts, nrec * 9ull * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
-    for (uint32_t u = 0; u < c.n_units; ++u) p->h_unit_rec_off[c.unit0 + u] = base + b->h_unit_rec_off[u];
+    CU(ctx, cudaMemcpyAsync(b->h_unit_rec_off, b->d_unit_rec_off, ((size_t)b->n_units + 1) * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st));
+    if (b->n_sites) {
+      CU(ctx, cudaMemcpyAsync(p->h_site_mean + c.site0, b->d_site_mean, b->n_sites * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CU(ctx, cudaMemcpyAsync(p->h_site_cnt + c.site0, b->d_site_cnt, b->n_sites * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    c.base = base;
     base += nrec;
+    if (debug) t_issue.push_back(since());
+  }
+  CU(ctx, cudaStreamSynchronize(p->d2h));
+  if (debug) t_copy.push_back(since());
+  for (lgmi_pipeline::Chunk& c : p->chunks) {
+    for (uint32_t u = 0; u < c.n_units; ++u) p->h_unit_rec_off[c.unit0 + u] = c.base + c.b->h_unit_rec_off[u];
   }
   p->h_unit_rec_off[p->n_units] = base;
-  for (lgmi_pipeline::Chunk& c : p->chunks) CU(ctx, cudaStreamSynchronize(c.b->own_stream));
+  if (debug) {
+    fprintf(stderr, "[lgmi pipeline] enqueued %.3f ms; groups counted at", t_enqueued);
+    for (double t : t_done) fprintf(stderr, " %.3f", t);
+    fprintf(stderr, "; D2H issued by");
+    for (double t : t_issue) fprintf(stderr, " %.3f", t);
+    fprintf(stderr, "; copied back at");
+    for (double t : t_copy) fprintf(stderr, " %.3f", t);
+    fprintf(stderr, " ms\n");
+  }
   memset(out, 0, sizeof *out);
   out->n_candidates = p->n_candidates;
   out->n_evaluated = p->n_candidates;

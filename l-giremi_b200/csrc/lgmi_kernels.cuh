@@ -822,7 +822,8 @@ __global__ void __launch_bounds__(256) k_split_records(const Header* __restrict_
 // start of a run: header and offsets zeroed, no item flagged, the count of items for
 // k_pairs_generic seeded, every site's mean = NaN / cnt = 0 (sites of units without a
 // pair, S < 2, keep that; everything else is overwritten)
-__global__ void k_run_init(Header* __restrict__ header, unsigned long long* __restrict__ unit_rec_off, uint32_t n_off,
+__global__ void k_run_init(Header* __restrict__ header, Header* __restrict__ host_header,
+                           unsigned long long* __restrict__ unit_rec_off, uint32_t n_off,
                            uint8_t* __restrict__ item_dense, uint32_t n_items, uint32_t* __restrict__ n_generic,
                            uint32_t n_generic0, double* __restrict__ mean, uint32_t* __restrict__ cnt, uint64_t n_sites) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -830,6 +831,10 @@ __global__ void k_run_init(Header* __restrict__ header, unsigned long long* __re
     header->n_records = 0ull;
     header->pad = 0ull;
     *n_generic = n_generic0;
+    if (host_header) {  // pinned host memory (unified addressing): the pipelined step reads the count from there
+      host_header->n_records = 0ull;
+      host_header->pad = 0ull;
+    }
   }
   if (k < n_off) unit_rec_off[k] = 0ull;
   if (k < n_items) item_dense[k] = 0;
@@ -841,10 +846,14 @@ __global__ void k_run_init(Header* __restrict__ header, unsigned long long* __re
 
 // after the scan: the total goes to the header and closes the per-unit offsets
 __global__ void k_scan_finish(const unsigned long long* __restrict__ total, Header* __restrict__ header,
-                              unsigned long long* __restrict__ unit_rec_off_end) {
+                              Header* __restrict__ host_header, unsigned long long* __restrict__ unit_rec_off_end) {
   if (threadIdx.x == 0) {
     header->n_records = *total;
     *unit_rec_off_end = *total;
+    if (host_header) {
+      host_header->n_records = *total;
+      __threadfence_system();
+    }
   }
 }
 
