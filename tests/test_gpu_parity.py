@@ -399,20 +399,6 @@ def test_pipelined_step_equals_one_submit(lg, gpu_ctx, n_chunks):
     b.close()
 
 
-def test_packed_two_plane_form_round_trips(lg):
-    """PlaneBatch.packed2(): 2 bits per (site, read) hold exactly the three planes."""
-    pb, _ = synth.make_heavy_tail(20261027, 40, s_max=120, r_max=900)
-    p2 = pb.packed2()
-    assert p2.size * 3 == pb.planes.size * 2
-    for k in range(pb.n_units):
-        S, W = int(pb.units['n_sites'][k]), int(pb.units['row_words'][k])
-        three = pb.planes[int(pb.units['plane_off'][k]):][:3 * S * W].reshape(S, 3, W)
-        two = p2[int(pb.units['plane_off'][k]) // 3 * 2:][:2 * S * W].reshape(S, 2, W)
-        assert np.array_equal(two[:, 0] & ~two[:, 1], three[:, 0])
-        assert np.array_equal(two[:, 1] & ~two[:, 0], three[:, 1])
-        assert np.array_equal(two[:, 0] | two[:, 1], three[:, 2])
-
-
 def test_pipeline_needs_back_to_back_units(lg, gpu_ctx):
     pb = synth.make_uniform_planes(3, 4, 5, 40, 0.5)
     bad = lg.PlaneBatch(pb.units[::-1].copy(), pb.planes, pb.site_flags)

@@ -70,3 +70,31 @@ def test_native_encoder_equals_python_encoder(lg, golden):
         assert np.array_equal(got.planes, want.planes)
         assert np.array_equal(got.site_flags, want.site_flags)
         assert got.bad_sites[0] == eu.bad_sites and got.positions[0] == eu.positions and got.types[0] == eu.types
+
+
+synth = importlib.import_module("l-giremi_b200.synth")
+
+
+def test_packed_two_plane_form_round_trips(lg):
+    """PlaneBatch.packed2(): 2 bits per (site, read) hold exactly the three planes."""
+    pb, _ = synth.make_heavy_tail(20261027, 40, s_max=120, r_max=900)
+    p2 = pb.packed2()
+    assert p2.size * 3 == pb.planes.size * 2
+    for k in range(pb.n_units):
+        S, W = int(pb.units['n_sites'][k]), int(pb.units['row_words'][k])
+        three = pb.planes[int(pb.units['plane_off'][k]):][:3 * S * W].reshape(S, 3, W)
+        two = p2[int(pb.units['plane_off'][k]) // 3 * 2:][:2 * S * W].reshape(S, 2, W)
+        assert np.array_equal(two[:, 0] & ~two[:, 1], three[:, 0])
+        assert np.array_equal(two[:, 1] & ~two[:, 0], three[:, 1])
+        assert np.array_equal(two[:, 0] | two[:, 1], three[:, 2])
+
+
+def test_concat_plane_batches_equals_pack_units(lg):
+    rng = np.random.default_rng(9)
+    ms = [random_mismatches(rng) for _ in range(12)] + [{}]
+    parts = [enc.encode_mismatches_native(m) for m in ms]
+    got = enc.concat_plane_batches(parts)
+    want = enc.pack_units([enc.encode_mismatches(m) for m in ms])
+    assert got.units.tolist() == want.units.tolist()
+    assert np.array_equal(got.planes, want.planes) and np.array_equal(got.site_flags, want.site_flags)
+    assert got.positions == want.positions and got.types == want.types
