@@ -42,6 +42,11 @@ assert np.array_equal(out[False].records, out[True].records) and np.array_equal(
 ctx.set_small_path(False)
 ctx.set_dense_threshold(2, 1)                     # everything with a pair through k_expand_planes + k_gram_i8
 d = lg.mi_step_batched(pb, 6, mode, ctx=ctx, n_chunks=1)
+assert d.n_dense_units >= 10
+p = lg.Pipeline(ctx, pb, 3)                       # ... also inside the groups of a pipelined step, packed input
+r = p.step(6, mode | lg.MODE_SPLIT_RECORDS, packed=True)
+assert r.n_dense_units == d.n_dense_units and np.array_equal(r.records, d.records) and np.array_equal(r.counts, d.counts)
+p.close()
 ctx.set_dense_threshold(*lg.DENSE_DEFAULT)
 assert np.array_equal(d.records, out[False].records) and np.array_equal(d.counts, out[False].counts)
 for chunks in (2, 5, 40):
