@@ -78,8 +78,7 @@ struct lgmi_batch {
   FastItem* d_fast_items = nullptr;
   uint8_t* d_item_dense = nullptr;
   uint32_t* d_n_generic = nullptr;
-  MeanItem* d_mean_items = nullptr;     // 32-site blocks of the units below kMeanWideMinSites sites, then 8-site
-  uint32_t n_mean_wide = 0;             // blocks of the wider units (k_site_mean_wide)
+  MeanItem* d_mean_items = nullptr;     // 32-site blocks of the multi-item units
   uint32_t* d_planes = nullptr;
   uint8_t* d_flags = nullptr;
   unsigned long long* d_item_cnt = nullptr;  // n_items + 1 (last stays 0)
@@ -372,7 +371,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   std::vector<DevUnit> du(n_units);
   std::vector<FastItem> fast_items, pre_items;
   uint64_t val_slots = 0;
-  std::vector<MeanItem> mean_items, mean_items_wide;
+  std::vector<MeanItem> mean_items;
   std::vector<DenseTile> dense_tiles;
   std::vector<TileItem> tile_items;
   std::vector<uint32_t> tile_words;  // W of each tile's unit (launch order: longest first)
@@ -452,10 +451,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
     if (nit > 1) {
       d.dense_off = dense;
       dense += np;
-      if (u.n_sites >= kMeanWideMinSites)
-        for (uint32_t s0 = 0; s0 < u.n_sites; s0 += (uint32_t)kMeanWideSites) mean_items_wide.push_back(MeanItem{k, s0});
-      else
-        for (uint32_t s0 = 0; s0 < u.n_sites; s0 += (uint32_t)kMeanSites) mean_items.push_back(MeanItem{k, s0});
+      for (uint32_t s0 = 0; s0 < u.n_sites; s0 += (uint32_t)kMeanSites) mean_items.push_back(MeanItem{k, s0});
     }
     for (uint32_t t = 0; t < nit; ++t) {
       Item it;
@@ -502,8 +498,6 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   b->n_fast = (uint32_t)fast_items.size();
   b->n_pre = (uint32_t)pre_items.size();
   b->n_mean_items = (uint32_t)mean_items.size();
-  b->n_mean_wide = (uint32_t)mean_items_wide.size();
-  mean_items.insert(mean_items.end(), mean_items_wide.begin(), mean_items_wide.end());
   b->n_dense = dense;
 
 #define BCU(call)                                                                    \
@@ -799,11 +793,6 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   if (b->n_mean_items) {
     k_site_mean_dense<<<b->n_mean_items, kMeanThreads, 0, bstream(b)>>>(b->d_units, b->d_mean_items, b->d_flags, b->d_dense,
                                                                        b->d_site_mean, b->d_site_cnt);
-    ++ctx->launches;
-  }
-  if (b->n_mean_wide) {
-    k_site_mean_wide<<<b->n_mean_wide, kMeanWideSites * 32, 0, bstream(b)>>>(
-        b->d_units, b->d_mean_items + b->n_mean_items, b->d_flags, b->d_dense, b->d_site_mean, b->d_site_cnt);
     ++ctx->launches;
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[1], bstream(b)));

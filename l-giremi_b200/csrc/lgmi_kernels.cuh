@@ -657,26 +657,32 @@ __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
 // Per-site mean for units whose pairs span several work items; reads the dense per-unit MI
 // scratch (pair order = upper triangle of the symmetric site x site matrix).  One CTA per 32
 // consecutive sites: 32 x 32 tiles of the matrix are staged in shared memory with coalesced
-// loads -- partners below the site block come from the partners' rows, partners above from the
-// sites' rows, stored transposed -- double-buffered, and warp 0 runs the 32 compensated sums
+// cp.async loads -- partners below the site block come from the partners' rows, partners above from
+// the sites' rows, stored transposed -- four tiles in flight, and warp 0 runs the 32 compensated sums
 // side by side, one site per lane, partners ascending.  The order of the additions is part of
 // the result (mutual_information.py:56-58 is a left-to-right float sum), so each site's sum is
 // serial; the 32 sites of a block are not.
 constexpr int kMeanSites = 32;    // sites per CTA (= lanes of the consuming warp)
-constexpr int kMeanThreads = 128;
-constexpr uint32_t kMeanWideMinSites = 512;  // from here on the warp-per-site form (k_site_mean_wide) is used
+constexpr int kMeanThreads = 256;
+constexpr int kMeanBufs = 4;      // tiles in flight
 struct MeanItem {
   uint32_t unit;
   uint32_t site_begin;
 };
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, bool copy) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = copy ? 8 : 0;  // src-size 0: the 8 destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmem_src), "r"(n) : "memory");
+}
+
 __global__ void __launch_bounds__(kMeanThreads) k_site_mean_dense(const DevUnit* __restrict__ units,
                                                                  const MeanItem* __restrict__ items,
                                                                  const uint8_t* __restrict__ site_flags,
                                                                  const double* __restrict__ dense,
                                                                  double* __restrict__ site_mean,
                                                                  uint32_t* __restrict__ site_cnt) {
-  __shared__ double s_tile[2][32][33];  // [buffer][partner][site]; NaN: no MI / not a pair
-  __shared__ uint8_t s_phet[2][32];     // partner is a het_snp
+  __shared__ double s_tile[kMeanBufs][32][33];  // [buffer][partner][site]
+  __shared__ uint32_t s_phet[kMeanBufs];        // bit tl: partner t0 + tl is a het_snp
   const MeanItem mi = items[blockIdx.x];
   const DevUnit u = units[mi.unit];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -685,102 +691,70 @@ __global__ void __launch_bounds__(kMeanThreads) k_site_mean_dense(const DevUnit*
   const double* __restrict__ d = dense + u.dense_off;
   const uint32_t n_blocks = (S + 31u) >> 5;
 
-  auto load_tile = [&](uint32_t b, uint32_t tb) {  // partners t0 .. t0 + 31 against sites s0 .. s0 + 31
-    const uint32_t t0 = tb << 5;
-    for (uint32_t e = tid; e < 1024u; e += kMeanThreads) {
-      // below the diagonal block the fast index runs over the sites (row of the partner), above it over
-      // the partners (row of the site); inside it either way
-      const uint32_t hi = e >> 5, lo = e & 31u;
-      const uint32_t tl = (t0 < s0) ? hi : lo, sl = (t0 < s0) ? lo : hi;
-      const uint32_t t = t0 + tl, s = s0 + sl;
-      double v = lg_nan();
-      if (t < S && s < S && t != s)
-        v = d[(t < s) ? lg_row_off(t, S) + (s - t - 1u) : lg_row_off(s, S) + (t - s - 1u)];
-      s_tile[b][tl][sl] = v;
+  // a tile by cp.async (nobody waits on its own loads): partners t0 .. t0 + 31 against sites s0 .. s0 + 31
+  auto request_tile = [&](uint32_t tb) {
+    if (tb < n_blocks) {
+      const uint32_t t0 = tb << 5, b = tb % kMeanBufs;
+      for (uint32_t e = tid; e < 1024u; e += kMeanThreads) {
+        // below the diagonal block the fast index runs over the sites (row of the partner), above it over
+        // the partners (row of the site); inside it either way
+        const uint32_t hi = e >> 5, lo = e & 31u;
+        const uint32_t tl = (t0 < s0) ? hi : lo, sl = (t0 < s0) ? lo : hi;
+        const uint32_t t = t0 + tl, s = s0 + sl;
+        const bool ok = t < S && s < S && t != s;
+        const uint64_t idx = ok ? ((t < s) ? lg_row_off(t, S) + (s - t - 1u) : lg_row_off(s, S) + (t - s - 1u)) : 0ull;
+        cp_async8(&s_tile[b][tl][sl], d + idx, ok);
+      }
+      if (warp == 1u) {
+        const uint32_t t = t0 + lane;
+        const uint32_t m = __ballot_sync(0xffffffffu, t < S && (flags[t < S ? t : 0u] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+        if (lane == 0) s_phet[b] = m;
+      }
     }
-    if (tid < 32u) s_phet[b][tid] = (t0 + tid < S) && (flags[t0 + tid] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
+    cp_async_commit();  // (an empty group keeps the count of groups per tile at one)
   };
 
   const uint32_t s = s0 + lane;
   const bool s_ok = s < S;
   const bool s_het = s_ok && (flags[s_ok ? s : 0u] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
-  lg_neumaier acc;
-  lg_neumaier_init(acc);
-  load_tile(0, 0);
-  __syncthreads();
+  // all MI values are >= +0.0: CPython's compensated sum (mutual_information.py:56-58) without branches;
+  // an absent value adds +0.0, which leaves sum and compensation as they are
+  double acc_s = 0.0, acc_c = 0.0;
+  uint32_t acc_n = 0;
+#pragma unroll
+  for (uint32_t tb = 0; tb + 1u < (uint32_t)kMeanBufs; ++tb) request_tile(tb);
   for (uint32_t tb = 0; tb < n_blocks; ++tb) {
-    const uint32_t b = tb & 1u;
-    if (warp == 0) {  // consume this tile: one site per lane, partners ascending
-      if (s_ok) {
-        for (uint32_t tl = 0; tl < 32u; ++tl) {
-          const double v = s_tile[b][tl][lane];
-          if (!isnan(v) && (s_het || s_phet[b][tl])) lg_neumaier_add(acc, v);
-        }
-      }
-    } else if (tb + 1u < n_blocks) {  // the other warps fetch the next tile meanwhile
-      const uint32_t t0 = (tb + 1u) << 5;
-      for (uint32_t e = tid - 32u; e < 1024u; e += kMeanThreads - 32u) {
-        const uint32_t hi = e >> 5, lo = e & 31u;
-        const uint32_t tl = (t0 < s0) ? hi : lo, sl = (t0 < s0) ? lo : hi;
-        const uint32_t t = t0 + tl, ss = s0 + sl;
-        double v = lg_nan();
-        if (t < S && ss < S && t != ss)
-          v = d[(t < ss) ? lg_row_off(t, S) + (ss - t - 1u) : lg_row_off(ss, S) + (t - ss - 1u)];
-        s_tile[b ^ 1u][tl][sl] = v;
-      }
-      if (tid >= 32u && tid < 64u) {
-        const uint32_t t = t0 + (tid - 32u);
-        s_phet[b ^ 1u][tid - 32u] = (t < S) && (flags[t < S ? t : 0u] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
-      }
-    }
+    request_tile(tb + kMeanBufs - 1u);   // into the buffer everybody left at the end of the previous iteration
+    cp_async_wait<kMeanBufs - 1>();      // tile tb has landed (this thread's part; the barrier covers the rest)
     __syncthreads();
-  }
-  if (warp == 0 && s_ok) {
-    site_mean[u.site_off + s] = lg_neumaier_mean(acc);
-    site_cnt[u.site_off + s] = (uint32_t)acc.n;
-  }
-}
-
-
-// The same for units with many sites (few of them, long sums): one WARP per site, so that a
-// single deep unit still fills the machine: the lanes
-// fetch 32 partners' MI at a time (coalesced for partners above the site), then
-// the compensated sum runs over them in partner order -- the order is part of
-// the result (mutual_information.py:56-58 is a left-to-right float sum), so the
-// additions stay serial while the loads do not.
-constexpr int kMeanWideSites = 8;  // sites (= warps) per CTA of the warp-per-site form
-__global__ void __launch_bounds__(kMeanWideSites * 32) k_site_mean_wide(const DevUnit* __restrict__ units,
-                                                                    const MeanItem* __restrict__ items,
-                                                                    const uint8_t* __restrict__ site_flags,
-                                                                    const double* __restrict__ dense,
-                                                                    double* __restrict__ site_mean,
-                                                                    uint32_t* __restrict__ site_cnt) {
-  const MeanItem mi = items[blockIdx.x];
-  const DevUnit u = units[mi.unit];
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t s = mi.site_begin + (threadIdx.x >> 5);
-  if (s >= u.S) return;
-  const uint8_t* __restrict__ flags = site_flags + u.site_off;
-  const double* __restrict__ d = dense + u.dense_off;
-  const bool s_het = (flags[s] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
-  const uint64_t row_s = lg_row_off(s, u.S);
-  lg_neumaier acc;
-  lg_neumaier_init(acc);
-  for (uint32_t t0 = 0; t0 < u.S; t0 += 32u) {
-    const uint32_t t = t0 + lane;
-    double v = lg_nan();
-    if (t < u.S && t != s && (s_het || (flags[t] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP))
-      v = d[(t < s) ? lg_row_off(t, u.S) + (s - t - 1u) : row_s + (t - s - 1u)];
-    uint32_t have = __ballot_sync(0xffffffffu, !isnan(v));
-    while (have) {  // ascending partner order; every lane carries the same accumulator
-      const int k = __ffs((int)have) - 1;
-      have &= have - 1u;
-      lg_neumaier_add(acc, __shfl_sync(0xffffffffu, v, k));
+    if (warp == 0 && s_ok) {             // one site per lane, partners ascending
+      const uint32_t b = tb % kMeanBufs, t0 = tb << 5;
+      const uint32_t partners = s_het ? 0xffffffffu : s_phet[b];  // a non-het site sums over its het partners only
+#pragma unroll 4
+      for (uint32_t tl = 0; tl < 32u; ++tl) {
+        const uint32_t t = t0 + tl;
+        const double v = s_tile[b][tl][lane];
+        const bool have = t < S && t != s && ((partners >> tl) & 1u) && __double2hiint(v) < 0x7ff00000;  // NaN: no MI
+        const double x = have ? v : 0.0;
+        const double tt = __dadd_rn(acc_s, x);
+        const double big = (acc_s >= x) ? acc_s : x, small = (acc_s >= x) ? x : acc_s;
+        acc_c = __dadd_rn(acc_c, __dadd_rn(__dsub_rn(big, tt), small));
+        acc_s = tt;
+        acc_n += have ? 1u : 0u;
+      }
     }
+    __syncthreads();  // tile tb consumed: its buffer is the target of the next request
   }
-  if (lane == 0) {
-    site_mean[u.site_off + s] = lg_neumaier_mean(acc);
-    site_cnt[u.site_off + s] = (uint32_t)acc.n;
+  cp_async_wait<0>();
+  if (warp == 0 && s_ok) {
+    double mean = lg_nan();
+    if (acc_n) {
+      double tot = acc_s;
+      if (acc_c != 0.0) tot = __dadd_rn(tot, acc_c);
+      mean = __ddiv_rn(tot, (double)acc_n);
+    }
+    site_mean[u.site_off + s] = mean;
+    site_cnt[u.site_off + s] = acc_n;
   }
 }
 
