@@ -58,7 +58,8 @@ struct lgmi_ctx {
 // one unit of the tensor-core path
 struct DensePlan {
   uint32_t unit = 0, S = 0, W = 0, S_pad = 0, k_blocks = 0, n_tiles = 0;
-  uint64_t plane_off = 0, gram_off = 0, tile_off = 0;
+  uint32_t n_whole = 0;  // the first n_whole work items are whole tiles; the rest share tiles (last wave, split in K)
+  uint64_t plane_off = 0, gram_off = 0, tile_off = 0, macs = 0;
   CUtensorMap tmap;
 };
 
@@ -425,10 +426,35 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
               const uint32_t i_min = I * (uint32_t)kDenseBM;
               const uint32_t j_max = std::min(J * (uint32_t)kDenseBN + (uint32_t)kDenseBN, pl.S) - 1u;
               if (J * (uint32_t)kDenseBN >= pl.S || i_min >= j_max) continue;
-              dense_tiles.push_back(DenseTile{(uint16_t)a, (uint16_t)bb, (uint16_t)I, (uint16_t)J});
+              dense_tiles.push_back(DenseTile{(uint16_t)a, (uint16_t)bb, (uint16_t)I, (uint16_t)J, 0, (uint16_t)pl.k_blocks, 0, 0});
             }
+      {
+        // one CTA per SM walks the list with stride #SMs: a last, partly filled wave leaves SMs idle for a whole
+        // tile time, so its tiles are cut along K into as many parts as fill it (added atomically into zeroed tiles)
+        const uint32_t n = (uint32_t)(dense_tiles.size() - pl.tile_off), grid = (uint32_t)ctx->num_sms;
+        const uint32_t rem = n % grid;
+        uint32_t parts = rem ? std::min<uint32_t>(8u, grid / rem) : 1u;
+        while (parts > 1u && pl.k_blocks < 8u * parts) --parts;  // at least 8 k-blocks (1 024 reads) per part
+        pl.n_whole = n;
+        if (parts >= 2u) {
+          pl.n_whole = n - rem;
+          std::vector<DenseTile> tail(dense_tiles.end() - rem, dense_tiles.end());
+          dense_tiles.resize(dense_tiles.size() - rem);
+          for (uint32_t q = 0; q < parts; ++q)
+            for (DenseTile t : tail) {
+              t.kb0 = (uint16_t)((uint64_t)pl.k_blocks * q / parts);
+              t.kb1 = (uint16_t)((uint64_t)pl.k_blocks * (q + 1) / parts);
+              t.partial = 1;
+              dense_tiles.push_back(t);
+            }
+        }
+      }
       pl.n_tiles = (uint32_t)(dense_tiles.size() - pl.tile_off);
-      b->dense_macs += (uint64_t)pl.n_tiles * kDenseBM * kDenseBN * pl.k_blocks * kDenseBK;
+      for (uint32_t t = 0; t < pl.n_tiles; ++t) {
+        const DenseTile& dt = dense_tiles[pl.tile_off + t];
+        pl.macs += (uint64_t)kDenseBM * kDenseBN * (dt.kb1 - dt.kb0) * kDenseBK;
+      }
+      b->dense_macs += pl.macs;
       gram_words += 9ull * pl.S_pad * pl.S_pad;
       x_bytes = std::max<uint64_t>(x_bytes, 3ull * pl.S_pad * pl.k_blocks * kDenseBK);
       d.gram_off = pl.gram_off;
@@ -680,6 +706,11 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     D.gram = b->d_gram + pl.gram_off;
     D.error = reinterpret_cast<uint32_t*>(&b->d_header->pad);
     const unsigned ggrid = (unsigned)std::min<uint32_t>(pl.n_tiles, (uint32_t)ctx->num_sms);
+    if (pl.n_tiles > pl.n_whole) {
+      k_zero_partial_tiles<<<pl.n_tiles - pl.n_whole, 256, 0, bstream(b)>>>(D.tiles + pl.n_whole, pl.n_tiles - pl.n_whole,
+                                                                            pl.S_pad, D.gram);
+      ++ctx->launches;
+    }
     const bool last = &pl == &b->dense_plans.back();
     if (last && timing) CU(ctx, cudaEventRecord(b->ev[6], bstream(b)));
     k_gram_i8<<<ggrid, kDenseThreads, kDenseSmemBytes, bstream(b)>>>(pl.tmap, D);
@@ -824,7 +855,7 @@ static int fill_scalars(lgmi_batch* b, lgmi_result* out) {
     CU(ctx, cudaEventElapsedTime(&ms, b->ev[6], b->ev[7]));
     out->gram_kernel_ms = ms;
     const DensePlan& pl = b->dense_plans.back();
-    out->gram_macs = (uint64_t)pl.n_tiles * kDenseBM * kDenseBN * pl.k_blocks * kDenseBK;
+    out->gram_macs = pl.macs;
   }
   out->n_dense_units = (uint32_t)b->dense_plans.size();
   out->dense_macs = b->dense_macs;

@@ -38,8 +38,11 @@ constexpr uint32_t kDenseSmemBytes = kDenseStages * kDenseStageBytes + 1024 /*al
 constexpr uint32_t kDenseTmemCols = 256;
 
 struct DenseTile {
-  uint16_t a, b;  // planes (label order: 0 other, 1 minor, 2 major)
-  uint16_t I, J;  // site blocks: rows [128 I, +128), columns [256 J, +256)
+  uint16_t a, b;      // planes (label order: 0 other, 1 minor, 2 major)
+  uint16_t I, J;      // site blocks: rows [128 I, +128), columns [256 J, +256)
+  uint16_t kb0, kb1;  // k-blocks [kb0, kb1) of this work item
+  uint16_t partial;   // 1: the tile's K range is shared by several items (last wave): results are added atomically
+  uint16_t pad;       //    into a zeroed tile
 };
 
 struct DenseParams {
@@ -164,6 +167,19 @@ __device__ __forceinline__ void tmem_load_32x32(uint32_t taddr, uint32_t (&r)[32
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// zero the 128 x 256 output tiles that several work items add into (one CTA per listed item; an item whose
+// kb0 is 0 zeroes its tile, the others skip)
+__global__ void __launch_bounds__(256) k_zero_partial_tiles(const DenseTile* __restrict__ tiles, uint32_t n_tiles,
+                                                            uint32_t S_pad, uint32_t* __restrict__ gram) {
+  const DenseTile tile = tiles[blockIdx.x];
+  if (blockIdx.x >= n_tiles || !tile.partial || tile.kb0 != 0) return;
+  uint32_t* base = gram + ((size_t)(tile.a * 3u + tile.b) * S_pad + (size_t)tile.I * kDenseBM) * S_pad + (size_t)tile.J * kDenseBN;
+  for (uint32_t e = threadIdx.x; e < (uint32_t)kDenseBM * (kDenseBN / 4); e += blockDim.x) {
+    const uint32_t row = e / (kDenseBN / 4), q = e % (kDenseBN / 4);
+    reinterpret_cast<uint4*>(base + (size_t)row * S_pad)[q] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // ------------------------------------------------------------------ the GEMM
 __global__ void __launch_bounds__(kDenseThreads, 1) k_gram_i8(const __grid_constant__ CUtensorMap tmap,
                                                               const DenseParams P) {
@@ -207,7 +223,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_gram_i8(const __grid_const
         const DenseTile tile = P.tiles[t];
         const int32_t row_a = (int32_t)(tile.a * P.S_pad + tile.I * kDenseBM);
         const int32_t row_b = (int32_t)(tile.b * P.S_pad + tile.J * kDenseBN);
-        for (uint32_t kb = 0; kb < P.k_blocks; ++kb) {
+        for (uint32_t kb = tile.kb0; kb < tile.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u, P.error);
           uint8_t* sa = smem + stage * kDenseStageBytes;
           uint8_t* sb = sa + kDenseBM * kDenseBK;
@@ -228,9 +244,10 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_gram_i8(const __grid_const
       const uint32_t idesc = umma_idesc_u8(kDenseBM, kDenseBN);
       uint32_t stage = 0, phase = 0, acc_phase = 0;
       for (uint32_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
+        const DenseTile tile = P.tiles[t];
         mbar_wait(acc_empty, acc_phase ^ 1u, P.error);  // epilogue has drained the accumulator
         tc_fence_after();
-        for (uint32_t kb = 0; kb < P.k_blocks; ++kb) {
+        for (uint32_t kb = tile.kb0; kb < tile.kb1; ++kb) {
           mbar_wait(&full[stage], phase, P.error);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kDenseStageBytes);
@@ -238,7 +255,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_gram_i8(const __grid_const
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
 #pragma unroll
           for (uint32_t k = 0; k < kDenseBK / 32; ++k)  // K = 32 bytes per instruction: +32 B on both operands
-            umma_i8(tmem_base, da + 2ull * k, db + 2ull * k, idesc, (kb | k) != 0u);
+            umma_i8(tmem_base, da + 2ull * k, db + 2ull * k, idesc, ((kb - tile.kb0) | k) != 0u);
           umma_commit(&empty[stage]);  // smem slot free once these MMAs have read it
           if (++stage == kDenseStages) {
             stage = 0;
@@ -262,9 +279,14 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_gram_i8(const __grid_const
       for (uint32_t c = 0; c < kDenseBN / 32; ++c) {
         uint32_t r[32];
         tmem_load_32x32(tmem_base + ((q * 32u) << 16) + c * 32u, r);
+        if (tile.partial) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v)
-          reinterpret_cast<uint4*>(out + c * 32u)[v] = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+          for (int v = 0; v < 32; ++v) atomicAdd(out + c * 32u + v, r[v]);  // (RED: no return value is used)
+        } else {
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            reinterpret_cast<uint4*>(out + c * 32u)[v] = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+        }
       }
       tc_fence_before();
       mbar_arrive(acc_empty);
