@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblgmi.so")
+# LGMI_LIB: another build of the same library (kernel experiments: tools/build_variant.py); default in-tree
+LIB_PATH = os.environ.get("LGMI_LIB") or os.path.join(HERE, "liblgmi.so")
 
 # numpy mirrors of the ABI structs
 UNIT_DESC = np.dtype([("plane_off", "<u8"), ("n_sites", "<u4"), ("n_reads", "<u4"),

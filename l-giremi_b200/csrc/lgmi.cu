@@ -298,6 +298,18 @@ extern "C" int lgmi_pinned_free(lgmi_t* ctx, void* ptr) {
 
 extern "C" uint64_t lgmi_launch_count(const lgmi_t* ctx) { return ctx ? ctx->launches : 0; }
 
+#ifdef LGMI_PHASE_CLOCKS
+// debug build only (tools/phase_clocks.py): read (and optionally clear) k_pairs_fast's per-barrier cycle sums
+extern "C" __attribute__((visibility("default"))) int lgmi_debug_phase_clocks(unsigned long long* out, int reset) {
+  if (out && cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(g_phase_clk)) != cudaSuccess) return LGMI_ERR_CUDA;
+  if (reset) {
+    static unsigned long long zero[8][kFastWarps][2];
+    if (cudaMemcpyToSymbol(g_phase_clk, zero, sizeof(zero)) != cudaSuccess) return LGMI_ERR_CUDA;
+  }
+  return LGMI_OK;
+}
+#endif
+
 extern "C" int lgmi_set_small_path(lgmi_t* ctx, int tensor_cores) {
   if (!ctx) return LGMI_ERR_ARG;
   ctx->small_path = tensor_cores ? 1 : 0;

@@ -368,10 +368,37 @@ __device__ __forceinline__ void fast_means(const FastParams& P, SM& sm, const un
   P.site_cnt[it.site_off + s] = acc.n;
 }
 
+// Debug build only (-DLGMI_PHASE_CLOCKS, tools/phase_clocks.py): lane 0 of every warp accumulates, per
+// barrier of the unit loop, the cycles it worked before arriving and the cycles it then waited.
+#ifdef LGMI_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[8][kFastWarps][2];
+__device__ __forceinline__ long long phase_clock() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");  // "memory": stays on its side of the barrier
+  return t;
+}
+#define LG_PHASE_DECL long long ph_t = phase_clock();
+#define LG_PHASE_SYNC(k, stmt)                                                            \
+  {                                                                                       \
+    const long long ph_a = phase_clock();                                                 \
+    stmt;                                                                                 \
+    const long long ph_r = phase_clock();                                                 \
+    if ((threadIdx.x & 31u) == 0u) {                                                      \
+      atomicAdd(&g_phase_clk[k][threadIdx.x >> 5][0], (unsigned long long)(ph_a - ph_t)); \
+      atomicAdd(&g_phase_clk[k][threadIdx.x >> 5][1], (unsigned long long)(ph_r - ph_a)); \
+    }                                                                                     \
+    ph_t = ph_r;                                                                          \
+  }
+#else
+#define LG_PHASE_DECL
+#define LG_PHASE_SYNC(k, stmt) stmt;
+#endif
+
 __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x;
+  LG_PHASE_DECL
 
   // per-CTA table: ln k (hi, lo) and RN(1/k) for k <= 256
   for (uint32_t k = tid; k <= (uint32_t)kFastMaxR; k += kFastThreads) {
@@ -414,14 +441,15 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
       sm.n_oth_total = 0u;
     }
     cp_async_wait<1>();  // this item's rows have landed (the next item's may still be in flight)
-    __syncthreads();
+    LG_PHASE_SYNC(0, __syncthreads())
     fast_land(sm, rows, it, P.site_flags + it.site_off);
-    __syncthreads();
+    LG_PHASE_SYNC(1, __syncthreads())
     // a site with more than kOthCap "other" reads does not fit the sparse lists: the generic kernel takes the unit
     const bool over = tid < S && sm.n_oth[tid] > (uint32_t)kOthCap;
     fast_site_lists(sm, S);
     fast_other_cells(sm, rows, S);
-    const bool dense = __syncthreads_or(over) != 0;  // (also: sm.info is read by every thread of the counts phase)
+    bool dense;
+    LG_PHASE_SYNC(2, dense = __syncthreads_or(over) != 0)  // (also: sm.info is read by every thread of the counts phase)
     if (dense) {
       if (tid == 0) {
         P.item_dense[it.item] = 1;
@@ -433,21 +461,21 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
       else if (nw <= 4u) fast_counts<4>(P, sm, rows, ijt, n_pairs);
       else if (nw <= 7u) fast_counts<7>(P, sm, rows, ijt, n_pairs);
       else fast_counts<8>(P, sm, rows, ijt, n_pairs);
-      __syncthreads();
+      LG_PHASE_SYNC(3, __syncthreads())
       if (tid < 32u) fast_chunk_prefix(sm, n_chunks);
       if (P.mode & LGMI_MODE_EMIT_COUNTS) {
         __syncthreads();
         fast_emit_counts(P, sm, sm.val, base, n_chunks);
       }
       fast_mi(sm, sm.val);
-      __syncthreads();
+      LG_PHASE_SYNC(4, __syncthreads())
       if (tid == 0) P.unit_rec_off[it.unit] = base;
       // the serial per-site sums occupy the first one or two warps; the others write the records
       const uint32_t mean_warps = (S + 31u) >> 5;
       if ((tid >> 5) < mean_warps) fast_means(P, sm, sm.val, it);
       else fast_emit(P, sm, sm.val, it, ijt, base, n_chunks, mean_warps);
     }
-    __syncthreads();  // everything of this item consumed before its buffers are reused
+    LG_PHASE_SYNC(5, __syncthreads())  // everything of this item consumed before its buffers are reused
     it = it_next;
     idx = idx_next;
     buf ^= 1u;
