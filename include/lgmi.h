@@ -131,6 +131,8 @@ typedef struct {
                                 /* exactly the reference's row order           */
   const uint32_t* counts;       /* 9 per record [a*3+b], a,b in {0 other,      */
                                 /* 1 minor, 2 major}; NULL unless EMIT_COUNTS  */
+                                /* (records / counts may also be NULL when     */
+                                /* n_records == 0: nothing was allocated)      */
   uint64_t n_sites;             /* length of the two per-site arrays           */
   const double* site_mean;      /* mean MI over het-kept pairs, NaN if none    */
                                 /* (mutual_information.py:48-60,               */

@@ -156,6 +156,8 @@ class StepResult:
 
     def unit_counts(self, unit):
         a, b = int(self.unit_rec_off[unit]), int(self.unit_rec_off[unit + 1])
+        if self.counts is None and self.n_records == 0:      # nothing survived: the library returns no table buffer
+            return np.zeros((0, 9), dtype=np.uint32)
         return self.counts[a:b]
 
 

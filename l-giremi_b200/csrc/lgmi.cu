@@ -77,6 +77,7 @@ struct lgmi_batch {
   DevUnit* d_units = nullptr;
   Item* d_items = nullptr;
   FastItem* d_fast_items = nullptr;
+  uint8_t* d_fast_empty = nullptr;           // per fast item: the pre-pass counted no emitted pair
   uint8_t* d_item_dense = nullptr;
   uint32_t* d_n_generic = nullptr;
   MeanItem* d_mean_items = nullptr;     // 32-site blocks of the multi-item units
@@ -337,6 +338,7 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   cudaFree(b->d_units);
   cudaFree(b->d_items);
   cudaFree(b->d_fast_items);
+  cudaFree(b->d_fast_empty);
   cudaFree(b->d_item_dense);
   cudaFree(b->d_n_generic);
   cudaFree(b->d_mean_items);
@@ -553,6 +555,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   BCU(cudaMalloc(&b->d_units, std::max<size_t>(1, n_units) * sizeof(DevUnit)));
   BCU(cudaMalloc(&b->d_items, std::max<size_t>(1, b->n_items) * sizeof(Item)));
   BCU(cudaMalloc(&b->d_fast_items, std::max<size_t>(1, fast_items.size()) * sizeof(FastItem)));
+  BCU(cudaMalloc(&b->d_fast_empty, std::max<size_t>(1, fast_items.size())));
   BCU(cudaMalloc(&b->d_item_dense, std::max<size_t>(1, b->n_items)));
   BCU(cudaMalloc(&b->d_n_generic, sizeof(uint32_t)));
   BCU(cudaMalloc(&b->d_mean_items, std::max<size_t>(1, mean_items.size()) * sizeof(MeanItem)));
@@ -765,6 +768,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     C.min_common = min_common;
     C.mode = mode;
     C.item_cnt = b->d_item_cnt;
+    C.fast_empty = b->d_fast_empty;
     const unsigned grid = (unsigned)std::min<uint64_t>(b->n_fast, (uint64_t)ctx->num_sms * 8u);
     k_count_fast<<<grid, kThreads, 0, bstream(b)>>>(C);
     ++ctx->launches;
@@ -796,6 +800,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     F.min_common = min_common;
     F.mode = mode;
     F.item_off = b->d_item_off;
+    F.fast_empty = b->d_fast_empty;
     F.item_dense = b->d_item_dense;
     F.n_generic = b->d_n_generic;
     F.records = b->d_records;

@@ -124,26 +124,34 @@ __device__ __forceinline__ uint32_t and_popc(const uint32_t* __restrict__ x, con
 constexpr unsigned long long kNoMi = 0x7ff8000000000000ull;
 
 // the four counts of a pair.  ri / rj point at landed rows: M at word 0, P at word 8.
+// |Pi&Pj| comes first: with the "other" cells it is the number of common reads, and a pair below
+// the min-common threshold (most pairs of sparsely covered units) skips the other three sets.
 template <int NW>
-__device__ __forceinline__ unsigned long long pair_counts(const uint32_t* __restrict__ ri,
-                                                          const uint32_t* __restrict__ rj) {
-  uint32_t Mi[8], Pi[8], Mj[8], Pj[8];
+__device__ __forceinline__ void load_row(uint32_t (&w)[8], const uint32_t* __restrict__ r) {
 #pragma unroll
   for (int k = 0; k < (NW + 3) / 4; ++k) {
-    const uint4 a = *reinterpret_cast<const uint4*>(ri + 4 * k);
-    const uint4 b = *reinterpret_cast<const uint4*>(ri + 8 + 4 * k);
-    const uint4 c = *reinterpret_cast<const uint4*>(rj + 4 * k);
-    const uint4 d = *reinterpret_cast<const uint4*>(rj + 8 + 4 * k);
-    Mi[4 * k] = a.x; Mi[4 * k + 1] = a.y; Mi[4 * k + 2] = a.z; Mi[4 * k + 3] = a.w;
-    Pi[4 * k] = b.x; Pi[4 * k + 1] = b.y; Pi[4 * k + 2] = b.z; Pi[4 * k + 3] = b.w;
-    Mj[4 * k] = c.x; Mj[4 * k + 1] = c.y; Mj[4 * k + 2] = c.z; Mj[4 * k + 3] = c.w;
-    Pj[4 * k] = d.x; Pj[4 * k + 1] = d.y; Pj[4 * k + 2] = d.z; Pj[4 * k + 3] = d.w;
+    const uint4 a = *reinterpret_cast<const uint4*>(r + 4 * k);
+    w[4 * k] = a.x; w[4 * k + 1] = a.y; w[4 * k + 2] = a.z; w[4 * k + 3] = a.w;
   }
+}
+
+// returns false (and leaves `packed` alone) when nPP + n_other < min_common
+template <int NW>
+__device__ __forceinline__ bool pair_counts(const uint32_t* __restrict__ ri, const uint32_t* __restrict__ rj,
+                                            uint32_t n_other, int min_common, unsigned long long& packed) {
+  uint32_t Pi[8], Pj[8];
+  load_row<NW>(Pi, ri + 8);
+  load_row<NW>(Pj, rj + 8);
   const uint32_t nPP = and_popc<NW>(Pi, Pj);
+  if ((int)(nPP + n_other) < min_common) return false;  // strict '<' drops (mutual_information.py:19)
+  uint32_t Mi[8], Mj[8];
+  load_row<NW>(Mi, ri);
+  load_row<NW>(Mj, rj);
   const uint32_t nMP = and_popc<NW>(Mi, Pj);
   const uint32_t nPM = and_popc<NW>(Pi, Mj);
   const uint32_t nMM = and_popc<NW>(Mi, Mj);
-  return (unsigned long long)(nPP | (nMP << 9) | (nPM << 18)) | ((unsigned long long)nMM << 27);
+  packed = (unsigned long long)(nPP | (nMP << 9) | (nPM << 18)) | ((unsigned long long)nMM << 27);
+  return true;
 }
 
 // ---------------------------------------------------------------------------

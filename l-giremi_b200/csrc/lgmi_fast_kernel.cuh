@@ -20,6 +20,7 @@ struct FastParams {
   int min_common;
   uint32_t mode;
   const unsigned long long* item_off;  // exclusive scan of the per-item emit counts
+  const uint8_t* fast_empty;           // per entry of `items`: nothing to emit (written by k_count_fast)
   uint8_t* item_dense;                 // 1: some site has more than kOthCap "other" reads -> generic kernel
   uint32_t* n_generic;                 // items the generic kernel has to take (incremented with item_dense)
   lgmi_pair_rec* records;
@@ -152,11 +153,11 @@ __device__ __forceinline__ void fast_counts(const FastParams& P, FastSmem& sm, c
       const bool het = ((fi | fj) & 1u) != 0u;
       unsigned long long v = kNoMi;
       if (het || !skip_nonhet) {
-        const unsigned long long cnt = pair_counts<NW>(rows + i * kRowStride, rows + j * kRowStride);
-        uint32_t n_common = (uint32_t)cnt & 511u;
         const uint32_t o = (sm.ocell[p >> 1] >> (16u * (p & 1u))) & 0x7fffu;
-        if (o) n_common += (o & 7u) + ((o >> 3) & 7u) + ((o >> 6) & 7u) + ((o >> 9) & 7u) + (o >> 12);
-        if ((int)n_common >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
+        uint32_t n_other = 0u;
+        if (o) n_other = (o & 7u) + ((o >> 3) & 7u) + ((o >> 6) & 7u) + ((o >> 9) & 7u) + (o >> 12);
+        unsigned long long cnt;
+        if (pair_counts<NW>(rows + i * kRowStride, rows + j * kRowStride, n_other, P.min_common, cnt)) {
           v = cnt | ((unsigned long long)o << 36);
           cls = o ? 3u : 2u;
           emit = het || !het_only;
@@ -334,6 +335,11 @@ __device__ __forceinline__ void fast_means(const FastParams& P, SM& sm, const un
                                            const FastItem& it) {
   const uint32_t tid = threadIdx.x, S = it.S;
   if (tid >= S) return;
+  if (sm.n_list2 + sm.n_list3 == 0u) {  // no pair of the unit reached min_common: nothing to average
+    P.site_mean[it.site_off + tid] = mi_nan();
+    P.site_cnt[it.site_off + tid] = 0u;
+    return;
+  }
   const uint32_t n_het = __popcll(sm.het_mask);
   const double* s_mi = reinterpret_cast<const double*>(val);
   MeanAcc acc{0.0, 0.0, 0u};
@@ -411,9 +417,11 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
   uint32_t idx = blockIdx.x;
   uint32_t buf = 0;
   FastItem it;
+  // an item the pre-pass counted no emitted pair for (no pair with enough common reads, or none next to a
+  // het SNP in HET_ONLY mode) has no rows and only NaN means: it is neither fetched nor processed
   if (idx < P.n_items) {
     it = P.items[idx];
-    fast_prefetch(sm.rows[0], it, P.planes);
+    if (!P.fast_empty[idx]) fast_prefetch(sm.rows[0], it, P.planes);
   }
   cp_async_commit();
 
@@ -422,60 +430,68 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
     const uint32_t idx_next = idx + gridDim.x;
     FastItem it_next;
     if (idx_next < P.n_items) {
+      const bool empty_next = P.fast_empty[idx_next] != 0;  // (independent of the descriptor load: no added latency)
       it_next = P.items[idx_next];
-      fast_prefetch(sm.rows[buf ^ 1u], it_next, P.planes);
+      if (!empty_next) fast_prefetch(sm.rows[buf ^ 1u], it_next, P.planes);
     }
     cp_async_commit();
-
     const uint32_t S = it.S;
-    const uint32_t n_pairs = S * (S - 1u) / 2u;
-    const uint32_t n_chunks = (n_pairs + 31u) >> 5;
     const unsigned long long base = P.item_off[it.item];
-    uint32_t* rows = sm.rows[buf];
-    const uint16_t* __restrict__ ijt = P.ij_tab + lg_ij_tab_off(S);
-    if (tid < (uint32_t)kFastMaxS) sm.n_oth[tid] = 0u;
-    for (uint32_t q = tid; q < (n_pairs + 1u) >> 1; q += kFastThreads) sm.ocell[q] = 0u;
-    if (tid == 0) {
-      sm.n_list2 = 0u;
-      sm.n_list3 = 0u;
-      sm.n_oth_total = 0u;
-    }
-    cp_async_wait<1>();  // this item's rows have landed (the next item's may still be in flight)
-    LG_PHASE_SYNC(0, __syncthreads())
-    fast_land(sm, rows, it, P.site_flags + it.site_off);
-    LG_PHASE_SYNC(1, __syncthreads())
-    // a site with more than kOthCap "other" reads does not fit the sparse lists: the generic kernel takes the unit
-    const bool over = tid < S && sm.n_oth[tid] > (uint32_t)kOthCap;
-    fast_site_lists(sm, S);
-    fast_other_cells(sm, rows, S);
-    bool dense;
-    LG_PHASE_SYNC(2, dense = __syncthreads_or(over) != 0)  // (also: sm.info is read by every thread of the counts phase)
-    if (dense) {
-      if (tid == 0) {
-        P.item_dense[it.item] = 1;
-        atomicAdd(P.n_generic, 1u);
+    if (P.fast_empty[idx]) {  // touches no shared memory: no barrier
+      if (tid < S) {
+        P.site_mean[it.site_off + tid] = mi_nan();
+        P.site_cnt[it.site_off + tid] = 0u;
       }
-    } else {
-      const uint32_t nw = ((uint32_t)it.R + 31u) >> 5;
-      if (nw <= 2u) fast_counts<2>(P, sm, rows, ijt, n_pairs);
-      else if (nw <= 4u) fast_counts<4>(P, sm, rows, ijt, n_pairs);
-      else if (nw <= 7u) fast_counts<7>(P, sm, rows, ijt, n_pairs);
-      else fast_counts<8>(P, sm, rows, ijt, n_pairs);
-      LG_PHASE_SYNC(3, __syncthreads())
-      if (tid < 32u) fast_chunk_prefix(sm, n_chunks);
-      if (P.mode & LGMI_MODE_EMIT_COUNTS) {
-        __syncthreads();
-        fast_emit_counts(P, sm, sm.val, base, n_chunks);
-      }
-      fast_mi(sm, sm.val);
-      LG_PHASE_SYNC(4, __syncthreads())
       if (tid == 0) P.unit_rec_off[it.unit] = base;
-      // the serial per-site sums occupy the first one or two warps; the others write the records
-      const uint32_t mean_warps = (S + 31u) >> 5;
-      if ((tid >> 5) < mean_warps) fast_means(P, sm, sm.val, it);
-      else fast_emit(P, sm, sm.val, it, ijt, base, n_chunks, mean_warps);
+    } else {
+      const uint32_t n_pairs = S * (S - 1u) / 2u;
+      const uint32_t n_chunks = (n_pairs + 31u) >> 5;
+      uint32_t* rows = sm.rows[buf];
+      const uint16_t* __restrict__ ijt = P.ij_tab + lg_ij_tab_off(S);
+      if (tid < (uint32_t)kFastMaxS) sm.n_oth[tid] = 0u;
+      for (uint32_t q = tid; q < (n_pairs + 1u) >> 1; q += kFastThreads) sm.ocell[q] = 0u;
+      if (tid == 0) {
+        sm.n_list2 = 0u;
+        sm.n_list3 = 0u;
+        sm.n_oth_total = 0u;
+      }
+      cp_async_wait<1>();  // this item's rows have landed (the next item's may still be in flight)
+      LG_PHASE_SYNC(0, __syncthreads())
+      fast_land(sm, rows, it, P.site_flags + it.site_off);
+      LG_PHASE_SYNC(1, __syncthreads())
+      // a site with more than kOthCap "other" reads does not fit the sparse lists: the generic kernel takes the unit
+      const bool over = tid < S && sm.n_oth[tid] > (uint32_t)kOthCap;
+      fast_site_lists(sm, S);
+      fast_other_cells(sm, rows, S);
+      bool dense;
+      LG_PHASE_SYNC(2, dense = __syncthreads_or(over) != 0)  // (also: sm.info is read by every thread of the counts phase)
+      if (dense) {
+        if (tid == 0) {
+          P.item_dense[it.item] = 1;
+          atomicAdd(P.n_generic, 1u);
+        }
+      } else {
+        const uint32_t nw = ((uint32_t)it.R + 31u) >> 5;
+        if (nw <= 2u) fast_counts<2>(P, sm, rows, ijt, n_pairs);
+        else if (nw <= 4u) fast_counts<4>(P, sm, rows, ijt, n_pairs);
+        else if (nw <= 7u) fast_counts<7>(P, sm, rows, ijt, n_pairs);
+        else fast_counts<8>(P, sm, rows, ijt, n_pairs);
+        LG_PHASE_SYNC(3, __syncthreads())
+        if (tid < 32u) fast_chunk_prefix(sm, n_chunks);
+        if (P.mode & LGMI_MODE_EMIT_COUNTS) {
+          __syncthreads();
+          fast_emit_counts(P, sm, sm.val, base, n_chunks);
+        }
+        fast_mi(sm, sm.val);
+        LG_PHASE_SYNC(4, __syncthreads())
+        if (tid == 0) P.unit_rec_off[it.unit] = base;
+        // the serial per-site sums occupy the first one or two warps; the others write the records
+        const uint32_t mean_warps = (S + 31u) >> 5;
+        if ((tid >> 5) < mean_warps) fast_means(P, sm, sm.val, it);
+        else fast_emit(P, sm, sm.val, it, ijt, base, n_chunks, mean_warps);
+      }
+      LG_PHASE_SYNC(5, __syncthreads())  // everything of this item consumed before its buffers are reused
     }
-    LG_PHASE_SYNC(5, __syncthreads())  // everything of this item consumed before its buffers are reused
     it = it_next;
     idx = idx_next;
     buf ^= 1u;

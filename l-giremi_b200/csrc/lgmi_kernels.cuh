@@ -504,6 +504,7 @@ struct CountFastParams {
   int min_common;
   uint32_t mode;
   unsigned long long* item_cnt;
+  uint8_t* fast_empty;  // per fast item (same index as `items`): 1 when the unit emits nothing -> k_pairs_fast skips it
 };
 
 template <int NW>
@@ -594,6 +595,7 @@ __global__ void __launch_bounds__(kThreads) k_count_fast(const CountFastParams P
 #pragma unroll
       for (int w = 0; w < kThreads / 32; ++w) tot += s_warp[w];
       P.item_cnt[it.item] = tot;
+      P.fast_empty[idx] = tot == 0u ? 1 : 0;
     }
     it = it_next;
     idx = idx_next;

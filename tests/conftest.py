@@ -139,7 +139,7 @@ def fast_host(liblgmi_path):
     lib.f_and_popc.restype = u32
     lib.f_and_popc.argtypes = [ctypes.c_int, vp, vp]
     lib.f_pair_counts.restype = ctypes.c_uint64
-    lib.f_pair_counts.argtypes = [ctypes.c_int, vp, vp]
+    lib.f_pair_counts.argtypes = [ctypes.c_int, vp, vp, ctypes.c_uint32, ctypes.c_int]
     return lib
 
 

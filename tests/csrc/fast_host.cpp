@@ -75,12 +75,16 @@ uint32_t f_and_popc(int nw, const uint32_t* x, const uint32_t* y) {
   }
 }
 double f_u32_to_double(uint32_t n) { return u32_to_double(n); }
-uint64_t f_pair_counts(int nw, const uint32_t* ri, const uint32_t* rj) {
+// packed counts of a pair, or ~0 when |Pi&Pj| + n_other < min_common (the early exit)
+uint64_t f_pair_counts(int nw, const uint32_t* ri, const uint32_t* rj, uint32_t n_other, int min_common) {
+  unsigned long long v = 0;
+  bool ok;
   switch (nw) {
-    case 2: return pair_counts<2>(ri, rj);
-    case 4: return pair_counts<4>(ri, rj);
-    case 7: return pair_counts<7>(ri, rj);
-    default: return pair_counts<8>(ri, rj);
+    case 2: ok = pair_counts<2>(ri, rj, n_other, min_common, v); break;
+    case 4: ok = pair_counts<4>(ri, rj, n_other, min_common, v); break;
+    case 7: ok = pair_counts<7>(ri, rj, n_other, min_common, v); break;
+    default: ok = pair_counts<8>(ri, rj, n_other, min_common, v); break;
   }
+  return ok ? (uint64_t)v : ~(uint64_t)0;
 }
 }

@@ -50,12 +50,18 @@ def test_pair_counts_packing(fast_host):
                 P[nw:] = 0
                 M[nw:] = 0
                 row[:8], row[8:16] = M, P
-            v = fast_host.f_pair_counts(nw, ri.ctypes.data, rj.ctypes.data)
+            v = fast_host.f_pair_counts(nw, ri.ctypes.data, rj.ctypes.data, 0, 0)
             pc = lambda a, b: int(sum(bin(int(x) & int(y)).count("1") for x, y in zip(a, b)))
             want = (pc(ri[8:16], rj[8:16]), pc(ri[:8], rj[8:16]), pc(ri[8:16], rj[:8]), pc(ri[:8], rj[:8]))
             got = (v & 511, (v >> 9) & 511, (v >> 18) & 511, (v >> 27) & 511)
             assert v >> 36 == 0
             assert got == want
+            # the min-common early exit: |Pi&Pj| + "other" reads against the threshold, strict '<'
+            none = (1 << 64) - 1
+            for n_other in (0, 3):
+                n = want[0] + n_other
+                assert fast_host.f_pair_counts(nw, ri.ctypes.data, rj.ctypes.data, n_other, n) == v
+                assert fast_host.f_pair_counts(nw, ri.ctypes.data, rj.ctypes.data, n_other, n + 1) == none
 
 
 def test_fast_2x2_same_bits_as_reference_arithmetic(fast_host, math_host, lntab):

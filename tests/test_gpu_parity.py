@@ -221,6 +221,20 @@ def test_heavy_tail_batch(lg, gpu_ctx):
     assert np.array_equal(again.records, full.records)
 
 
+@pytest.mark.parametrize("cov", [0.01, 0.05, 0.1, 0.25, 0.5])
+def test_cfg5_grid_against_oracle(lg, gpu_ctx, cov):
+    """BASELINE.json configs[4] at oracle size: the mi_min_common_read x coverage grid on 50-site x
+    200-read units -- from 'no pair has enough common reads' to 'every pair survives'."""
+    rng = np.random.default_rng(int(cov * 1000) + 11)
+    eus = [_synth_unit(rng, 50, 200, cov) for _ in range(12)]
+    survivors = []
+    for mc in (6, 10, 20, 50):
+        survivors.append(check_batch(lg, gpu_ctx, eus, mc).n_records)
+    assert survivors == sorted(survivors, reverse=True)      # a larger threshold never keeps more pairs
+    if cov <= 0.05:
+        assert survivors[-1] == 0                            # <= 10 covered reads per site: nothing reaches 50
+
+
 def test_deep_unit_large_counts(lg, gpu_ctx):
     """R = 30 000: counts beyond 2^14, ln table grown on demand."""
     rng = np.random.default_rng(5)

@@ -31,6 +31,10 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    # exactly ONE line on stdout: libraries that print banners to fd 1 (NCCL's version line) go to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--units", type=int, default=20000)
     ap.add_argument("--steps", type=int, default=10)
