@@ -23,6 +23,8 @@ Prints ONE JSON line (rank 0):
                 timed live with CUDA events on the launching stream
   cpu_baseline  the unmodified reference (baseline/_ref; the oracle's port if that is
                 absent) on the host cores over a bounded sample of the same units (N=1)
+  het_only      rank 0's device-resident step in HET_ONLY | SKIP_NONHET mode (only the pairs the
+                reference keeps are evaluated): reported separately, never in `value`
   dense         N=1 only: BASELINE.json configs[2], one unit of 2 000 sites x 100 000
                 reads through the int8 tcgen05 path, with a tensor roofline for k_gram_i8
 """
@@ -395,6 +397,29 @@ def run_gpu(args):
     dev_ms_max = float(t.item())
     value = pairs_per_step * world * args.steps / (dev_ms_max * 1e-3)
 
+    # ---- the same step restricted to what the reference keeps (reported separately) ----
+    # HET_ONLY | SKIP_NONHET: only pairs next to a het SNP are evaluated (mismatch.py:393-396 drops the
+    # others right after computing them); rows and per-site means are identical to the HET_ONLY output.
+    mode_het = lg.MODE_HET_ONLY | lg.MODE_SKIP_NONHET
+    for _ in range(3):
+        batch.run(mc, mode_het)
+    rh = batch.sync()
+    het_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        het_ev[k][0].record(stream)
+        batch.run(mc, mode_het)
+        het_ev[k][1].record(stream)
+        batch.sync()
+    het_ms = sum(a.elapsed_time(b) for a, b in het_ev) / args.steps
+    is_het = (pb.site_flags & 3) == lg.SITE_HET_SNP
+    n_het = np.add.reduceat(is_het.astype(np.int64), pb.units["site_off"].astype(np.int64))
+    n_s = pb.units["n_sites"].astype(np.int64)
+    het_pairs = int((n_s * (n_s - 1) // 2 - (n_s - n_het) * (n_s - n_het - 1) // 2).sum())
+    het_leg = {"mode": "HET_ONLY | SKIP_NONHET: only pairs next to a het SNP evaluated (same rows and means as HET_ONLY)",
+               "ms_per_step": het_ms, "evaluated_pairs_per_step": het_pairs, "rows_per_step": int(rh.n_records),
+               "candidate_pairs_per_s": pairs_per_step / (het_ms * 1e-3), "evaluated_pairs_per_s": het_pairs / (het_ms * 1e-3)}
+
     # ---- end to end through the C ABI with host buffers ----------------------------------------
     # lgmi_pipeline_step: pinned host planes in, pinned host rows + per-site means out; H2D, kernels and
     # D2H of consecutive groups of units overlap inside the call (what lg.mi_step_batched does for big batches)
@@ -492,6 +517,7 @@ def run_gpu(args):
         "gpu_launches": launches * world,
         "clocks": clocks,
     }
+    line["het_only"] = het_leg
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if dense is not None:

@@ -10,7 +10,7 @@ number of footprints:
                              (unchanged, imported from the installed `giremi`) plus
                              the bit-plane encoding of both strands -- worker side
   analyse_extracted(regs)    one submit for every (footprint, strand) unit
-                             (api.mi_step_batched, MODE_HET_ONLY), then the frames
+                             (api.mi_step_batched, HET_ONLY | SKIP_NONHET), then the frames
   region_mismatch_analysis   drop-in with the reference's signature (one region)
   footprint_bulk_calculation drop-in for giremi/script/giremi.py:20-95: one submit
                              per chunk of footprints instead of two Python MI loops
@@ -131,7 +131,10 @@ def analyse_extracted(regions, min_common_reads=5, ctx=None):
             if reg.encoded[s] is not None:
                 units.append(reg.encoded[s])
                 owner.append((r, s))
-    res = api.mi_step_batched(concat_plane_batches(units), min_common_reads, api.MODE_HET_ONLY, ctx=ctx) if units else None
+    # only pairs next to a het SNP are evaluated: mismatch.py:393-396 keeps no other pair and
+    # mismatch_pair_mi_full is used for nothing else, so the frames are the same
+    mode = api.MODE_HET_ONLY | api.MODE_SKIP_NONHET
+    res = api.mi_step_batched(concat_plane_batches(units), min_common_reads, mode, ctx=ctx) if units else None
     pair_rows = [{'+': None, '-': None} for _ in regions]
     mean_of = [{'+': {}, '-': {}} for _ in regions]
     site_off = 0

@@ -209,6 +209,8 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaFuncSetAttribute(k_pairs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem)) !=
           cudaSuccess ||
+      cudaFuncSetAttribute(k_pairs_fast_het, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem)) !=
+          cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pairs_ctas_per_sm, k_pairs_fast, kFastThreads,
                                                     sizeof(FastSmem)) != cudaSuccess ||
       ctx->pairs_ctas_per_sm < 1) {
@@ -822,7 +824,10 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     if (b->n_fast) {
       // persistent CTAs: a whole number of CTAs per SM, never more than there are items
       const unsigned grid = (unsigned)std::min<uint64_t>(b->n_fast, (uint64_t)ctx->num_sms * ctx->pairs_ctas_per_sm);
-      k_pairs_fast<<<grid, kFastThreads, sizeof(FastSmem), bstream(b)>>>(F);
+      if ((mode & (LGMI_MODE_HET_ONLY | LGMI_MODE_SKIP_NONHET)) == (LGMI_MODE_HET_ONLY | LGMI_MODE_SKIP_NONHET))
+        k_pairs_fast_het<<<grid, kFastThreads, sizeof(FastSmem), bstream(b)>>>(F);
+      else
+        k_pairs_fast<<<grid, kFastThreads, sizeof(FastSmem), bstream(b)>>>(F);
       ++ctx->launches;
     }
   }

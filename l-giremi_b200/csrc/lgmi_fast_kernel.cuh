@@ -108,15 +108,20 @@ __device__ __forceinline__ void fast_site_lists(SM& sm, uint32_t S) {
 // for every listed (site s, read r) and every partner site t that covers r, one 3-bit cell of
 // the pair gets +1 -- T[0][0], T[0][1], T[0][2] when s is the pair's first site (by t's label
 // at r), T[1][0], T[2][0] when it is the second (a read "other" at both sites is counted from
-// the first site only).  One warp per entry, lanes over the partners.
-__device__ __forceinline__ void fast_other_cells(FastSmem& sm, const uint32_t* __restrict__ rows, uint32_t S) {
+// the first site only).  One warp per entry, lanes over the partners.  `need` = the sites some
+// partner of which is needed whatever the entry's site is: all ones normally, the het sites when
+// only pairs next to a het SNP are evaluated (SKIP_NONHET).
+__device__ __forceinline__ void fast_other_cells(FastSmem& sm, const uint32_t* __restrict__ rows, uint32_t S,
+                                                 unsigned long long need) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t E = sm.n_oth_total;
   for (uint32_t e = warp; e < E; e += kFastWarps) {
     const uint32_t v = sm.oth_flat[e];
     const uint32_t s = v >> 8, w = (v & 255u) >> 5, bit = v & 31u;
+    const bool s_needed = ((need >> s) & 1ull) != 0ull;
     for (uint32_t t = lane; t < S; t += 32u) {
       if (t == s) continue;
+      if (!s_needed && !((need >> t) & 1ull)) continue;  // this pair is not evaluated
       const uint32_t* rt = rows + t * kRowStride;
       if (!((rt[16u + w] >> bit) & 1u)) continue;  // t does not cover the read
       const uint32_t Pt = (rt[8u + w] >> bit) & 1u, Mt = (rt[w] >> bit) & 1u;
@@ -179,6 +184,51 @@ __device__ __forceinline__ void fast_counts(const FastParams& P, FastSmem& sm, c
     b3 = __shfl_sync(0xffffffffu, b3, 0);
     if (cls == 2u) sm.list[b2 + __popc(m2 & lt)] = (uint16_t)p;
     if (cls == 3u) sm.list[kFastMaxPairs - 1u - (b3 + __popc(m3 & lt))] = (uint16_t)p;
+  }
+}
+
+// SKIP_NONHET: the same for the pairs next to a het SNP only, enumerated from the het sites instead
+// of filtered out of all pairs (a tenth of the sites are het: a filter would leave most lanes idle).
+// One warp per (het site h, block of 32 partners t); a pair of two het sites belongs to the smaller
+// one.  sm.val / sm.emit_mask were pre-filled with "no MI" / 0 for every pair of the unit.
+template <int NW>
+__device__ __forceinline__ void fast_counts_het(const FastParams& P, FastSmem& sm, const uint32_t* __restrict__ rows,
+                                                uint32_t S) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned long long het = sm.het_mask;
+  const uint32_t n_het = __popcll(het);
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t two = S > 32u ? 1u : 0u;  // one or two 32-partner blocks per het site (S <= 64)
+  for (uint32_t item = warp; item < (n_het << two); item += kFastWarps) {
+    const uint32_t h = sm.het_list[item >> two];
+    {
+      const uint32_t t = ((item & two) << 5) + lane;
+      uint32_t cls = 0u, p = 0u;
+      if (t < S && t != h && !(((het >> t) & 1ull) && t < h)) {
+        const uint32_t i = t < h ? t : h, j = t < h ? h : t;
+        p = ((i * (2u * S - i - 1u)) >> 1) + (j - i - 1u);
+        const uint32_t o = (sm.ocell[p >> 1] >> (16u * (p & 1u))) & 0x7fffu;
+        uint32_t n_other = 0u;
+        if (o) n_other = (o & 7u) + ((o >> 3) & 7u) + ((o >> 6) & 7u) + ((o >> 9) & 7u) + (o >> 12);
+        unsigned long long cnt;
+        if (pair_counts<NW>(rows + i * kRowStride, rows + j * kRowStride, n_other, P.min_common, cnt)) {
+          sm.val[p] = cnt | ((unsigned long long)o << 36);
+          cls = o ? 3u : 2u;
+          atomicOr(&sm.emit_mask[p >> 5], 1u << (p & 31u));
+        }
+      }
+      const uint32_t m2 = __ballot_sync(0xffffffffu, cls == 2u);
+      const uint32_t m3 = __ballot_sync(0xffffffffu, cls == 3u);
+      uint32_t b2 = 0u, b3 = 0u;
+      if (lane == 0) {
+        if (m2) b2 = atomicAdd(&sm.n_list2, (uint32_t)__popc(m2));
+        if (m3) b3 = atomicAdd(&sm.n_list3, (uint32_t)__popc(m3));
+      }
+      b2 = __shfl_sync(0xffffffffu, b2, 0);
+      b3 = __shfl_sync(0xffffffffu, b3, 0);
+      if (cls == 2u) sm.list[b2 + __popc(m2 & lt)] = (uint16_t)p;
+      if (cls == 3u) sm.list[kFastMaxPairs - 1u - (b3 + __popc(m3 & lt))] = (uint16_t)p;
+    }
   }
 }
 
@@ -400,7 +450,9 @@ __device__ __forceinline__ long long phase_clock() {
 #define LG_PHASE_SYNC(k, stmt) stmt;
 #endif
 
-__global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams P) {
+// kHetPairsOnly: the HET_ONLY | SKIP_NONHET instantiation (k_pairs_fast_het): counts by fast_counts_het
+template <bool kHetPairsOnly>
+__device__ __forceinline__ void pairs_fast_body(const FastParams& P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x;
@@ -414,6 +466,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
     sm.tab.inv[k] = k ? __drcp_rn((double)k) : 0.0;
   }
 
+  constexpr bool het_pairs_only = kHetPairsOnly;
   uint32_t idx = blockIdx.x;
   uint32_t buf = 0;
   FastItem it;
@@ -455,6 +508,10 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
         sm.n_list3 = 0u;
         sm.n_oth_total = 0u;
       }
+      if (het_pairs_only) {  // fast_counts_het only touches the pairs next to a het site
+        for (uint32_t q = tid; q < n_pairs; q += kFastThreads) sm.val[q] = kNoMi;
+        if (tid < n_chunks) sm.emit_mask[tid] = 0u;
+      }
       cp_async_wait<1>();  // this item's rows have landed (the next item's may still be in flight)
       LG_PHASE_SYNC(0, __syncthreads())
       fast_land(sm, rows, it, P.site_flags + it.site_off);
@@ -462,7 +519,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
       // a site with more than kOthCap "other" reads does not fit the sparse lists: the generic kernel takes the unit
       const bool over = tid < S && sm.n_oth[tid] > (uint32_t)kOthCap;
       fast_site_lists(sm, S);
-      fast_other_cells(sm, rows, S);
+      fast_other_cells(sm, rows, S, het_pairs_only ? sm.het_mask : ~0ull);
       bool dense;
       LG_PHASE_SYNC(2, dense = __syncthreads_or(over) != 0)  // (also: sm.info is read by every thread of the counts phase)
       if (dense) {
@@ -472,7 +529,10 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
         }
       } else {
         const uint32_t nw = ((uint32_t)it.R + 31u) >> 5;
-        if (nw <= 2u) fast_counts<2>(P, sm, rows, ijt, n_pairs);
+        if (het_pairs_only) {
+          if (nw <= 4u) fast_counts_het<4>(P, sm, rows, S);
+          else fast_counts_het<8>(P, sm, rows, S);
+        } else if (nw <= 2u) fast_counts<2>(P, sm, rows, ijt, n_pairs);
         else if (nw <= 4u) fast_counts<4>(P, sm, rows, ijt, n_pairs);
         else if (nw <= 7u) fast_counts<7>(P, sm, rows, ijt, n_pairs);
         else fast_counts<8>(P, sm, rows, ijt, n_pairs);
@@ -498,5 +558,9 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams
   }
   cp_async_wait<0>();
 }
+
+__global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams P) { pairs_fast_body<false>(P); }
+// launched instead of k_pairs_fast when the mode is HET_ONLY | SKIP_NONHET
+__global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast_het(const FastParams P) { pairs_fast_body<true>(P); }
 
 }  // namespace lgmi
