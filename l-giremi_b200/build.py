@@ -31,7 +31,7 @@ def sources():
     out = []
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for name in sorted(os.listdir(root)):
-            if name.endswith((".cu", ".cuh", ".c", ".h")):
+            if name.endswith((".cu", ".cuh", ".inl", ".c", ".h")):
                 out.append(os.path.join(root, name))
     return out
 

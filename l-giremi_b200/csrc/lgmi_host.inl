@@ -117,40 +117,77 @@ extern "C" int lgmi_encode_unit(uint32_t n_sites, const uint8_t* site_type, cons
   if ((n_sites && (!site_type || !n_depth_entries || !n_nt_entries || !site_flags)) || !n_reads_out || !row_words_out)
     return LGMI_ERR_ARG;
   // ---- pass 1: intern the read names in order of first appearance; (site, read) -> last allele wins
-  std::unordered_map<std::string_view, uint32_t> index;
+  // Open-addressing table of the distinct names (keys are views into the blob): 64-bit FNV-1a, linear
+  // probing, at most half full.  Ids are handed out in order of first appearance.
+  struct NameSlot {
+    uint64_t hash;
+    const char* ptr;
+    uint32_t len, id;
+  };
+  std::vector<NameSlot> table(1024, NameSlot{0, nullptr, 0, 0});
+  uint32_t n_names = 0;
+  auto grow = [&]() {
+    std::vector<NameSlot> bigger(table.size() * 2, NameSlot{0, nullptr, 0, 0});
+    const size_t mask = bigger.size() - 1;
+    for (const NameSlot& e : table) {
+      if (!e.ptr) continue;
+      size_t k = (size_t)e.hash & mask;
+      while (bigger[k].ptr) k = (k + 1) & mask;
+      bigger[k] = e;
+    }
+    table.swap(bigger);
+  };
   std::vector<std::vector<std::pair<uint32_t, uint32_t>>> site_reads(n_sites);  // (read, allele) in encounter order
+  // per read: the last site it was seen at (+1) and its position in that site's list -- the per-site
+  // "read already listed" test without a hash map per site
+  std::vector<uint32_t> seen_site, seen_slot;
   uint64_t cursor = 0;
   size_t nt_k = 0;
   for (uint32_t s = 0; s < n_sites; ++s) {
-    std::unordered_map<uint32_t, uint32_t> slot;  // read -> position in site_reads[s]
     for (uint32_t e = 0; e < n_nt_entries[s]; ++e, ++nt_k) {
       const uint32_t allele = nt_allele[nt_k];
+      site_reads[s].reserve(site_reads[s].size() + nt_n_names[nt_k]);
       for (uint32_t q = 0; q < nt_n_names[nt_k]; ++q) {
         if (cursor > blob_len) return LGMI_ERR_ARG;
         const char* b = names_blob + cursor;
-        const void* nl = memchr(b, '\n', blob_len - cursor);
-        const uint64_t len = nl ? (uint64_t)((const char*)nl - b) : blob_len - cursor;
-        cursor += len + 1;
-        const std::string_view name(b, len);
-        auto it = index.find(name);
-        uint32_t r;
-        if (it == index.end()) {
-          r = (uint32_t)index.size();
-          index.emplace(name, r);
-        } else {
-          r = it->second;
+        uint64_t h = 1469598103934665603ull;
+        uint64_t len = 0;
+        const uint64_t room = blob_len - cursor;
+        while (len < room && b[len] != '\n') {
+          h = (h ^ (unsigned char)b[len]) * 1099511628211ull;
+          ++len;
         }
-        auto sl = slot.find(r);
-        if (sl == slot.end()) {
-          slot.emplace(r, (uint32_t)site_reads[s].size());
+        cursor += len + 1;
+        h ^= h >> 29;  // the low bits index the table
+        size_t k = (size_t)h & (table.size() - 1);
+        uint32_t r;
+        for (;;) {
+          NameSlot& slot = table[k];
+          if (!slot.ptr) {
+            r = n_names++;
+            slot = NameSlot{h, b, (uint32_t)len, r};
+            seen_site.push_back(0u);
+            seen_slot.push_back(0u);
+            if ((size_t)n_names * 2 > table.size()) grow();
+            break;
+          }
+          if (slot.hash == h && slot.len == len && memcmp(slot.ptr, b, len) == 0) {
+            r = slot.id;
+            break;
+          }
+          k = (k + 1) & (table.size() - 1);
+        }
+        if (seen_site[r] != s + 1u) {
+          seen_site[r] = s + 1u;
+          seen_slot[r] = (uint32_t)site_reads[s].size();
           site_reads[s].emplace_back(r, allele);
         } else {
-          site_reads[s][sl->second].second = allele;  // mutual_information.py:15-16: dict() keeps the last
+          site_reads[s][seen_slot[r]].second = allele;  // mutual_information.py:15-16: dict() keeps the last
         }
       }
     }
   }
-  const uint32_t R = (uint32_t)index.size();
+  const uint32_t R = n_names;
   const uint32_t W = 4u * ((R + 127u) / 128u);
   *n_reads_out = R;
   *row_words_out = W;
