@@ -236,3 +236,19 @@ def test_unit_costs_formula(lg):
     lib = L.load()
     want = [lib.lgmi_unit_cost(int(s), int(r)) for s, r in zip(units["n_sites"], units["n_reads"])]
     assert lg.unit_costs(units).tolist() == want == [0, 0, 4900, 1999000 * 1563]
+
+
+def test_experiment_switches_still_compile(tmp_path):
+    """The two compile-time switches of the pair kernel (-DLGMI_PHASE_CLOCKS: per-barrier cycle counts
+    for tools/phase_clocks.py; -DLGMI_HET_DEFERRED_MEANS: the het-only kernel's means one unit behind)
+    are off in the product build; this keeps them compiling (device code only, no link)."""
+    import importlib
+    bld = importlib.import_module("l-giremi_b200.build")
+    out = str(tmp_path / "variant.cubin")
+    flags = [f for f in bld.NVCC_FLAGS if not f.startswith("-fPIC") and f not in ("-Xcompiler", "-Xptxas", "-v")]
+    cmd = [bld.find_nvcc(), *flags, "-DLGMI_PHASE_CLOCKS", "-DLGMI_HET_DEFERRED_MEANS", "-cubin", "-o", out,
+           os.path.join(bld.CSRC, "lgmi.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    sass = subprocess.run(["cuobjdump", "-elf", out], capture_output=True, text=True).stdout
+    assert "g_phase_clk" in sass                           # the debug counters exist only in this build
