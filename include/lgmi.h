@@ -124,8 +124,11 @@ typedef struct {
 typedef struct {
   uint64_t n_candidates;        /* sum over units of S(S-1)/2                  */
   uint64_t n_evaluated;         /* candidates whose MI was computed or dropped */
-                                /* by the filter (== n_candidates unless       */
-                                /* SKIP_NONHET)                                */
+                                /* by the filter: n_candidates, or under       */
+                                /* SKIP_NONHET the candidates with a het_snp   */
+                                /* partner (counted from the host flag bytes;  */
+                                /* n_candidates when the caller filled the     */
+                                /* device buffers itself)                      */
   uint64_t n_records;           /* emitted pairs                               */
   const lgmi_pair_rec* records; /* unit order, then pair order (i, then j) --  */
                                 /* exactly the reference's row order           */
@@ -158,6 +161,8 @@ typedef struct lgmi_batch lgmi_batch_t;
 
 /* ----- context ------------------------------------------------------------ */
 LGMI_API int lgmi_version(void);
+/* number of CUDA devices this process sees (0: none, or no driver)             */
+LGMI_API int lgmi_device_count(void);
 /* device: CUDA ordinal.  Fails with LGMI_ERR_NODEVICE if there is no GPU.     */
 LGMI_API int lgmi_create(int device, lgmi_t** out);
 LGMI_API void lgmi_destroy(lgmi_t* ctx);
@@ -182,6 +187,15 @@ LGMI_API int lgmi_set_dense_threshold(lgmi_t* ctx, uint32_t min_sites, uint32_t 
  * integers either way; applies to batches created afterwards.  Environment    *
  * LGMI_SMALL_PATH=0/1 sets the default.                                       */
 LGMI_API int lgmi_set_small_path(lgmi_t* ctx, int tensor_cores);
+/* Mid-depth units (more than 64 sites or 256 reads, below the dense threshold)   *
+ * have their counts built on the tensor cores in one batched launch              *
+ * (tensor_cores != 0, default: k_tile_gram expands the bit-planes in the kernel, *
+ * one tcgen05 int8 MMA per label row block, then k_tile_finish) or by tiled      *
+ * AND+popcount (0: k_tile_mi; units deeper than 65 535 reads always).  Same       *
+ * integers and the same MI bits either way (mutual_information.py:15-41);        *
+ * applies to batches created afterwards.  Environment LGMI_TILE_PATH=0/1 sets    *
+ * the default.                                                                    */
+LGMI_API int lgmi_set_tile_path(lgmi_t* ctx, int tensor_cores);
 
 /* ----- batched MI step: replaces the per-unit loop                           *
  *   mismatch.py:387-404 = mutual_information.py:6-45 -> het filter -> :48-60  */
@@ -251,9 +265,17 @@ LGMI_API int lgmi_site_mean_csr(lgmi_t* ctx, const uint64_t* offsets, const doub
  * site_flags carries the type in its low 2 bits.  call may be NULL.           */
 LGMI_API int lgmi_ecdf(lgmi_t* ctx, const double* mean, const uint8_t* site_flags, uint64_t n,
               double threshold, double* mip, uint8_t* call);
-/* ecdf(x)(samples): y[searchsorted(sort(x), samples, 'left')]  (stat.py:16-27)*/
+/* ecdf(x)(samples): y[searchsorted(sort(x), samples, 'left')]  (stat.py:16-27)*
+ * NaNs in x sort last and a NaN sample lands on the first of them, as numpy    *
+ * orders them.                                                                 */
 LGMI_API int lgmi_ecdf_eval(lgmi_t* ctx, const double* x, uint64_t n, const double* samples,
                    uint64_t n_samples, double* out);
+/* ecdf(x) itself (stat.py:16-19), built ONCE: sorted_out = sort(x) (n values)  *
+ * and y_out = [0] ++ linspace(1/n, 1, n) (n + 1 values), both computed on the  *
+ * device.  The callable the reference returns (stat.py:21-27) is then          *
+ * y_out[searchsorted(sorted_out, sample, 'left')]: the CLI applies it row by   *
+ * row (giremi.py:424-428), which must not cost a device round trip per row.    */
+LGMI_API int lgmi_ecdf_table(lgmi_t* ctx, const double* x, uint64_t n, double* sorted_out, double* y_out);
 
 /* ----- host-side native pieces either side of the step (no device needed) --- *
  * One read's short-form cs tag (minimap2 --cs): its substitutions in contig    *

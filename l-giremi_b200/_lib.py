@@ -38,13 +38,13 @@ DENSE_DEFAULT = (48, 8192)    # lgmi_set_dense_threshold defaults: (min_sites, m
 EXPORTS = (
     "lgmi_version", "lgmi_create", "lgmi_destroy", "lgmi_last_error", "lgmi_set_stream",
     "lgmi_pinned_alloc", "lgmi_pinned_free", "lgmi_launch_count", "lgmi_set_dense_threshold",
-    "lgmi_set_small_path",
+    "lgmi_set_small_path", "lgmi_set_tile_path",
     "lgmi_batch_create", "lgmi_batch_destroy", "lgmi_batch_upload", "lgmi_batch_run",
     "lgmi_batch_download", "lgmi_batch_sync", "lgmi_batch_device_ptrs",
     "lgmi_batch_algorithmic_bytes", "lgmi_pipeline_create", "lgmi_pipeline_step", "lgmi_pipeline_step_packed",
     "lgmi_pipeline_destroy",
     "lgmi_submit", "lgmi_wait", "lgmi_site_mean_csr",
-    "lgmi_ecdf", "lgmi_ecdf_eval", "lgmi_cs_scan", "lgmi_encode_unit", "lgmi_unit_cost", "lgmi_partition_lpt",
+    "lgmi_ecdf", "lgmi_ecdf_eval", "lgmi_ecdf_table", "lgmi_device_count", "lgmi_cs_scan", "lgmi_encode_unit", "lgmi_unit_cost", "lgmi_partition_lpt",
 )
 
 
@@ -104,6 +104,7 @@ def load():
         "lgmi_launch_count": (u64, [vp]),
         "lgmi_set_dense_threshold": (i32, [vp, u32, u32]),
         "lgmi_set_small_path": (i32, [vp, i32]),
+        "lgmi_set_tile_path": (i32, [vp, i32]),
         "lgmi_batch_create": (i32, [vp, vp, u32, u64, u64, pvp]),
         "lgmi_batch_destroy": (None, [vp]),
         "lgmi_batch_upload": (i32, [vp, vp, vp]),
@@ -121,6 +122,8 @@ def load():
         "lgmi_site_mean_csr": (i32, [vp, vp, vp, u64, vp]),
         "lgmi_ecdf": (i32, [vp, vp, vp, u64, C.c_double, vp, vp]),
         "lgmi_ecdf_eval": (i32, [vp, vp, u64, vp, u64, vp]),
+        "lgmi_ecdf_table": (i32, [vp, vp, u64, vp, vp]),
+        "lgmi_device_count": (i32, []),
         "lgmi_cs_scan": (i32, [C.c_char_p, u64, C.c_int64, i32, u32, vp, vp, vp, C.POINTER(u32), u32, vp, vp,
                                C.POINTER(u32)]),
         "lgmi_encode_unit": (i32, [u32, vp, vp, vp, vp, vp, vp, vp, C.c_char_p, u64, u64, vp, vp, vp,

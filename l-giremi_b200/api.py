@@ -58,6 +58,10 @@ class Context:
         """Small units counted by popcount (False, default) or on the tensor cores (True)."""
         check(self._lib.lgmi_set_small_path(self.handle, 1 if tensor_cores else 0), self.handle)
 
+    def set_tile_path(self, tensor_cores):
+        """Mid-depth units counted on the tensor cores (True, default: k_tile_gram) or by tiled popcount (False)."""
+        check(self._lib.lgmi_set_tile_path(self.handle, 1 if tensor_cores else 0), self.handle)
+
     @property
     def launch_count(self):
         return int(self._lib.lgmi_launch_count(self.handle))
@@ -91,15 +95,33 @@ class _Pinned:
 _default_ctx = None
 
 
+def device_count() -> int:
+    """CUDA devices this process sees (0 without a driver)."""
+    return int(_lib.load().lgmi_device_count())
+
+
+def default_device() -> int:
+    """Which GPU a process gets when nobody said: LGMI_DEVICE, else LOCAL_RANK (torchrun), else -- inside a
+    multiprocessing pool worker, as when the reference's `l-giremi -t N` runs the name-level drop-ins in its
+    forked workers (giremi.py:375-380) -- worker index modulo the number of GPUs, so that N workers use
+    min(N, 8) GPUs instead of all sharing device 0."""
+    import multiprocessing as mp
+    import os
+    for key in ("LGMI_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(key, "") != "":
+            return int(os.environ[key])
+    ident = getattr(mp.current_process(), "_identity", ())
+    if ident:
+        return (int(ident[0]) - 1) % max(1, device_count())
+    return 0
+
+
 def get_context(device=None) -> Context:
     """Process-wide context, created on first use (after any fork: CUDA must be
     initialised in the process that uses it)."""
     global _default_ctx
     if _default_ctx is None or _default_ctx.handle is None:
-        import os
-        if device is None:
-            device = int(os.environ.get("LGMI_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-        _default_ctx = Context(device)
+        _default_ctx = Context(default_device() if device is None else device)
     return _default_ctx
 
 
@@ -328,20 +350,36 @@ def mean_mismatch_pair_mutual_info(mismatch_pair_mi):
 
 def ecdf(x):
     """Drop-in for giremi.stat.ecdf (stat.py:7-29): returns a callable mapping a
-    sample (scalar or array) to ``y[searchsorted(sort(x), sample)]``."""
+    sample (scalar or array) to ``y[searchsorted(sort(x), sample)]``.
+
+    The sort and the ordinates ``[0] ++ linspace(1/n, 1, n)`` are computed ONCE, on the
+    device, when the callable is built (lgmi_ecdf_table); evaluating it is an index
+    into that table.  The CLI calls it once per row through DataFrame.apply
+    (giremi.py:424-428): a device round trip per call would be far slower than the
+    reference.  Large sample arrays go to the device in one launch (lgmi_ecdf_eval)."""
     xs = np.ascontiguousarray(np.array(x, dtype=np.float64).reshape(-1))
     if xs.size == 0:
         raise ZeroDivisionError('division by zero')      # 1/n at stat.py:19
+    ctx = get_context()
+    table_x = np.empty(xs.size, dtype=np.float64)
+    table_y = np.empty(xs.size + 1, dtype=np.float64)
+    check(ctx._lib.lgmi_ecdf_table(ctx.handle, ptr(xs), xs.size, ptr(table_x), ptr(table_y)), ctx.handle)
 
     def childfunc(sample):
         s = np.asarray(sample, dtype=np.float64)
-        flat = np.ascontiguousarray(s).reshape(-1)             # (ascontiguousarray alone would make 0-d into 1-d)
-        out = np.empty(flat.size, dtype=np.float64)
-        ctx = get_context()
-        check(ctx._lib.lgmi_ecdf_eval(ctx.handle, ptr(xs), xs.size, ptr(flat), flat.size, ptr(out)), ctx.handle)
-        return np.float64(out[0]) if s.ndim == 0 else out.reshape(s.shape)
+        if s.size >= ECDF_DEVICE_MIN_SAMPLES:
+            flat = np.ascontiguousarray(s).reshape(-1)
+            out = np.empty(flat.size, dtype=np.float64)
+            check(ctx._lib.lgmi_ecdf_eval(ctx.handle, ptr(table_x), table_x.size, ptr(flat), flat.size, ptr(out)),
+                  ctx.handle)
+            return out.reshape(s.shape)
+        out = table_y[np.searchsorted(table_x, s, side='left')]   # numpy orders NaN last, as the table does
+        return np.float64(out) if s.ndim == 0 else out
 
     return childfunc
+
+
+ECDF_DEVICE_MIN_SAMPLES = 4096   # sample arrays at least this long are evaluated on the device
 
 
 def mip_and_calls(mean_mi, site_types, threshold=0.05, ctx=None):

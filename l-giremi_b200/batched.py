@@ -15,6 +15,12 @@ number of footprints:
   footprint_bulk_calculation drop-in for giremi/script/giremi.py:20-95: one submit
                              per chunk of footprints instead of two Python MI loops
                              per footprint
+  main                       drop-in for giremi/script/giremi.py:324-455 (the `l-giremi`
+                             console script): the pool workers only extract and encode
+                             (extract_footprints); the PARENT owns the GPUs -- every
+                             visible one, units partitioned by pair-count cost
+                             (multigpu.DevicePool) -- and the mip / label pass
+                             (:415-429) is one launch instead of a Python call per row
 
 The frames have the reference's columns, row order and dtypes; tests compare them
 with pandas.testing.assert_frame_equal against the unmodified reference.
@@ -36,27 +42,33 @@ _STRANDS = ('+', '-')
 
 
 class RegionExtract:
-    """What a worker hands to the parent for one footprint."""
+    """What a worker hands to the parent for one footprint: the bit-planes of its (up to two)
+    units and everything of the three output tables that does not depend on the MI step.  The
+    reference's dicts (read-name lists) stay in the worker unless keep_dicts is set."""
 
-    __slots__ = ("chromosome", "mismatches", "removed", "encoded")
+    __slots__ = ("chromosome", "encoded", "site_rows", "site_pos", "removed_rows", "mismatches", "removed")
 
-    def __init__(self, chromosome, mismatches, removed):
+    def __init__(self, chromosome, mismatches, removed, keep_dicts=True):
         self.chromosome = chromosome
-        self.mismatches = mismatches            # {'+': {pos: site}, '-': {...}}  (reference objects, untouched)
-        self.removed = removed
         # a strand enters the MI step only with at least two sites (mismatch.py:388)
         # (native encoder, csrc/lgmi_host.inl: one PlaneBatch of one unit per strand)
         self.encoded = {s: (encode_mismatches_native(mismatches[s]) if len(mismatches[s]) > 1 else None)
                         for s in _STRANDS}
+        self.site_rows, self.site_pos = {}, {}
+        for s in _STRANDS:
+            self.site_rows[s], self.site_pos[s] = _site_frame_rows(chromosome, s, mismatches[s])
+        self.removed_rows = [[chromosome, s, pos, removed[s][pos]['removed']] for s in _STRANDS for pos in removed[s]]
+        self.mismatches = mismatches if keep_dicts else None   # {'+': {pos: site}, '-': {...}}  (reference objects)
+        self.removed = removed if keep_dicts else None
 
 
-def extract_region(chromosome, start_pos, end_pos, sam, genome, **filters) -> RegionExtract:
+def extract_region(chromosome, start_pos, end_pos, sam, genome, keep_dicts=True, **filters) -> RegionExtract:
     """Extraction and site filters by the reference's own code (mismatch.py:11-342), then encode."""
     from giremi.mismatch import get_region_mismatches_with_filters
     filters.pop('min_common_reads', None)
     mismatches, removed = get_region_mismatches_with_filters(
         chromosome=chromosome, start_pos=start_pos, end_pos=end_pos, sam=sam, genome=genome, **filters)
-    return RegionExtract(chromosome, mismatches, removed)
+    return RegionExtract(chromosome, mismatches, removed, keep_dicts=keep_dicts)
 
 
 def _alt_major(site):
@@ -68,10 +80,12 @@ def _alt_major(site):
     return ref, alts[0][0], alts[0][1], total
 
 
-def _site_frame_rows(chromosome, strand, sites, mean_of):
+def _site_frame_rows(chromosome, strand, sites):
+    """Rows of the site table (mismatch.py:420-494) with mean_mi still NaN, and the position of each
+    row (the parent fills mean_mi from the MI step by position)."""
     het = [d / t for (_r, _a, d, t) in (_alt_major(s) for s in sites.values() if s['type'] == 'het_snp')]
     allelic_ratio = sum(het) / len(het) if het else 0.5
-    rows = []
+    rows, positions = [], []
     for pos, site in sites.items():
         ref, alt, alt_depth, total = _alt_major(site)
         ratio = alt_depth / total
@@ -85,8 +99,9 @@ def _site_frame_rows(chromosome, strand, sites, mean_of):
         if 'N' in change:
             continue                                    # mismatch.py:483-490
         rows.append([site['type'], chromosome, strand, pos, ref, change, ratio, ratio - allelic_ratio, total, acgt,
-                     up, down, mean_of.get(pos, np.nan)])
-    return rows
+                     up, down, np.nan])
+        positions.append(pos)
+    return rows, positions
 
 
 class _UnitMeta:
@@ -122,9 +137,27 @@ def write_mi_table(path, frames):
     return len(df)
 
 
-def analyse_extracted(regions, min_common_reads=5, ctx=None):
+def _check_bad_sites(units, metas, min_common_reads, ctx):
+    """The reference raises IndexError (mutual_information.py:30/32) as soon as a pair with enough common
+    reads touches a site whose `depth` holds fewer than two alleles -- any such pair, not only those next to a
+    het SNP.  The batched step evaluates het-adjacent pairs only, so units with such a site (the reference's
+    filters never let one through, mismatch.py:275-282) are looked at once more with every pair kept."""
+    flagged = [k for k, m in enumerate(metas) if m.bad_sites]
+    if not flagged:
+        return
+    res = api.mi_step_batched(concat_plane_batches([units[k] for k in flagged]), min_common_reads,
+                              api.MODE_ALL_PAIRS, ctx=ctx)
+    for n, k in enumerate(flagged):
+        rec = res.unit_records(n)
+        bad = np.fromiter(metas[k].bad_sites, dtype=np.int64)
+        if len(rec) and (np.isin(rec['i'], bad).any() or np.isin(rec['j'], bad).any()):
+            raise IndexError('list index out of range')
+
+
+def analyse_extracted(regions, min_common_reads=5, ctx=None, pool=None):
     """[(df_mismatches, df_mismatch_pair_mi, df_removed_mismatches), ...] for the extracted
-    regions, with ONE GPU submit for all of their (footprint, strand) units."""
+    regions, with ONE GPU submit for all of their (footprint, strand) units -- or, given a
+    multigpu.DevicePool, one submit per GPU over a cost-balanced partition of the units."""
     units, owner = [], []
     for r, reg in enumerate(regions):
         for s in _STRANDS:
@@ -134,21 +167,23 @@ def analyse_extracted(regions, min_common_reads=5, ctx=None):
     # only pairs next to a het SNP are evaluated: mismatch.py:393-396 keeps no other pair and
     # mismatch_pair_mi_full is used for nothing else, so the frames are the same
     mode = api.MODE_HET_ONLY | api.MODE_SKIP_NONHET
-    res = api.mi_step_batched(concat_plane_batches(units), min_common_reads, mode, ctx=ctx) if units else None
+    res = None
+    metas = [_UnitMeta(u) for u in units]
+    if units:
+        first = pool.contexts[0] if pool is not None else ctx
+        _check_bad_sites(units, metas, min_common_reads, first)
+        pb = concat_plane_batches(units)
+        res = pool.run(pb, min_common_reads, mode) if pool is not None else \
+            api.mi_step_batched(pb, min_common_reads, mode, ctx=ctx)
     pair_rows = [{'+': None, '-': None} for _ in regions]
     mean_of = [{'+': {}, '-': {}} for _ in regions]
     site_off = 0
     for u, (r, s) in enumerate(owner):
-        eu = _UnitMeta(units[u])
+        eu = metas[u]
         rec = res.unit_records(u)
-        if eu.bad_sites and len(rec):
-            bad = np.fromiter(eu.bad_sites, dtype=np.int64)
-            if np.isin(rec['i'], bad).any() or np.isin(rec['j'], bad).any():
-                raise IndexError('list index out of range')          # mutual_information.py:30/32
-        pos = eu.positions
         pair_rows[r][s] = pair_frame(regions[r].chromosome, s, eu, rec)
         mean = res.site_mean[site_off:site_off + eu.n_sites]
-        mean_of[r][s] = {p: float(m) for p, m in zip(pos, mean.tolist()) if m == m}   # NaN: in no kept pair
+        mean_of[r][s] = {p: float(m) for p, m in zip(eu.positions, mean.tolist()) if m == m}   # NaN: in no kept pair
         site_off += eu.n_sites
     out = []
     for r, reg in enumerate(regions):
@@ -159,11 +194,11 @@ def analyse_extracted(regions, min_common_reads=5, ctx=None):
             df_pairs = parts[0] if len(parts) == 1 else pd.concat(parts, axis=0, ignore_index=True)
         site_rows = []
         for s in _STRANDS:
-            site_rows += _site_frame_rows(reg.chromosome, s, reg.mismatches[s], mean_of[r][s])
+            found = mean_of[r][s]
+            for row, pos in zip(reg.site_rows[s], reg.site_pos[s]):
+                site_rows.append(row[:-1] + [found.get(pos, np.nan)])
         df_sites = pd.DataFrame.from_records(site_rows, columns=_SITE_COLUMNS)
-        df_removed = pd.DataFrame.from_records(
-            [[reg.chromosome, s, pos, reg.removed[s][pos]['removed']] for s in _STRANDS for pos in reg.removed[s]],
-            columns=_REMOVED_COLUMNS)
+        df_removed = pd.DataFrame.from_records(reg.removed_rows, columns=_REMOVED_COLUMNS)
         out.append((df_sites, df_pairs, df_removed))
     return out
 
@@ -180,10 +215,11 @@ _FILTER_KEYS = ('keep_non_spliced_read', 'min_dist_from_splice', 'min_allele_dep
                 'mismatch_window_size', 'max_window_mismatch', 'max_window_mismatch_type', 'mode')
 
 
-def footprint_bulk_calculation(footprints, variables):
-    """Drop-in for giremi.script.giremi.footprint_bulk_calculation (giremi.py:20-95):
-    same inputs, same four DataFrames; every footprint of the chunk is extracted first
-    and the MI step of all of them is one GPU submit."""
+def extract_footprints(footprints, variables, keep_dicts=False):
+    """The worker half of giremi/script/giremi.py:20-95 for one chunk of footprints: strand
+    correction, SNP positions, repeats, extraction + filters (all the reference's own code) and the
+    bit-plane encoding.  No MI, no CUDA: safe in a forked pool worker.  Returns
+    (read-strand rows, [RegionExtract, ...])."""
     import pysam
     from giremi.fileio import read_simple_repeat_intervals, read_snp_positions_in_region
     from giremi.strand import correct_read_strand_in_region
@@ -205,15 +241,115 @@ def footprint_bulk_calculation(footprints, variables):
         simple_repeat_intervals = [[rs, re] for rs, re in repeats[chromosome]
                                    if (rs > end_pos) or (re < start_pos)]          # as written at giremi.py:55-59
         regions.append(extract_region(
-            chromosome, start_pos, end_pos, sam, genome, simple_repeat_intervals=simple_repeat_intervals,
+            chromosome, start_pos, end_pos, sam, genome, keep_dicts=keep_dicts,
+            simple_repeat_intervals=simple_repeat_intervals,
             snp_positions=snp_positions, read_strand_dict=read_strand_dict,
             **{k: variables[k] for k in _FILTER_KEYS}))
-    frames = analyse_extracted(regions, variables['mi_min_common_reads'])
+    for fh in (sam, genome, vcf, gtf):
+        fh.close()
+    return strand_list, regions
+
+
+def _chunk_frames(strand_list, frames):
+    """The four DataFrames footprint_bulk_calculation returns for one chunk (giremi.py:79-93)."""
     mismatch_df = pd.concat([f[0] for f in frames], axis=0)
     mi_df = pd.concat([f[1] for f in frames], axis=0)
     removed_df = pd.concat([f[2] for f in frames], axis=0)
     strand_df = pd.DataFrame.from_records(strand_list,
                                           columns=['read_name', 'original_read_strand', 'corrected_read_strand'])
-    for fh in (sam, genome, vcf, gtf):
-        fh.close()
     return mismatch_df, mi_df, strand_df, removed_df
+
+
+def footprint_bulk_calculation(footprints, variables):
+    """Drop-in for giremi.script.giremi.footprint_bulk_calculation (giremi.py:20-95):
+    same inputs, same four DataFrames; every footprint of the chunk is extracted first
+    and the MI step of all of them is one GPU submit.  Called inside a pool worker (the stock
+    `main`), the worker's GPU is worker index modulo the number of GPUs (api.default_device)."""
+    strand_list, regions = extract_footprints(footprints, variables)
+    return _chunk_frames(strand_list, analyse_extracted(regions, variables['mi_min_common_reads']))
+
+
+# argparse destination -> key of the `variables` dict the reference's main builds (giremi.py:327-352)
+_VARIABLE_OF_ARG = {
+    'bam_file': 'bam_file', 'genome_fasta': 'genome_file', 'annotation_gtf': 'gtf_file', 'repeat_txt': 'repeat_file',
+    'snp_bcf': 'snp_file', 'padding_exon': 'exon_padding', 'padding_gene': 'gene_padding',
+    'homopoly_length': 'homopoly_length', 'keep_non_spliced_read': 'keep_non_spliced_read',
+    'max_het_snp_ratio': 'max_het_snp_ratio', 'min_allele_depth': 'min_allele_depth',
+    'min_allele_ratio': 'min_allele_ratio', 'min_dist_from_splice': 'min_dist_from_splice',
+    'min_het_snp_ratio': 'min_het_snp_ratio', 'min_total_depth': 'min_total_depth',
+    'mi_p_threshold': 'mip_threshold', 'mi_min_common_read': 'mi_min_common_reads',
+    'mi_calculation_only': 'mi_calculation_only', 'mismatch_window_size': 'mismatch_window_size',
+    'max_window_mismatch': 'max_window_mismatch', 'max_window_mismatch_type': 'max_window_mismatch_type',
+    'mode': 'mode', 'model': 'model', 'skip_strand_correction': 'skip_strand_correction',
+}
+
+# wall-clock seconds of the last main(): what tools/run_cli.py reports as the MI-step time of the patched CLI
+last_run_times = {}
+
+
+def main():
+    """Drop-in for giremi.script.giremi.main (giremi.py:324-455), the `l-giremi` console script:
+    same arguments (the reference's own parse_args), same five output files.
+
+    Differences in HOW, none in WHAT: (1) the `-t` pool workers extract and encode only
+    (extract_footprints) -- no worker touches CUDA; (2) the parent, after the pool has returned,
+    runs the MI step of ALL chunks' units over every visible GPU (multigpu.DevicePool: LPT
+    partition by pair-count cost, one submit per GPU, results merged back in the reference's
+    order); (3) the empirical p-value of every site (giremi.py:415-429: ecdf over the het-SNP
+    means, then a Python call per row) is one lgmi_ecdf launch (api.mip_and_calls).  The GLM
+    scoring (run_glm) is the reference's own."""
+    import logging
+    import multiprocessing as mp
+    import time
+    from functools import partial
+    import giremi.script.giremi as cli
+    from giremi.footprint import get_footprints
+    from . import multigpu
+    args = cli.parse_args()
+    variables = {key: getattr(args, dest) for dest, key in _VARIABLE_OF_ARG.items()}
+    logging.basicConfig(format='%(asctime)s %(levelname)s %(message)s', level=logging.INFO)
+    logging.info('Get regions that are covered by enough reads.')
+    footprints = get_footprints(variables['bam_file'], args.chromosomes, variables['min_total_depth'])
+    n = int(len(footprints) / args.thread / 2)                         # chunking as giremi.py:367-370
+    chunks = [footprints[i:(i + n)] for i in range(0, len(footprints), n)]
+    logging.info('Calculate mismatches in each region.')
+    t0 = time.perf_counter()
+    with mp.Pool(args.thread) as p:
+        extracted = p.map(partial(extract_footprints, variables=variables), chunks)
+    t1 = time.perf_counter()
+    pool = multigpu.get_pool()                                          # CUDA starts here, in the parent
+    regions = [reg for _strand_rows, regs in extracted for reg in regs]
+    frames = analyse_extracted(regions, variables['mi_min_common_reads'], pool=pool)
+    t2 = time.perf_counter()
+    results, k = [], 0
+    for strand_rows, regs in extracted:
+        results.append(_chunk_frames(strand_rows, frames[k:k + len(regs)]))
+        k += len(regs)
+    mismatch_df = pd.concat([r[0] for r in results], axis=0)
+    mi_df = pd.concat([r[1] for r in results], axis=0)
+    strand_df = pd.concat([r[2] for r in results], axis=0)
+    removed_df = pd.concat([r[3] for r in results], axis=0)
+    strand_df.to_csv(args.output_prefix + '.strand.txt', sep='\t', index=False)
+    mi_df.to_csv(args.output_prefix + '.mi.txt', sep='\t', index=False)
+    removed_df.to_csv(args.output_prefix + '.removed.txt', sep='\t', index=False)
+    t3 = time.perf_counter()
+    mip_s = 0.0
+    if not variables['mi_calculation_only']:
+        logging.info('Score the RNA editing sites.')
+        mismatch_df.loc[:, 'mip'] = np.nan
+        if mismatch_df['mean_mi'].notna().sum() > 0:
+            ta = time.perf_counter()
+            mip, _call = api.mip_and_calls(mismatch_df['mean_mi'].to_numpy(dtype=np.float64),
+                                           mismatch_df['type'].to_numpy(), variables['mip_threshold'],
+                                           ctx=pool.contexts[0])
+            mismatch_df.loc[:, 'mip'] = mip
+            mip_s = time.perf_counter() - ta
+        glmresult, scorepf = cli.run_glm(mismatch_df, mip_threshold=variables['mip_threshold'], model=variables['model'])
+        del glmresult['label']
+        del glmresult['id']
+        glmresult.to_csv(args.output_prefix + '.mismatch.txt', sep='\t', index=False)
+        scorepf.to_csv(args.output_prefix + '.score_performance.txt', sep='\t', index=False)
+    last_run_times.update({'extract_pool_s': t1 - t0, 'mi_step_s': t2 - t1, 'write_tables_s': t3 - t2, 'mip_s': mip_s,
+                           'n_gpus': len(pool), 'n_units': sum(1 for reg in regions for s in _STRANDS
+                                                               if reg.encoded[s] is not None)})
+    logging.info('All done!')

@@ -50,6 +50,7 @@ struct lgmi_ctx {
   int pairs_ctas_per_sm = 0;
   int pre_ctas_per_sm = 0;
   int small_path = 0;  // 0: popcount (k_pairs_fast, default: faster); 1: counted on the tensor cores
+  int tile_path = 1;   // mid-depth units: 1 tensor cores (k_tile_gram, default), 0 popcount (k_tile_mi)
   // tensor-core path: units at least this large build their tables with k_gram_i8
   uint32_t dense_min_sites = 48, dense_min_reads = 8192;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
@@ -109,6 +110,10 @@ struct lgmi_batch {
   // tiled popcount path
   TileItem* d_tile_items = nullptr;
   uint32_t n_tile_items = 0;
+  TileItem* d_gram_tiles = nullptr;    // k_tile_gram's work items (128 x 48 site blocks)
+  uint32_t n_gram_tiles = 0;
+  uint2* d_tile_cnt = nullptr;         // its output: 24 bytes of counts per pair slot
+  uint32_t* d_tile_next = nullptr;     // its work counter
   uint32_t n_tiled_work_items = 0;     // work items (Item) of the k_tile_mi units: k_pairs_generic<true>'s
   uint32_t* d_tile_counts = nullptr;  // EMIT_COUNTS only, allocated on first use
   uint64_t n_tiled_slots = 0;
@@ -124,9 +129,23 @@ struct lgmi_batch {
   // run state
   bool uploaded = false, ran = false;
   uint32_t last_mode = 0;
-  uint64_t last_evaluated = 0;
-  uint64_t n_het_pairs_candidates = 0;
+  // candidates with a het_snp partner (what SKIP_NONHET evaluates); known once host flags have been seen
+  uint64_t n_het_candidates = 0;
+  bool het_known = false;
 };
+
+// candidate pairs next to a het_snp site, from the host copy of the flag bytes
+static uint64_t het_candidates(const std::vector<lgmi_unit_desc>& units, const uint8_t* site_flags) {
+  uint64_t tot = 0;
+  for (const lgmi_unit_desc& u : units) {
+    uint64_t h = 0;
+    for (uint32_t s = 0; s < u.n_sites; ++s)
+      h += (site_flags[u.site_off + s] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP ? 1u : 0u;
+    const uint64_t S = u.n_sites, o = S - h;
+    tot += (S >= 2 ? S * (S - 1) / 2 : 0) - (o >= 2 ? o * (o - 1) / 2 : 0);
+  }
+  return tot;
+}
 
 // --------------------------------------------------------------------------- helpers
 static inline cudaStream_t bstream(const lgmi_batch* b) { return b->own_stream ? b->own_stream : b->ctx->stream; }
@@ -231,6 +250,13 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
     return rc;
   }
   if (const char* e = getenv("LGMI_SMALL_PATH")) ctx->small_path = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("LGMI_TILE_PATH")) ctx->tile_path = atoi(e) ? 1 : 0;
+  if (cudaFuncSetAttribute(k_tile_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTgSmemBytes) != cudaSuccess) {
+    int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: k_tile_gram cannot be resident (%s)",
+                  cudaGetErrorString(cudaGetLastError()));
+    lgmi_destroy(ctx);
+    return rc;
+  }
   {
     cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &q) != cudaSuccess ||
@@ -319,6 +345,12 @@ extern "C" int lgmi_set_small_path(lgmi_t* ctx, int tensor_cores) {
   return LGMI_OK;
 }
 
+extern "C" int lgmi_set_tile_path(lgmi_t* ctx, int tensor_cores) {
+  if (!ctx) return LGMI_ERR_ARG;
+  ctx->tile_path = tensor_cores ? 1 : 0;
+  return LGMI_OK;
+}
+
 extern "C" int lgmi_set_dense_threshold(lgmi_t* ctx, uint32_t min_sites, uint32_t min_reads) {
   if (!ctx) return LGMI_ERR_ARG;
   if (min_sites < 2) return fail(ctx, LGMI_ERR_ARG, "lgmi_set_dense_threshold: min_sites must be >= 2");
@@ -360,6 +392,9 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   cudaFree(b->d_gram);
   cudaFree(b->d_tiles);
   cudaFree(b->d_tile_items);
+  cudaFree(b->d_gram_tiles);
+  cudaFree(b->d_tile_cnt);
+  cudaFree(b->d_tile_next);
   cudaFree(b->d_tile_counts);
   cudaFree(b->d_pre_items);
   cudaFree(b->d_val);
@@ -390,8 +425,9 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   uint64_t val_slots = 0;
   std::vector<MeanItem> mean_items;
   std::vector<DenseTile> dense_tiles;
-  std::vector<TileItem> tile_items;
-  std::vector<uint32_t> tile_words;  // W of each tile's unit (launch order: longest first)
+  std::vector<TileItem> tile_items, gram_tiles;
+  std::vector<uint32_t> tile_words, gram_words_of;  // W of each tile's unit (launch order: longest first)
+  bool any_gram_tiled = false;
   uint64_t dense = 0, gram_words = 0, x_bytes = 0;
   for (uint32_t k = 0; k < n_units; ++k) {
     const lgmi_unit_desc& u = units[k];
@@ -442,7 +478,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
               const uint32_t i_min = I * (uint32_t)kDenseBM;
               const uint32_t j_max = std::min(J * (uint32_t)kDenseBN + (uint32_t)kDenseBN, pl.S) - 1u;
               if (J * (uint32_t)kDenseBN >= pl.S || i_min >= j_max) continue;
-              dense_tiles.push_back(DenseTile{(uint16_t)a, (uint16_t)bb, (uint16_t)I, (uint16_t)J, 0, (uint16_t)pl.k_blocks, 0, 0});
+              dense_tiles.push_back(DenseTile{(uint8_t)a, (uint8_t)bb, (uint16_t)I, (uint16_t)J, 0, 0u, pl.k_blocks});
             }
       {
         // one CTA per SM walks the list with stride #SMs: a last, partly filled wave leaves SMs idle for a whole
@@ -458,8 +494,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
           dense_tiles.resize(dense_tiles.size() - rem);
           for (uint32_t q = 0; q < parts; ++q)
             for (DenseTile t : tail) {
-              t.kb0 = (uint16_t)((uint64_t)pl.k_blocks * q / parts);
-              t.kb1 = (uint16_t)((uint64_t)pl.k_blocks * (q + 1) / parts);
+              t.kb0 = (uint32_t)((uint64_t)pl.k_blocks * q / parts);
+              t.kb1 = (uint32_t)((uint64_t)pl.k_blocks * (q + 1) / parts);
               t.partial = 1;
               dense_tiles.push_back(t);
             }
@@ -478,17 +514,33 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       b->dense_plans.push_back(pl);
     } else if (np && !(nit == 1 && u.n_sites <= (uint32_t)kFastMaxS && u.n_reads <= (uint32_t)kFastMaxR)) {
       // tiled popcount path: MI of every pair precomputed by k_tile_mi into the dense scratch
-      d.tiled = 1;
+      // (or, by default, counted on the tensor cores by k_tile_gram and finished by k_tile_finish)
+      const bool gram = ctx->tile_path && u.n_reads >= 1u && u.n_reads <= kTgMaxReads;
+      d.tiled = gram ? 2 : 1;
       if (nit == 1) {
         d.dense_off = dense;
         dense += np;
       }
-      const uint32_t nb = (u.n_sites + (uint32_t)kTileSites - 1u) / (uint32_t)kTileSites;
-      for (uint32_t I = 0; I < nb; ++I)
-        for (uint32_t J = I; J < nb; ++J) {
-          tile_items.push_back(TileItem{k, (uint16_t)I, (uint16_t)J});
-          tile_words.push_back(u.row_words);
-        }
+      if (gram) {
+        any_gram_tiled = true;
+        const uint32_t nI = (u.n_sites + (uint32_t)kTgSitesI - 1u) / (uint32_t)kTgSitesI;
+        const uint32_t nJ = (u.n_sites + (uint32_t)kTgSitesJ - 1u) / (uint32_t)kTgSitesJ;
+        for (uint32_t I = 0; I < nI; ++I)
+          for (uint32_t J = 0; J < nJ; ++J) {
+            // some pair i < j with i in row block I and j in column block J
+            const uint32_t j_max = std::min((J + 1u) * (uint32_t)kTgSitesJ, u.n_sites) - 1u;
+            if (I * (uint32_t)kTgSitesI >= j_max) continue;
+            gram_tiles.push_back(TileItem{k, (uint16_t)I, (uint16_t)J});
+            gram_words_of.push_back(u.row_words);
+          }
+      } else {
+        const uint32_t nb = (u.n_sites + (uint32_t)kTileSites - 1u) / (uint32_t)kTileSites;
+        for (uint32_t I = 0; I < nb; ++I)
+          for (uint32_t J = I; J < nb; ++J) {
+            tile_items.push_back(TileItem{k, (uint16_t)I, (uint16_t)J});
+            tile_words.push_back(u.row_words);
+          }
+      }
     }
     if (nit > 1) {
       d.dense_off = dense;
@@ -500,7 +552,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       it.unit = k;
       it.pair_begin = t * (uint32_t)kPairsMax;
       it.pair_cnt = (uint32_t)std::min<uint64_t>(kPairsMax, np - (uint64_t)t * kPairsMax);
-      it.flags = (t == 0 ? ITEM_FIRST : 0u) | (nit == 1 ? ITEM_SINGLE : 0u) | (d.tiled ? ITEM_TILED : 0u);
+      it.flags = (t == 0 ? ITEM_FIRST : 0u) | (nit == 1 ? ITEM_SINGLE : 0u) | (d.tiled ? ITEM_TILED : 0u) |
+                 (d.tiled == 2 ? ITEM_TILED_GRAM : 0u);
       if (d.tiled) ++b->n_tiled_work_items;
       if (nit == 1 && np >= 1 && u.n_sites <= (uint32_t)kFastMaxS && u.n_reads <= (uint32_t)kFastMaxR) {
         it.flags |= ITEM_FAST;
@@ -525,16 +578,19 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       b->h_items.push_back(it);
     }
   }
-  {
+  auto deepest_first = [](std::vector<TileItem>& items, const std::vector<uint32_t>& words) {
     // the deepest tiles first: CTAs are handed out in order, so the long ones do not end up in the tail
-    std::vector<uint32_t> order(tile_items.size());
+    std::vector<uint32_t> order(items.size());
     for (uint32_t t = 0; t < order.size(); ++t) order[t] = t;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return tile_words[x] > tile_words[y]; });
-    std::vector<TileItem> sorted(tile_items.size());
-    for (uint32_t t = 0; t < order.size(); ++t) sorted[t] = tile_items[order[t]];
-    tile_items.swap(sorted);
-  }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return words[x] > words[y]; });
+    std::vector<TileItem> sorted(items.size());
+    for (uint32_t t = 0; t < order.size(); ++t) sorted[t] = items[order[t]];
+    items.swap(sorted);
+  };
+  deepest_first(tile_items, tile_words);
+  deepest_first(gram_tiles, gram_words_of);
   b->n_tile_items = (uint32_t)tile_items.size();
+  b->n_gram_tiles = (uint32_t)gram_tiles.size();
 
   b->n_items = (uint32_t)b->h_items.size();
   b->n_fast = (uint32_t)fast_items.size();
@@ -585,6 +641,13 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
     BCU(cudaMemcpyAsync(b->d_tile_items, tile_items.data(), tile_items.size() * sizeof(TileItem), cudaMemcpyHostToDevice,
                         bstream(b)));
   }
+  BCU(cudaMalloc(&b->d_tile_next, sizeof(uint32_t)));
+  if (!gram_tiles.empty()) {
+    BCU(cudaMalloc(&b->d_gram_tiles, gram_tiles.size() * sizeof(TileItem)));
+    BCU(cudaMemcpyAsync(b->d_gram_tiles, gram_tiles.data(), gram_tiles.size() * sizeof(TileItem), cudaMemcpyHostToDevice,
+                        bstream(b)));
+  }
+  if (any_gram_tiled) BCU(cudaMalloc(&b->d_tile_cnt, std::max<uint64_t>(1, dense) * 3ull * sizeof(uint2)));
   if (!b->dense_plans.empty()) {
     BCU(cudaMalloc(&b->d_x, x_bytes));
     BCU(cudaMemsetAsync(b->d_x, 0, x_bytes, bstream(b)));  // rows of the site padding stay zero
@@ -646,6 +709,8 @@ extern "C" int lgmi_batch_upload(lgmi_batch_t* b, const uint32_t* planes, const 
     CU(ctx, cudaMemcpyAsync(b->d_planes, planes, b->plane_words * sizeof(uint32_t), cudaMemcpyHostToDevice, bstream(b)));
   if (b->n_sites)
     CU(ctx, cudaMemcpyAsync(b->d_flags, site_flags, b->n_sites, cudaMemcpyHostToDevice, bstream(b)));
+  b->n_het_candidates = b->n_sites ? het_candidates(b->h_units, site_flags) : 0;
+  b->het_known = true;
   b->uploaded = true;
   return LGMI_OK;
 }
@@ -665,7 +730,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     CU(ctx, cudaMalloc(&b->d_counts, b->rec_cap * 9ull * sizeof(uint32_t)));
     b->counts_cap = b->rec_cap;
   }
-  if ((mode & LGMI_MODE_EMIT_COUNTS) && b->n_tile_items && !b->d_tile_counts) {
+  if ((mode & LGMI_MODE_EMIT_COUNTS) && (b->n_tile_items || b->n_gram_tiles) && !b->d_tile_counts) {
     CU(ctx, cudaStreamSynchronize(bstream(b)));
     CU(ctx, cudaMalloc(&b->d_tile_counts, std::max<uint64_t>(1, b->n_dense) * 9ull * sizeof(uint32_t)));
   }
@@ -705,7 +770,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
                                                                   b->d_item_dense, b->n_items, b->d_n_generic,
                                                                   b->n_items - b->n_fast - b->n_pre - b->n_tiled_work_items, b->d_site_mean,
                                                                   b->d_site_cnt,
-                                                                  b->n_sites);
+                                                                  b->n_sites, b->d_tile_next);
     ++ctx->launches;
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[4], bstream(b)));
@@ -739,6 +804,25 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
     // K1 + K2 of the medium units: counts + MI per 16 x 16 block of site pairs
     const unsigned tgrid = (unsigned)std::min<uint64_t>(b->n_tile_items, (uint64_t)ctx->num_sms * 3u);
     k_tile_mi<<<tgrid, kThreads, 0, bstream(b)>>>(P, b->d_tile_items, b->n_tile_items);
+    ++ctx->launches;
+  }
+  if (b->n_gram_tiles) {
+    // K1 of the medium units on the tensor cores (batched, bits expanded in the kernel), then K2 per pair
+    TileGramParams T;
+    T.units = b->d_units;
+    T.planes = b->d_planes;
+    T.site_flags = b->d_flags;
+    T.mode = mode;
+    T.tiles = b->d_gram_tiles;
+    T.n_tiles = b->n_gram_tiles;
+    T.cnt = b->d_tile_cnt;
+    T.next = b->d_tile_next;
+    T.error = reinterpret_cast<uint32_t*>(&b->d_header->pad);
+    const unsigned ggrid = (unsigned)std::min<uint32_t>(b->n_gram_tiles, (uint32_t)ctx->num_sms);
+    k_tile_gram<<<ggrid, kTgThreads, kTgSmemBytes, bstream(b)>>>(T);
+    ++ctx->launches;
+    const unsigned fgrid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 8u);
+    k_tile_finish<<<fgrid, kThreads, 0, bstream(b)>>>(P, b->d_tile_cnt);
     ++ctx->launches;
   }
   if (b->n_pre) {
@@ -834,7 +918,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   if (timing) CU(ctx, cudaEventRecord(b->ev[3], bstream(b)));
   if (b->n_items) {
     // everything the small-unit kernel does not take; exits at once when there is nothing
-    if (b->n_tile_items) {  // ordering + emission of what k_tile_mi computed
+    if (b->n_tile_items || b->n_gram_tiles) {  // ordering + emission of what k_tile_mi / k_tile_finish computed
       const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
       k_pairs_generic<true><<<grid, kThreads, 0, bstream(b)>>>(P);
       ++ctx->launches;
@@ -852,7 +936,6 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   CU(ctx, cudaGetLastError());
   b->ran = true;
   b->last_mode = mode;
-  b->last_evaluated = b->n_candidates;  // refined on the host in sync for SKIP_NONHET
   return LGMI_OK;
 }
 
@@ -860,7 +943,9 @@ static int fill_scalars(lgmi_batch* b, lgmi_result* out) {
   lgmi_ctx* ctx = b->ctx;
   memset(out, 0, sizeof *out);
   out->n_candidates = b->n_candidates;
-  out->n_evaluated = b->n_candidates;
+  // SKIP_NONHET evaluates only the candidates next to a het_snp (counted from the host flags; a caller that
+  // filled the device buffers itself gets n_candidates)
+  out->n_evaluated = ((b->last_mode & LGMI_MODE_SKIP_NONHET) && b->het_known) ? b->n_het_candidates : b->n_candidates;
   out->n_records = b->h_header->n_records;
   out->n_sites = b->n_sites;
   float ms = 0.f;
@@ -882,7 +967,7 @@ static int fill_scalars(lgmi_batch* b, lgmi_result* out) {
   out->n_dense_units = (uint32_t)b->dense_plans.size();
   out->dense_macs = b->dense_macs;
   if (b->h_header->pad)
-    return fail(ctx, LGMI_ERR_CUDA, "k_gram_i8: a pipeline barrier timed out (tensor-core path)");
+    return fail(ctx, LGMI_ERR_CUDA, "k_gram_i8 / k_tile_gram: a pipeline barrier timed out (tensor-core path)");
   return LGMI_OK;
 }
 
@@ -953,6 +1038,7 @@ extern "C" int lgmi_batch_device_ptrs(lgmi_batch_t* b, void** d_planes, void** d
   if (d_records) *d_records = b->d_records;
   if (d_site_mean) *d_site_mean = b->d_site_mean;
   b->uploaded = true;  // a device-resident caller fills the buffers itself
+  b->het_known = false;
   return LGMI_OK;
 }
 
@@ -1168,6 +1254,10 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
       ++ctx->launches;
     }
     b->uploaded = true;
+    if (mode & LGMI_MODE_SKIP_NONHET) {
+      b->n_het_candidates = b->n_sites ? het_candidates(b->h_units, site_flags + c.site0) : 0;
+      b->het_known = true;
+    }
     if (!rc) rc = lgmi_batch_run(b, min_common, mode);
     if (rc) return rc;
     if (split) {
@@ -1236,7 +1326,7 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
   }
   memset(out, 0, sizeof *out);
   out->n_candidates = p->n_candidates;
-  out->n_evaluated = p->n_candidates;
+  out->n_evaluated = 0;
   out->n_records = base;
   out->records = split ? nullptr : p->h_records;
   out->rec_mi = split ? p->h_rec_mi : nullptr;
@@ -1250,6 +1340,7 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
     lgmi_result r;
     int rc = fill_scalars(c.b, &r);
     if (rc) return rc;
+    out->n_evaluated += r.n_evaluated;
     out->kernel_ms += r.kernel_ms;
     out->pairs_kernel_ms += r.pairs_kernel_ms;
     out->dense_kernel_ms += r.dense_kernel_ms;
@@ -1365,6 +1456,33 @@ extern "C" int lgmi_ecdf(lgmi_t* ctx, const double* mean, const uint8_t* site_fl
   return LGMI_OK;
 }
 
+// sorts x on the device (NaNs canonicalised: last, as numpy.sort leaves them); d_sorted / d_nan are in the scratch
+static int ecdf_sort(lgmi_ctx* ctx, const double* x, uint64_t n, size_t extra_bytes, char** scratch, double** d_sorted,
+                     unsigned long long** d_nan) {
+  size_t sort_bytes = 0;
+  CU(ctx, cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const double*)nullptr, (double*)nullptr, (int)n, 0, 64,
+                                        ctx->stream));
+  const size_t a_x = 0;
+  const size_t a_sorted = align_up(a_x + n * 8, 256);
+  const size_t a_nan = align_up(a_sorted + n * 8, 256);
+  const size_t a_tmp = align_up(a_nan + 8, 256);
+  const size_t a_extra = align_up(a_tmp + sort_bytes, 256);
+  int rc = ensure_scratch(ctx, a_extra + extra_bytes);
+  if (rc) return rc;
+  char* p = static_cast<char*>(ctx->d_scratch);
+  double* d_x = reinterpret_cast<double*>(p + a_x);
+  *d_sorted = reinterpret_cast<double*>(p + a_sorted);
+  *d_nan = reinterpret_cast<unsigned long long*>(p + a_nan);
+  *scratch = p + a_extra;
+  CU(ctx, cudaMemcpyAsync(d_x, x, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemsetAsync(*d_nan, 0, 8, ctx->stream));
+  k_canon_nan<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_x, n, *d_nan);
+  ++ctx->launches;
+  CU(ctx, cub::DeviceRadixSort::SortKeys(p + a_tmp, sort_bytes, d_x, *d_sorted, (int)n, 0, 64, ctx->stream));
+  ++ctx->launches;
+  return LGMI_OK;
+}
+
 extern "C" int lgmi_ecdf_eval(lgmi_t* ctx, const double* x, uint64_t n, const double* samples, uint64_t m,
                               double* out) {
   if (!ctx || (n && !x) || (m && (!samples || !out))) return fail(ctx, LGMI_ERR_ARG, "lgmi_ecdf_eval: NULL argument");
@@ -1372,31 +1490,46 @@ extern "C" int lgmi_ecdf_eval(lgmi_t* ctx, const double* x, uint64_t n, const do
   if (m == 0) return LGMI_OK;
   if (n > 0x7fffffffull) return fail(ctx, LGMI_ERR_UNSUPPORTED, "lgmi_ecdf_eval: more than 2^31-1 values");
   CU(ctx, cudaSetDevice(ctx->device));
-  size_t sort_bytes = 0;
-  CU(ctx, cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const double*)nullptr, (double*)nullptr, (int)n, 0, 64,
-                                        ctx->stream));
-  const size_t a_x = 0;
-  const size_t a_sorted = align_up(a_x + n * 8, 256);
-  const size_t a_s = align_up(a_sorted + n * 8, 256);
-  const size_t a_o = align_up(a_s + m * 8, 256);
-  const size_t a_tmp = align_up(a_o + m * 8, 256);
-  int rc = ensure_scratch(ctx, a_tmp + sort_bytes);
+  char* extra = nullptr;
+  double* d_sorted = nullptr;
+  unsigned long long* d_nan = nullptr;
+  const size_t a_o = align_up(m * 8, 256);
+  int rc = ecdf_sort(ctx, x, n, a_o + m * 8, &extra, &d_sorted, &d_nan);
   if (rc) return rc;
-  char* p = static_cast<char*>(ctx->d_scratch);
-  double* d_x = reinterpret_cast<double*>(p + a_x);
-  double* d_sorted = reinterpret_cast<double*>(p + a_sorted);
-  double* d_s = reinterpret_cast<double*>(p + a_s);
-  double* d_o = reinterpret_cast<double*>(p + a_o);
-  CU(ctx, cudaMemcpyAsync(d_x, x, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  double* d_s = reinterpret_cast<double*>(extra);
+  double* d_o = reinterpret_cast<double*>(extra + a_o);
   CU(ctx, cudaMemcpyAsync(d_s, samples, m * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU(ctx, cub::DeviceRadixSort::SortKeys(p + a_tmp, sort_bytes, d_x, d_sorted, (int)n, 0, 64, ctx->stream));
-  ++ctx->launches;
-  k_ecdf_eval<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(d_sorted, n, d_s, m, d_o);
+  k_ecdf_eval<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(d_sorted, n, d_nan, d_s, m, d_o);
   ++ctx->launches;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(out, d_o, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return LGMI_OK;
+}
+
+extern "C" int lgmi_ecdf_table(lgmi_t* ctx, const double* x, uint64_t n, double* sorted_out, double* y_out) {
+  if (!ctx || (n && (!x || !sorted_out)) || !y_out) return fail(ctx, LGMI_ERR_ARG, "lgmi_ecdf_table: NULL argument");
+  if (n == 0) return fail(ctx, LGMI_ERR_ARG, "lgmi_ecdf_table: empty x (the reference divides by len(x))");
+  if (n > 0x7fffffffull) return fail(ctx, LGMI_ERR_UNSUPPORTED, "lgmi_ecdf_table: more than 2^31-1 values");
+  CU(ctx, cudaSetDevice(ctx->device));
+  char* extra = nullptr;
+  double* d_sorted = nullptr;
+  unsigned long long* d_nan = nullptr;
+  int rc = ecdf_sort(ctx, x, n, (n + 1) * 8, &extra, &d_sorted, &d_nan);
+  if (rc) return rc;
+  double* d_y = reinterpret_cast<double*>(extra);
+  k_ecdf_ordinates<<<(unsigned)((n + 256) / 256), 256, 0, ctx->stream>>>(n, d_y);
+  ++ctx->launches;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(sorted_out, d_sorted, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(y_out, d_y, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LGMI_OK;
+}
+
+extern "C" int lgmi_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
 
 // --------------------------------------------------------------------------- partitioning

@@ -38,12 +38,13 @@ constexpr uint32_t kDenseSmemBytes = kDenseStages * kDenseStageBytes + 1024 /*al
 constexpr uint32_t kDenseTmemCols = 256;
 
 struct DenseTile {
-  uint16_t a, b;      // planes (label order: 0 other, 1 minor, 2 major)
+  uint8_t a, b;       // planes (label order: 0 other, 1 minor, 2 major)
   uint16_t I, J;      // site blocks: rows [128 I, +128), columns [256 J, +256)
-  uint16_t kb0, kb1;  // k-blocks [kb0, kb1) of this work item
   uint16_t partial;   // 1: the tile's K range is shared by several items (last wave): results are added atomically
-  uint16_t pad;       //    into a zeroed tile
+                      //    into a zeroed tile
+  uint32_t kb0, kb1;  // k-blocks [kb0, kb1) of this work item (32 bits: a unit may have millions of reads)
 };
+static_assert(sizeof(DenseTile) == 16, "DenseTile layout");
 
 struct DenseParams {
   const DenseTile* tiles;

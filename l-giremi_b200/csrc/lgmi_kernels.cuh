@@ -34,13 +34,14 @@ struct DevUnit {
   uint32_t S, R, W, site_off;
   uint32_t first_item, n_items;
   uint32_t S_pad;
-  uint32_t tiled;      // 1: MI of every pair is precomputed into the dense scratch by k_tile_mi
+  uint32_t tiled;      // MI of every pair is precomputed into the dense scratch: 1 by k_tile_mi, 2 by k_tile_gram + k_tile_finish
 };
 constexpr uint64_t kNoGram = ~0ull;
 
 enum : uint32_t {
   ITEM_FIRST = 1u, ITEM_SINGLE = 2u, ITEM_FAST = 4u, ITEM_PRE = 8u /* counted by k_small_gram */,
-  ITEM_TILED = 16u /* MI precomputed by k_tile_mi */
+  ITEM_TILED = 16u /* MI precomputed by k_tile_mi or k_tile_gram + k_tile_finish */,
+  ITEM_TILED_GRAM = 32u /* ... by the latter, which also counts the item's emitted pairs */
 };
 
 struct Item {
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
   const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
   for (uint32_t item_idx = blockIdx.x; item_idx < P.n_items; item_idx += gridDim.x) {
     const Item it = P.items[item_idx];
-    if (it.flags & (ITEM_PRE | ITEM_FAST)) continue;  // counted by k_small_gram / k_count_fast
+    if (it.flags & (ITEM_PRE | ITEM_FAST | ITEM_TILED_GRAM)) continue;  // counted by k_small_gram / k_count_fast / k_tile_finish
     const DevUnit u = P.units[it.unit];
     const uint8_t* __restrict__ flags = P.site_flags + u.site_off;
     uint32_t mine = 0;
@@ -801,12 +802,14 @@ __global__ void __launch_bounds__(256) k_split_records(const Header* __restrict_
 __global__ void k_run_init(Header* __restrict__ header, Header* __restrict__ host_header,
                            unsigned long long* __restrict__ unit_rec_off, uint32_t n_off,
                            uint8_t* __restrict__ item_dense, uint32_t n_items, uint32_t* __restrict__ n_generic,
-                           uint32_t n_generic0, double* __restrict__ mean, uint32_t* __restrict__ cnt, uint64_t n_sites) {
+                           uint32_t n_generic0, double* __restrict__ mean, uint32_t* __restrict__ cnt, uint64_t n_sites,
+                           uint32_t* __restrict__ tile_next) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k == 0) {
     header->n_records = 0ull;
     header->pad = 0ull;
     *n_generic = n_generic0;
+    *tile_next = 0u;  // k_tile_gram's work counter
     if (host_header) {  // pinned host memory (unified addressing): the pipelined step reads the count from there
       host_header->n_records = 0ull;
       host_header->pad = 0ull;
@@ -888,15 +891,37 @@ __global__ void k_ecdf_mip(const double* __restrict__ mean, const uint8_t* __res
   if (call) call[k] = c;
 }
 
-// ecdf(x)(samples) with x already sorted on the device
-__global__ void k_ecdf_eval(const double* __restrict__ sorted_x, uint64_t n,
+// numpy.sort puts every NaN last whatever its sign or payload; the radix sort orders by bit pattern,
+// so NaNs become the canonical quiet NaN (sorts after +inf) first.  Counts them.
+__global__ void k_canon_nan(double* __restrict__ x, uint64_t n, unsigned long long* __restrict__ n_nan) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool nan = false;
+  if (k < n) {
+    nan = isnan(x[k]);
+    if (nan) x[k] = lg_nan();
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, nan);
+  if ((threadIdx.x & 31u) == 0 && bal) atomicAdd(n_nan, (unsigned long long)__popc(bal));
+}
+
+// ecdf(x)(samples) with x already sorted on the device (NaNs, if any, at the end)
+__global__ void k_ecdf_eval(const double* __restrict__ sorted_x, uint64_t n, const unsigned long long* __restrict__ n_nan,
                             const double* __restrict__ samples, uint64_t m, double* __restrict__ out) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m) return;
   const double v = samples[k];
-  // np.searchsorted places NaN after everything (NaN sorts last)
-  const uint64_t idx = isnan(v) ? n : lower_bound(sorted_x, n, v);
+  // np.searchsorted orders NaN after everything: a NaN sample lands on the first NaN of x (or at the end)
+  const uint64_t n_num = n - *n_nan;
+  const uint64_t idx = isnan(v) ? n_num : lower_bound(sorted_x, n_num, v);
   out[k] = lg_ecdf_y(idx, n);
 }
 
+// the ECDF ordinates y = [0] ++ linspace(1/n, 1, n) of stat.py:19, all n + 1 of them
+__global__ void k_ecdf_ordinates(uint64_t n, double* __restrict__ y) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= n) y[k] = lg_ecdf_y(k, n);
+}
+
 }  // namespace lgmi
+
+#include "lgmi_tilegram.cuh"

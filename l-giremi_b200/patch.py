@@ -26,14 +26,18 @@ _BATCHED_TARGETS = (
     ("giremi.mismatch", "region_mismatch_analysis"),
     ("giremi.script.giremi", "region_mismatch_analysis"),
     ("giremi.script.giremi", "footprint_bulk_calculation"),
+    ("giremi.script.giremi", "main"),
 )
 
 
 def install(batched=False):
     """Replace the reference's bindings in every giremi module already imported.
-    With batched=True also `region_mismatch_analysis` (mismatch.py:345) and the CLI's
-    `footprint_bulk_calculation` (giremi.py:20), so that each chunk of footprints is
-    one GPU submit.  Returns the list of (module, name) actually patched."""
+    With batched=True also `region_mismatch_analysis` (mismatch.py:345), the CLI's
+    `footprint_bulk_calculation` (giremi.py:20) -- each chunk of footprints one GPU submit --
+    and the CLI's `main` (giremi.py:324): workers extract, the parent owns every GPU and runs
+    the mip pass in one launch.  Callers that hold their own reference to the stock `main`
+    keep it (it then runs the patched per-chunk function in its workers).  Returns the list of
+    (module, name) actually patched."""
     from . import api, batched as batched_mod
     done = []
     todo = [(m, a, api) for m, a in _TARGETS]

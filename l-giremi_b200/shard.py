@@ -15,6 +15,7 @@ import numpy as np
 from ._lib import PAIR_REC
 from .api import partition_lpt, unit_costs
 from .encode import PlaneBatch
+from .multigpu import MergedResult, merge_shards  # noqa: F401  (MergedResult: rank 0's view after the gather)
 
 
 def plan(units, world_size):
@@ -27,18 +28,6 @@ def local_shard(pb: PlaneBatch, rank, world_size):
     bin_of, _ = plan(pb.units, world_size)
     index = np.nonzero(bin_of == rank)[0]
     return pb.subset(index), index
-
-
-class MergedResult:
-    """Rank 0's view after the gather: same fields as api.StepResult, global order."""
-
-    def __init__(self, records, site_mean, site_cnt, unit_rec_off, n_candidates):
-        self.records, self.site_mean, self.site_cnt = records, site_mean, site_cnt
-        self.unit_rec_off, self.n_candidates = unit_rec_off, n_candidates
-        self.n_records = len(records)
-
-    def unit_records(self, unit):
-        return self.records[int(self.unit_rec_off[unit]):int(self.unit_rec_off[unit + 1])]
 
 
 def _gather_bytes(buf: np.ndarray, dst, group, device):
@@ -82,34 +71,12 @@ def gather_to_rank0(pb_global: PlaneBatch, local_result, local_index, group=None
     gathered = [_gather_bytes(p, 0, group, device) for p in payloads]
     if rank != 0:
         return None
-    units = pb_global.units
-    n_units = len(units)
-    n_sites = pb_global.n_sites
-    site_mean = np.full(n_sites, np.nan)
-    site_cnt = np.zeros(n_sites, dtype=np.uint32)
-    per_unit_count = np.zeros(n_units, dtype=np.int64)
-    pieces = []
+    parts = []
     for r in range(world):
-        recs = gathered[0][r].view(PAIR_REC)
-        mean = gathered[1][r].view(np.float64)
-        cnt = gathered[2][r].view(np.uint32)
-        off = gathered[3][r].view(np.uint64).astype(np.int64)
+        off = gathered[3][r].view(np.uint64)
         index = gathered[4][r].view(np.int64)
         assert len(off) == len(index) + 1
-        per_unit_count[index] = np.diff(off)
-        local_site = 0
-        for k, g in enumerate(index.tolist()):
-            s0, ns = int(units['site_off'][g]), int(units['n_sites'][g])
-            site_mean[s0:s0 + ns] = mean[local_site:local_site + ns]
-            site_cnt[s0:s0 + ns] = cnt[local_site:local_site + ns]
-            local_site += ns
-        recs = recs.copy()
-        recs['unit'] = index[recs['unit']] if len(recs) else recs['unit']
-        pieces.append(recs)
-    records = np.concatenate(pieces) if pieces else np.zeros(0, PAIR_REC)
-    # ranks hold ascending global indices and emit in (unit, i, j) order, so a stable sort by unit suffices
-    records = records[np.argsort(records['unit'], kind='stable')]
-    unit_rec_off = np.zeros(n_units + 1, dtype=np.uint64)
-    unit_rec_off[1:] = np.cumsum(per_unit_count)
-    s = units['n_sites'].astype(np.int64)
-    return MergedResult(records, site_mean, site_cnt, unit_rec_off, int((s * (s - 1) // 2).sum()))
+        parts.append((index, gathered[0][r].view(PAIR_REC), gathered[1][r].view(np.float64),
+                      gathered[2][r].view(np.uint32), off, None))
+    # ranks hold ascending global indices and emit in (unit, i, j) order: the merge is index bookkeeping
+    return merge_shards(pb_global.units, pb_global.n_sites, parts)

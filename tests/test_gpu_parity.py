@@ -255,6 +255,31 @@ def test_many_sites_multi_item_unit(lg, gpu_ctx):
     check_batch(lg, gpu_ctx, [small, eu, small], 6)
 
 
+def test_mid_units_popcount_and_tensor_paths_agree(lg, gpu_ctx):
+    """Mid-depth units (more than 64 sites or 256 reads): k_tile_gram + k_tile_finish (tcgen05, default) and
+    k_tile_mi (popcount) must give the same records, tables and means bit for bit, and both match the oracle.
+    Shapes straddle the 128-site row blocks, the 48-site column blocks and the 128-read k-blocks."""
+    rng = np.random.default_rng(20261031)
+    shapes = [(65, 40), (48, 257), (49, 300), (129, 129), (97, 1000), (2, 700), (3, 4097), (257, 70), (200, 385),
+              (145, 128), (64, 9000)]
+    eus = [_synth_unit(rng, S, R, cov) for (S, R), cov in zip(shapes, [0.5, 0.3, 0.7, 0.5, 0.2, 1.0, 0.6, 0.4, 0.5, 0.9, 0.3])]
+    eus.insert(3, enc.EncodedUnit([1, 2, 3], ['het_snp', 'mismatch', 'snp'], eus[0].labels[:3, :30]))   # a small unit between
+    pb = lg.pack_units(eus)
+    out = {}
+    try:
+        for tensor in (True, False):
+            gpu_ctx.set_tile_path(tensor)
+            full = check_batch(lg, gpu_ctx, eus, 6, min_exact=0.9)
+            het = lg.mi_step_batched(pb, 9, lg.MODE_HET_ONLY | lg.MODE_SKIP_NONHET | lg.MODE_EMIT_COUNTS, ctx=gpu_ctx)
+            out[tensor] = (full, het)
+    finally:
+        gpu_ctx.set_tile_path(True)
+    for a, b in zip(out[True], out[False]):
+        assert np.array_equal(a.records, b.records) and np.array_equal(a.counts, b.counts)
+        assert np.array_equal(a.site_mean, b.site_mean, equal_nan=True) and np.array_equal(a.site_cnt, b.site_cnt)
+        assert np.array_equal(a.unit_rec_off, b.unit_rec_off)
+
+
 # --------------------------------------------------------------------------- tensor-core path (K3)
 def _synth_unit(rng, S, R, cov):
     a, k = synth.draw_alleles(rng, 1, S, R, cov)

@@ -110,3 +110,28 @@ def test_single_rank_shard_is_identity(lg):
     local, index = shard.local_shard(pb, 0, 1)
     assert index.tolist() == list(range(pb.n_units))
     assert np.array_equal(local.planes, pb.planes) and np.array_equal(local.units, pb.units)
+
+
+def test_merge_shards_in_process_three_shards_one_empty(lg):
+    """multigpu.merge_shards (what the parent-owned DevicePool and the gather both use) on three
+    shards, one of them empty, with the 3x3 tables riding along."""
+    mg = importlib.import_module("l-giremi_b200.multigpu")
+    pb, labels = make_world()
+    want = oracle_step(pb, labels, 6)
+    bin_of, _ = lg.partition_lpt(lg.unit_costs(pb.units), 2)
+    parts = []
+    for k in (0, 1, 2):
+        index = np.flatnonzero(bin_of == k)                 # shard 2 is empty
+        res = oracle_step(pb.subset(index), [labels[g] for g in index], 6)
+        counts = np.repeat(np.arange(len(res.records), dtype=np.uint32)[:, None] * 10 + k, 9, axis=1)
+        parts.append((index, res.records, res.site_mean, res.site_cnt, res.unit_rec_off, counts))
+    got = mg.merge_shards(pb.units, pb.n_sites, parts)
+    assert np.array_equal(got.records, want.records)
+    assert np.array_equal(got.site_mean, want.site_mean, equal_nan=True) and np.array_equal(got.site_cnt, want.site_cnt)
+    assert np.array_equal(got.unit_rec_off, want.unit_rec_off) and got.n_candidates == pb.n_candidates
+    # every unit's table rows came from the shard that owns the unit, in the shard's row order
+    for u in range(pb.n_units):
+        c = got.unit_counts(u)
+        assert len(c) == len(got.unit_records(u))
+        if len(c):
+            assert (c[:, 0] % 10 == bin_of[u]).all() and (np.diff(c[:, 0] // 10) == 1).all()
