@@ -110,6 +110,22 @@ typedef struct {
                                    /* `records` NULL; the unit of a row follows */
                                    /* from unit_rec_off                         */
 
+#define LGMI_MODE_TIGHT_INPUT 0x20u /* lgmi_pipeline_step_packed: the two-plane     */
+                                   /* rows are ceil(R/32) words wide instead of W, */
+                                   /* units back to back (no 128-read padding on   */
+                                   /* the wire)                                    */
+#define LGMI_MODE_COMPACT_OUTPUT 0x40u /* lgmi_pipeline_step*: split rows (as       */
+                                   /* SPLIT_RECORDS) with 2-byte (i, j) entries    */
+                                   /* when no unit has more than 256 sites, and no */
+                                   /* per-site count (site_cnt NULL: it is the     */
+                                   /* number of rows a site appears in)            */
+#define LGMI_MODE_GRAPH 0x10u       /* lgmi_batch_run: replay the launch chain as   */
+                                   /* one CUDA graph (captured on first use per    */
+                                   /* (min_common, mode)); the per-kernel times of */
+                                   /* lgmi_result are then 0.  Groups of a         */
+                                   /* pipelined step always run this way           */
+                                   /* (LGMI_GRAPHS=0 in the environment: never)    */
+
 /* one emitted pair == one row [p1,type1,p2,type2,mi] of                       *
  * mutual_information.py:42-44; i<j index the unit's sorted positions.         */
 typedef struct {
@@ -150,10 +166,12 @@ typedef struct {
   uint32_t n_dense_units;       /* units that took the tensor-core path        */
   uint64_t dense_macs;          /* int8 multiply-accumulates issued for them   */
   float gram_kernel_ms;         /* k_gram_i8 of the last such unit, alone      */
-  uint32_t reserved;
+  uint32_t rec_ij_bytes;        /* width of a rec_ij entry: 4, or 2 (see below)*/
   uint64_t gram_macs;           /* multiply-accumulates of that launch         */
   const double* rec_mi;         /* LGMI_MODE_SPLIT_RECORDS: MI of every row    */
-  const uint32_t* rec_ij;       /* ... and its i | j << 16                     */
+  const uint32_t* rec_ij;       /* ... and its i | j << 16; under              */
+                                /* LGMI_MODE_COMPACT_OUTPUT with no unit above */
+                                /* 256 sites an array of uint16: i | j << 8    */
 } lgmi_result;
 
 typedef struct lgmi_ctx lgmi_t;

@@ -31,6 +31,9 @@ MODE_HET_ONLY = 0x1
 MODE_EMIT_COUNTS = 0x2
 MODE_SKIP_NONHET = 0x4
 MODE_SPLIT_RECORDS = 0x8
+MODE_GRAPH = 0x10
+MODE_TIGHT_INPUT = 0x20
+MODE_COMPACT_OUTPUT = 0x40
 
 ERR_NODEVICE = -5
 DENSE_DEFAULT = (48, 8192)    # lgmi_set_dense_threshold defaults: (min_sites, min_reads)
@@ -65,7 +68,7 @@ class Result(C.Structure):
         ("n_dense_units", C.c_uint32),
         ("dense_macs", C.c_uint64),
         ("gram_kernel_ms", C.c_float),
-        ("reserved", C.c_uint32),
+        ("rec_ij_bytes", C.c_uint32),
         ("gram_macs", C.c_uint64),
         ("rec_mi", C.c_void_p),
         ("rec_ij", C.c_void_p),

@@ -17,7 +17,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (MODE_ALL_PAIRS, MODE_EMIT_COUNTS, MODE_HET_ONLY, MODE_SKIP_NONHET, MODE_SPLIT_RECORDS,
+from ._lib import (MODE_ALL_PAIRS, MODE_COMPACT_OUTPUT, MODE_EMIT_COUNTS, MODE_HET_ONLY, MODE_GRAPH, MODE_SKIP_NONHET,
+                   MODE_SPLIT_RECORDS, MODE_TIGHT_INPUT,
                    PAIR_REC, SITE_TYPE_CODE, LgmiError, Result, array_at, check, ptr)
 from .encode import EncodedUnit, PlaneBatch, encode_batch, encode_mismatches, pack_units
 
@@ -143,20 +144,37 @@ class StepResult:
         self.rec_mi = self.rec_ij = None
         if not res.records and res.rec_mi:                   # MODE_SPLIT_RECORDS: two arrays instead of 16-byte rows
             self.rec_mi = array_at(res.rec_mi, np.float64, self.n_records)
-            self.rec_ij = array_at(res.rec_ij, np.uint32, self.n_records)
+            # (i | j << 16 as uint32, or -- MODE_COMPACT_OUTPUT, no unit above 256 sites -- i | j << 8 as uint16)
+            self.rec_ij = array_at(res.rec_ij, np.uint16 if int(res.rec_ij_bytes) == 2 else np.uint32, self.n_records)
             if copy:
                 self.rec_mi, self.rec_ij = self.rec_mi.copy(), self.rec_ij.copy()
             rec = None
         else:
             rec = array_at(res.records, PAIR_REC, self.n_records)
         mean = array_at(res.site_mean, np.float64, int(res.n_sites))
-        cnt = array_at(res.site_cnt, np.uint32, int(res.n_sites))
+        cnt = array_at(res.site_cnt, np.uint32, int(res.n_sites)) if res.site_cnt else None
         counts = array_at(res.counts, np.uint32, self.n_records * 9).reshape(-1, 9) if res.counts else None
         if copy:
             rec = rec.copy() if rec is not None else None
-            mean, cnt, off = mean.copy(), cnt.copy(), off.copy()
+            mean, off = mean.copy(), off.copy()
+            cnt = cnt.copy() if cnt is not None else None
             counts = counts.copy() if counts is not None else None
-        self._records, self.site_mean, self.site_cnt, self.unit_rec_off, self.counts = rec, mean, cnt, off, counts
+        self._records, self.site_mean, self._site_cnt, self.unit_rec_off, self.counts = rec, mean, cnt, off, counts
+        self._site_off = None                                # per-unit first site: set by the owner of the unit table
+
+    @property
+    def site_cnt(self):
+        """Rows each site appears in.  Not shipped under MODE_COMPACT_OUTPUT: then counted here from the
+        rows (needs the unit table's site offsets, which Pipeline.step attaches)."""
+        if self._site_cnt is None:
+            if self._site_off is None:
+                raise ValueError("site_cnt was not downloaded (MODE_COMPACT_OUTPUT) and the unit table is unknown")
+            rec = self.records
+            base = self._site_off[rec['unit']]
+            n = len(self.site_mean)
+            self._site_cnt = (np.bincount(base + rec['i'], minlength=n) +
+                              np.bincount(base + rec['j'], minlength=n)).astype(np.uint32)
+        return self._site_cnt
 
     @property
     def records(self):
@@ -165,8 +183,10 @@ class StepResult:
         if self._records is None:
             rec = np.empty(self.n_records, dtype=PAIR_REC)
             rec['mi'] = self.rec_mi
-            rec['i'] = self.rec_ij & 0xffff
-            rec['j'] = self.rec_ij >> 16
+            if self.rec_ij.dtype == np.uint16:
+                rec['i'], rec['j'] = self.rec_ij & 0xff, self.rec_ij >> 8
+            else:
+                rec['i'], rec['j'] = self.rec_ij & 0xffff, self.rec_ij >> 16
             n = np.diff(self.unit_rec_off.astype(np.int64))
             rec['unit'] = np.repeat(np.arange(len(n), dtype=np.uint32), n)
             self._records = rec
@@ -251,18 +271,30 @@ class Pipeline:
                                              int(n_chunks), C.byref(h)), ctx.handle)
         self.handle = h
 
-    def step(self, min_common, mode=MODE_HET_ONLY, planes=None, site_flags=None, copy=True, packed=False) -> StepResult:
+    def step(self, min_common, mode=MODE_HET_ONLY, planes=None, site_flags=None, copy=True, packed=False,
+             tight=False) -> StepResult:
         """One pipelined step.  packed=True: `planes` is the two-plane form (PlaneBatch.packed2(),
-        two thirds of the bytes); mode | MODE_SPLIT_RECORDS: rows come back as rec_mi / rec_ij."""
+        two thirds of the bytes); tight=True: its rows without the 128-read padding
+        (PlaneBatch.packed2(tight=True), MODE_TIGHT_INPUT); mode | MODE_SPLIT_RECORDS: rows come back as
+        rec_mi / rec_ij; mode | MODE_COMPACT_OUTPUT: the same with 2-byte (i, j) entries where no unit has
+        more than 256 sites, and no per-site count over the wire."""
+        packed = packed or tight
         if planes is None:
-            planes = self.pb.packed2() if packed else self.pb.planes
+            planes = self.pb.packed2(tight=tight) if packed else self.pb.planes
         site_flags = self.pb.site_flags if site_flags is None else site_flags
-        assert planes.dtype == np.uint32 and planes.size == (self.pb.planes.size // 3 * 2 if packed else self.pb.planes.size)
+        if tight:
+            mode |= MODE_TIGHT_INPUT
+            want = int((2 * self.pb.units['n_sites'].astype(np.int64) * ((self.pb.units['n_reads'].astype(np.int64) + 31) // 32)).sum())
+        else:
+            want = self.pb.planes.size // 3 * 2 if packed else self.pb.planes.size
+        assert planes.dtype == np.uint32 and planes.size == want
         assert site_flags.dtype == np.uint8 and site_flags.size == self.pb.n_sites
         res = Result()
         fn = self._lib.lgmi_pipeline_step_packed if packed else self._lib.lgmi_pipeline_step
         check(fn(self.handle, ptr(planes), ptr(site_flags), int(min_common), int(mode), C.byref(res)), self.ctx.handle)
-        return StepResult(res, self.pb.n_units, copy=copy)
+        out = StepResult(res, self.pb.n_units, copy=copy)
+        out._site_off = self.pb.units['site_off'].astype(np.int64)
+        return out
 
     def close(self):
         if getattr(self, "handle", None):

@@ -15,7 +15,9 @@
 #include <cstring>
 #include <new>
 #include <queue>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -29,6 +31,79 @@ extern "C" void lgmi_build_lntab(double* hi_lo_pairs, uint64_t k_begin, uint64_t
 using namespace lgmi;
 
 static thread_local std::string g_create_error;
+
+// Size-bucketed cache of device and pinned-host blocks owned by a context.  Batches and pipelines are created and
+// destroyed per submit by the drop-in seam (one chunk of footprints = one submit); cudaMalloc / cudaHostAlloc /
+// cudaFree cost tens of microseconds to milliseconds each and cudaFree synchronises the device, so their buffers
+// are recycled instead.  A block is only returned to the cache after the owning batch's stream has been
+// synchronised (lgmi_batch_destroy), i.e. nothing in flight can still touch it.
+struct MemPool {
+  std::multimap<size_t, void*> free_blocks;
+  std::unordered_map<void*, size_t> live;
+  size_t cached_bytes = 0, cap_bytes = 0;
+  uint64_t hits = 0, misses = 0;
+  bool host = false;
+  static size_t bucket(size_t n) {  // sixteenth-of-an-octave steps: at most 1/8 over-allocation
+    if (n <= 4096) return 4096;
+    size_t p = 1;
+    while (p < n) p <<= 1;
+    const size_t step = p >> 4;
+    return (n + step - 1) / step * step;
+  }
+  cudaError_t raw_alloc(void** out, size_t sz) {
+    return host ? cudaHostAlloc(out, sz, cudaHostAllocDefault) : cudaMalloc(out, sz);
+  }
+  void raw_free(void* p) {
+    if (host) cudaFreeHost(p); else cudaFree(p);
+  }
+  void trim() {
+    for (auto& kv : free_blocks) raw_free(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+  cudaError_t alloc(void** out, size_t bytes) {
+    const size_t sz = bucket(bytes ? bytes : 1);
+    auto it = free_blocks.lower_bound(sz);
+    if (it != free_blocks.end() && it->first <= sz + sz / 4) {
+      *out = it->second;
+      live[*out] = it->first;
+      cached_bytes -= it->first;
+      free_blocks.erase(it);
+      ++hits;
+      return cudaSuccess;
+    }
+    ++misses;
+    cudaError_t e = raw_alloc(out, sz);
+    if (e == cudaErrorMemoryAllocation) {  // give the cache back and try once more
+      cudaGetLastError();
+      trim();
+      e = raw_alloc(out, sz);
+    }
+    if (e == cudaSuccess) live[*out] = sz;
+    return e;
+  }
+  void release(void* p) {
+    if (!p) return;
+    auto it = live.find(p);
+    if (it == live.end()) {  // not ours (never happens): hand it to the runtime
+      raw_free(p);
+      return;
+    }
+    const size_t sz = it->second;
+    live.erase(it);
+    if (cached_bytes + sz > cap_bytes) {
+      raw_free(p);
+      return;
+    }
+    free_blocks.emplace(sz, p);
+    cached_bytes += sz;
+  }
+  void destroy() {
+    trim();
+    for (auto& kv : live) raw_free(kv.first);
+    live.clear();
+  }
+};
 
 struct lgmi_ctx {
   int device = 0;
@@ -54,7 +129,19 @@ struct lgmi_ctx {
   // tensor-core path: units at least this large build their tables with k_gram_i8
   uint32_t dense_min_sites = 48, dense_min_reads = 8192;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
+  MemPool dev_pool, host_pool;   // recycled buffers of batches / pipelines
+  uint64_t lntab_gen = 0;        // bumped when the ln table moves: captured graphs hold its address
+  int pipeline_graphs = 1;       // groups of a pipelined step replay their launch chain as a CUDA graph (LGMI_GRAPHS=0: off)
 };
+
+template <class T>
+static cudaError_t pool_malloc(lgmi_ctx* ctx, T** out, size_t bytes) {
+  return ctx->dev_pool.alloc(reinterpret_cast<void**>(out), bytes);
+}
+template <class T>
+static cudaError_t pool_host_alloc(lgmi_ctx* ctx, T** out, size_t bytes) {
+  return ctx->host_pool.alloc(reinterpret_cast<void**>(out), bytes);
+}
 
 // one unit of the tensor-core path
 struct DensePlan {
@@ -126,8 +213,17 @@ struct lgmi_batch {
   double* h_site_mean = nullptr;
   uint32_t* h_site_cnt = nullptr;
   unsigned long long* h_unit_rec_off = nullptr;
+  // launch chains captured as CUDA graphs, one per (min_common, mode)
+  struct Graph {
+    int min_common;
+    uint32_t mode;
+    uint64_t lntab_gen;
+    uint64_t launches;  // kernels in the chain
+    cudaGraphExec_t exec;
+  };
+  std::vector<Graph> graphs;
   // run state
-  bool uploaded = false, ran = false;
+  bool uploaded = false, ran = false, last_timed = false;
   uint32_t last_mode = 0;
   // candidates with a het_snp partner (what SKIP_NONHET evaluates); known once host flags have been seen
   uint64_t n_het_candidates = 0;
@@ -181,6 +277,7 @@ static int ensure_lntab(lgmi_ctx* ctx, uint64_t k_max) {
   CU(ctx, cudaMalloc(&ctx->d_lntab, cap * sizeof(lg_dd)));
   CU(ctx, cudaMemcpy(ctx->d_lntab, host.data(), cap * sizeof(lg_dd), cudaMemcpyHostToDevice));
   ctx->ln_cap = cap;
+  ++ctx->lntab_gen;
   return LGMI_OK;
 }
 
@@ -226,6 +323,10 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
   }
   ctx->stream = ctx->own_stream;
   ctx->num_sms = prop.multiProcessorCount;
+  ctx->host_pool.host = true;
+  ctx->dev_pool.cap_bytes = 16ull << 30;   // cached (idle) bytes kept at most; LGMI_POOL_MB overrides both
+  ctx->host_pool.cap_bytes = 4ull << 30;
+  if (const char* e = getenv("LGMI_POOL_MB")) ctx->dev_pool.cap_bytes = ctx->host_pool.cap_bytes = (size_t)atoll(e) << 20;
   if (cudaFuncSetAttribute(k_pairs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem)) !=
           cudaSuccess ||
       cudaFuncSetAttribute(k_pairs_fast_het, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem)) !=
@@ -251,6 +352,7 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
   }
   if (const char* e = getenv("LGMI_SMALL_PATH")) ctx->small_path = atoi(e) ? 1 : 0;
   if (const char* e = getenv("LGMI_TILE_PATH")) ctx->tile_path = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("LGMI_GRAPHS")) ctx->pipeline_graphs = atoi(e) ? 1 : 0;
   if (cudaFuncSetAttribute(k_tile_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTgSmemBytes) != cudaSuccess) {
     int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: k_tile_gram cannot be resident (%s)",
                   cudaGetErrorString(cudaGetLastError()));
@@ -296,6 +398,8 @@ extern "C" void lgmi_destroy(lgmi_t* ctx) {
   if (ctx->d_lntab) cudaFree(ctx->d_lntab);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_ij_tab) cudaFree(ctx->d_ij_tab);
+  ctx->dev_pool.destroy();
+  ctx->host_pool.destroy();
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -362,6 +466,7 @@ extern "C" int lgmi_set_dense_threshold(lgmi_t* ctx, uint32_t min_sites, uint32_
 // --------------------------------------------------------------------------- batch
 extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   if (!b) return;
+  lgmi_ctx* ctx = b->ctx;  // (always set: a batch is born with its context)
   if (b->ctx) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(bstream(b));
@@ -369,41 +474,42 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   }
   for (cudaEvent_t e : b->ev)
     if (e) cudaEventDestroy(e);
-  cudaFree(b->d_units);
-  cudaFree(b->d_items);
-  cudaFree(b->d_fast_items);
-  cudaFree(b->d_fast_empty);
-  cudaFree(b->d_item_dense);
-  cudaFree(b->d_n_generic);
-  cudaFree(b->d_mean_items);
-  cudaFree(b->d_planes);
-  cudaFree(b->d_flags);
-  cudaFree(b->d_item_cnt);
-  cudaFree(b->d_item_off);
-  cudaFree(b->d_scan_tmp);
-  cudaFree(b->d_header);
-  cudaFree(b->d_records);
-  cudaFree(b->d_counts);
-  cudaFree(b->d_site_mean);
-  cudaFree(b->d_site_cnt);
-  cudaFree(b->d_dense);
-  cudaFree(b->d_unit_rec_off);
-  cudaFree(b->d_x);
-  cudaFree(b->d_gram);
-  cudaFree(b->d_tiles);
-  cudaFree(b->d_tile_items);
-  cudaFree(b->d_gram_tiles);
-  cudaFree(b->d_tile_cnt);
-  cudaFree(b->d_tile_next);
-  cudaFree(b->d_tile_counts);
-  cudaFree(b->d_pre_items);
-  cudaFree(b->d_val);
-  cudaFreeHost(b->h_header);
-  cudaFreeHost(b->h_records);
-  cudaFreeHost(b->h_counts);
-  cudaFreeHost(b->h_site_mean);
-  cudaFreeHost(b->h_site_cnt);
-  cudaFreeHost(b->h_unit_rec_off);
+  for (lgmi_batch::Graph& g : b->graphs) cudaGraphExecDestroy(g.exec);
+  ctx->dev_pool.release(b->d_units);
+  ctx->dev_pool.release(b->d_items);
+  ctx->dev_pool.release(b->d_fast_items);
+  ctx->dev_pool.release(b->d_fast_empty);
+  ctx->dev_pool.release(b->d_item_dense);
+  ctx->dev_pool.release(b->d_n_generic);
+  ctx->dev_pool.release(b->d_mean_items);
+  ctx->dev_pool.release(b->d_planes);
+  ctx->dev_pool.release(b->d_flags);
+  ctx->dev_pool.release(b->d_item_cnt);
+  ctx->dev_pool.release(b->d_item_off);
+  ctx->dev_pool.release(b->d_scan_tmp);
+  ctx->dev_pool.release(b->d_header);
+  ctx->dev_pool.release(b->d_records);
+  ctx->dev_pool.release(b->d_counts);
+  ctx->dev_pool.release(b->d_site_mean);
+  ctx->dev_pool.release(b->d_site_cnt);
+  ctx->dev_pool.release(b->d_dense);
+  ctx->dev_pool.release(b->d_unit_rec_off);
+  ctx->dev_pool.release(b->d_x);
+  ctx->dev_pool.release(b->d_gram);
+  ctx->dev_pool.release(b->d_tiles);
+  ctx->dev_pool.release(b->d_tile_items);
+  ctx->dev_pool.release(b->d_gram_tiles);
+  ctx->dev_pool.release(b->d_tile_cnt);
+  ctx->dev_pool.release(b->d_tile_next);
+  ctx->dev_pool.release(b->d_tile_counts);
+  ctx->dev_pool.release(b->d_pre_items);
+  ctx->dev_pool.release(b->d_val);
+  ctx->host_pool.release(b->h_header);
+  ctx->host_pool.release(b->h_records);
+  ctx->host_pool.release(b->h_counts);
+  ctx->host_pool.release(b->h_site_mean);
+  ctx->host_pool.release(b->h_site_cnt);
+  ctx->host_pool.release(b->h_unit_rec_off);
   delete b;
 }
 
@@ -610,49 +716,49 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   } while (0)
 
   for (cudaEvent_t& e : b->ev) BCU(cudaEventCreate(&e));
-  BCU(cudaMalloc(&b->d_units, std::max<size_t>(1, n_units) * sizeof(DevUnit)));
-  BCU(cudaMalloc(&b->d_items, std::max<size_t>(1, b->n_items) * sizeof(Item)));
-  BCU(cudaMalloc(&b->d_fast_items, std::max<size_t>(1, fast_items.size()) * sizeof(FastItem)));
-  BCU(cudaMalloc(&b->d_fast_empty, std::max<size_t>(1, fast_items.size())));
-  BCU(cudaMalloc(&b->d_item_dense, std::max<size_t>(1, b->n_items)));
-  BCU(cudaMalloc(&b->d_n_generic, sizeof(uint32_t)));
-  BCU(cudaMalloc(&b->d_mean_items, std::max<size_t>(1, mean_items.size()) * sizeof(MeanItem)));
-  BCU(cudaMalloc(&b->d_planes, std::max<uint64_t>(4, plane_words) * sizeof(uint32_t)));
-  BCU(cudaMalloc(&b->d_flags, std::max<uint64_t>(1, n_sites)));
-  BCU(cudaMalloc(&b->d_item_cnt, ((size_t)b->n_items + 1) * sizeof(unsigned long long)));
-  BCU(cudaMalloc(&b->d_item_off, ((size_t)b->n_items + 1) * sizeof(unsigned long long)));
+  BCU(pool_malloc(ctx, &b->d_units, std::max<size_t>(1, n_units) * sizeof(DevUnit)));
+  BCU(pool_malloc(ctx, &b->d_items, std::max<size_t>(1, b->n_items) * sizeof(Item)));
+  BCU(pool_malloc(ctx, &b->d_fast_items, std::max<size_t>(1, fast_items.size()) * sizeof(FastItem)));
+  BCU(pool_malloc(ctx, &b->d_fast_empty, std::max<size_t>(1, fast_items.size())));
+  BCU(pool_malloc(ctx, &b->d_item_dense, std::max<size_t>(1, b->n_items)));
+  BCU(pool_malloc(ctx, &b->d_n_generic, sizeof(uint32_t)));
+  BCU(pool_malloc(ctx, &b->d_mean_items, std::max<size_t>(1, mean_items.size()) * sizeof(MeanItem)));
+  BCU(pool_malloc(ctx, &b->d_planes, std::max<uint64_t>(4, plane_words) * sizeof(uint32_t)));
+  BCU(pool_malloc(ctx, &b->d_flags, std::max<uint64_t>(1, n_sites)));
+  BCU(pool_malloc(ctx, &b->d_item_cnt, ((size_t)b->n_items + 1) * sizeof(unsigned long long)));
+  BCU(pool_malloc(ctx, &b->d_item_off, ((size_t)b->n_items + 1) * sizeof(unsigned long long)));
   BCU(cub::DeviceScan::ExclusiveSum(nullptr, b->scan_tmp_bytes, b->d_item_cnt, b->d_item_off, (int)b->n_items + 1,
                                     bstream(b)));
-  BCU(cudaMalloc(&b->d_scan_tmp, std::max<size_t>(b->scan_tmp_bytes, 16)));
+  BCU(pool_malloc(ctx, &b->d_scan_tmp, std::max<size_t>(b->scan_tmp_bytes, 16)));
   BCU(cudaMemsetAsync(b->d_item_cnt, 0, ((size_t)b->n_items + 1) * sizeof(unsigned long long), bstream(b)));
-  BCU(cudaMalloc(&b->d_header, sizeof(Header)));
-  BCU(cudaMalloc(&b->d_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double)));
-  BCU(cudaMalloc(&b->d_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t)));
-  BCU(cudaMalloc(&b->d_dense, std::max<uint64_t>(1, dense) * sizeof(double)));
-  BCU(cudaMalloc(&b->d_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long)));
+  BCU(pool_malloc(ctx, &b->d_header, sizeof(Header)));
+  BCU(pool_malloc(ctx, &b->d_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double)));
+  BCU(pool_malloc(ctx, &b->d_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t)));
+  BCU(pool_malloc(ctx, &b->d_dense, std::max<uint64_t>(1, dense) * sizeof(double)));
+  BCU(pool_malloc(ctx, &b->d_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long)));
   if (!pre_items.empty()) {
-    BCU(cudaMalloc(&b->d_pre_items, pre_items.size() * sizeof(FastItem)));
+    BCU(pool_malloc(ctx, &b->d_pre_items, pre_items.size() * sizeof(FastItem)));
     BCU(cudaMemcpyAsync(b->d_pre_items, pre_items.data(), pre_items.size() * sizeof(FastItem), cudaMemcpyHostToDevice,
                         bstream(b)));
-    BCU(cudaMalloc(&b->d_val, val_slots * sizeof(unsigned long long)));
+    BCU(pool_malloc(ctx, &b->d_val, val_slots * sizeof(unsigned long long)));
   }
   if (!tile_items.empty()) {
-    BCU(cudaMalloc(&b->d_tile_items, tile_items.size() * sizeof(TileItem)));
+    BCU(pool_malloc(ctx, &b->d_tile_items, tile_items.size() * sizeof(TileItem)));
     BCU(cudaMemcpyAsync(b->d_tile_items, tile_items.data(), tile_items.size() * sizeof(TileItem), cudaMemcpyHostToDevice,
                         bstream(b)));
   }
-  BCU(cudaMalloc(&b->d_tile_next, sizeof(uint32_t)));
+  BCU(pool_malloc(ctx, &b->d_tile_next, sizeof(uint32_t)));
   if (!gram_tiles.empty()) {
-    BCU(cudaMalloc(&b->d_gram_tiles, gram_tiles.size() * sizeof(TileItem)));
+    BCU(pool_malloc(ctx, &b->d_gram_tiles, gram_tiles.size() * sizeof(TileItem)));
     BCU(cudaMemcpyAsync(b->d_gram_tiles, gram_tiles.data(), gram_tiles.size() * sizeof(TileItem), cudaMemcpyHostToDevice,
                         bstream(b)));
   }
-  if (any_gram_tiled) BCU(cudaMalloc(&b->d_tile_cnt, std::max<uint64_t>(1, dense) * 3ull * sizeof(uint2)));
+  if (any_gram_tiled) BCU(pool_malloc(ctx, &b->d_tile_cnt, std::max<uint64_t>(1, dense) * 3ull * sizeof(uint2)));
   if (!b->dense_plans.empty()) {
-    BCU(cudaMalloc(&b->d_x, x_bytes));
+    BCU(pool_malloc(ctx, &b->d_x, x_bytes));
     BCU(cudaMemsetAsync(b->d_x, 0, x_bytes, bstream(b)));  // rows of the site padding stay zero
-    BCU(cudaMalloc(&b->d_gram, gram_words * sizeof(uint32_t)));
-    BCU(cudaMalloc(&b->d_tiles, dense_tiles.size() * sizeof(DenseTile)));
+    BCU(pool_malloc(ctx, &b->d_gram, gram_words * sizeof(uint32_t)));
+    BCU(pool_malloc(ctx, &b->d_tiles, dense_tiles.size() * sizeof(DenseTile)));
     BCU(cudaMemcpyAsync(b->d_tiles, dense_tiles.data(), dense_tiles.size() * sizeof(DenseTile), cudaMemcpyHostToDevice,
                         bstream(b)));
     typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -676,11 +782,11 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
     }
   }
   b->rec_cap = std::max<uint64_t>(1, b->n_candidates);
-  BCU(cudaMalloc(&b->d_records, b->rec_cap * sizeof(lgmi_pair_rec)));
-  BCU(cudaHostAlloc(&b->h_header, sizeof(Header), cudaHostAllocDefault));
-  BCU(cudaHostAlloc(&b->h_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double), cudaHostAllocDefault));
-  BCU(cudaHostAlloc(&b->h_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t), cudaHostAllocDefault));
-  BCU(cudaHostAlloc(&b->h_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
+  BCU(pool_malloc(ctx, &b->d_records, b->rec_cap * sizeof(lgmi_pair_rec)));
+  BCU(pool_host_alloc(ctx, &b->h_header, sizeof(Header)));
+  BCU(pool_host_alloc(ctx, &b->h_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double)));
+  BCU(pool_host_alloc(ctx, &b->h_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t)));
+  BCU(pool_host_alloc(ctx, &b->h_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long)));
   if (n_units) BCU(cudaMemcpyAsync(b->d_units, du.data(), n_units * sizeof(DevUnit), cudaMemcpyHostToDevice, bstream(b)));
   if (b->n_items) BCU(cudaMemcpyAsync(b->d_items, b->h_items.data(), b->n_items * sizeof(Item), cudaMemcpyHostToDevice, bstream(b)));
   if (!fast_items.empty())
@@ -715,6 +821,13 @@ extern "C" int lgmi_batch_upload(lgmi_batch_t* b, const uint32_t* planes, const 
   return LGMI_OK;
 }
 
+static void drop_graphs(lgmi_batch* b) {
+  for (lgmi_batch::Graph& g : b->graphs) cudaGraphExecDestroy(g.exec);
+  b->graphs.clear();
+}
+
+static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing);
+
 extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   if (!b) return LGMI_ERR_ARG;
   lgmi_ctx* ctx = b->ctx;
@@ -722,18 +835,64 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   if ((mode & LGMI_MODE_SKIP_NONHET) && !(mode & LGMI_MODE_HET_ONLY))
     return fail(ctx, LGMI_ERR_ARG, "LGMI_MODE_SKIP_NONHET requires LGMI_MODE_HET_ONLY");
   CU(ctx, cudaSetDevice(ctx->device));
+  // LGMI_MODE_GRAPH (and every group of a pipelined step): the whole launch chain as ONE cudaGraphLaunch
+  const bool as_graph = (mode & LGMI_MODE_GRAPH) != 0u || (b->own_stream != nullptr && ctx->pipeline_graphs);
+  mode &= ~LGMI_MODE_GRAPH;
+  // buffers the chain needs exist before anything is launched or captured
   if ((mode & LGMI_MODE_EMIT_COUNTS) && b->counts_cap < b->rec_cap) {
     CU(ctx, cudaStreamSynchronize(bstream(b)));
-    if (b->d_counts) CU(ctx, cudaFree(b->d_counts));
+    if (b->d_counts) ctx->dev_pool.release(b->d_counts);
     b->d_counts = nullptr;
     b->counts_cap = 0;
-    CU(ctx, cudaMalloc(&b->d_counts, b->rec_cap * 9ull * sizeof(uint32_t)));
+    drop_graphs(b);
+    CU(ctx, pool_malloc(ctx, &b->d_counts, b->rec_cap * 9ull * sizeof(uint32_t)));
     b->counts_cap = b->rec_cap;
   }
   if ((mode & LGMI_MODE_EMIT_COUNTS) && (b->n_tile_items || b->n_gram_tiles) && !b->d_tile_counts) {
     CU(ctx, cudaStreamSynchronize(bstream(b)));
-    CU(ctx, cudaMalloc(&b->d_tile_counts, std::max<uint64_t>(1, b->n_dense) * 9ull * sizeof(uint32_t)));
+    drop_graphs(b);
+    CU(ctx, pool_malloc(ctx, &b->d_tile_counts, std::max<uint64_t>(1, b->n_dense) * 9ull * sizeof(uint32_t)));
   }
+  if (!as_graph) return run_chain(b, min_common, mode, b->own_stream == nullptr);
+  lgmi_batch::Graph* hit = nullptr;
+  for (lgmi_batch::Graph& g : b->graphs)
+    if (g.min_common == min_common && g.mode == mode) hit = &g;
+  if (hit && hit->lntab_gen != ctx->lntab_gen) {  // the ln table has moved since the capture
+    drop_graphs(b);
+    hit = nullptr;
+  }
+  if (!hit) {
+    cudaStream_t st = bstream(b);
+    cudaGraph_t graph = nullptr;
+    const uint64_t launches0 = ctx->launches;
+    CU(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_chain(b, min_common, mode, false);
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    const uint64_t n_launch = ctx->launches - launches0;
+    ctx->launches = launches0;
+    if (rc != LGMI_OK || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc != LGMI_OK ? rc : fail(ctx, LGMI_ERR_CUDA, "graph capture of the launch chain failed: %s", cudaGetErrorString(e));
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return fail(ctx, LGMI_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+    b->graphs.push_back(lgmi_batch::Graph{min_common, mode, ctx->lntab_gen, n_launch, exec});
+    hit = &b->graphs.back();
+  }
+  CU(ctx, cudaGraphLaunch(hit->exec, bstream(b)));
+  ctx->launches += hit->launches;
+  b->ran = true;
+  b->last_mode = mode;
+  b->last_timed = false;
+  return LGMI_OK;
+}
+
+// the launch chain of one run on the batch's stream (also what a graph capture records)
+static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) {
+  lgmi_ctx* ctx = b->ctx;
   RunParams P;
   P.units = b->d_units;
   P.items = b->d_items;
@@ -760,7 +919,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   P.unit_base = b->unit_base;
   P.tile_counts = b->d_tile_counts;
 
-  const bool timing = b->own_stream == nullptr;  // pipeline groups skip the per-kernel events (fewer API calls)
+  // (pipeline groups and graph replays skip the per-kernel events)
   if (timing) CU(ctx, cudaEventRecord(b->ev[0], bstream(b)));
   {
     // one launch resets the run state: header, offsets, flags, NaN means (sites of pair-less units keep them)
@@ -936,6 +1095,7 @@ extern "C" int lgmi_batch_run(lgmi_batch_t* b, int min_common, uint32_t mode) {
   CU(ctx, cudaGetLastError());
   b->ran = true;
   b->last_mode = mode;
+  b->last_timed = timing;
   return LGMI_OK;
 }
 
@@ -949,7 +1109,7 @@ static int fill_scalars(lgmi_batch* b, lgmi_result* out) {
   out->n_records = b->h_header->n_records;
   out->n_sites = b->n_sites;
   float ms = 0.f;
-  const bool timing = b->own_stream == nullptr;
+  const bool timing = b->last_timed;
   if (timing) {
     CU(ctx, cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]));
     out->kernel_ms = ms;
@@ -998,20 +1158,20 @@ extern "C" int lgmi_batch_download(lgmi_batch_t* b, lgmi_result* out) {
   const uint64_t nrec = b->h_header->n_records;
   if (nrec > b->rec_cap) return fail(ctx, LGMI_ERR_STATE, "record count %llu exceeds capacity", (unsigned long long)nrec);
   if (nrec > b->h_rec_cap) {
-    if (b->h_records) CU(ctx, cudaFreeHost(b->h_records));
+    if (b->h_records) ctx->host_pool.release(b->h_records);
     b->h_records = nullptr;
     b->h_rec_cap = 0;
     const uint64_t cap = std::max<uint64_t>(nrec + nrec / 8, 1024);
-    CU(ctx, cudaHostAlloc(&b->h_records, cap * sizeof(lgmi_pair_rec), cudaHostAllocDefault));
+    CU(ctx, pool_host_alloc(ctx, &b->h_records, cap * sizeof(lgmi_pair_rec)));
     b->h_rec_cap = cap;
   }
   const bool want_counts = (b->last_mode & LGMI_MODE_EMIT_COUNTS) != 0u;
   if (want_counts && nrec > b->h_counts_cap) {
-    if (b->h_counts) CU(ctx, cudaFreeHost(b->h_counts));
+    if (b->h_counts) ctx->host_pool.release(b->h_counts);
     b->h_counts = nullptr;
     b->h_counts_cap = 0;
     const uint64_t cap = std::max<uint64_t>(nrec + nrec / 8, 1024);
-    CU(ctx, cudaHostAlloc(&b->h_counts, cap * 9ull * sizeof(uint32_t), cudaHostAllocDefault));
+    CU(ctx, pool_host_alloc(ctx, &b->h_counts, cap * 9ull * sizeof(uint32_t)));
     b->h_counts_cap = cap;
   }
   if (nrec) {
@@ -1067,6 +1227,8 @@ struct lgmi_pipeline {
     cudaEvent_t done = nullptr;     // the group's kernels have finished
     cudaEvent_t landed = nullptr;   // the group's input is in device memory
     uint32_t* d_packed = nullptr;   // two-plane input staging (lgmi_pipeline_step_packed)
+    unsigned long long* d_tight_off = nullptr;  // LGMI_MODE_TIGHT_INPUT: first word of each unit, relative to the group
+    uint64_t tight0 = 0, tight_words = 0;       // the group's slice of the tight two-plane input
     double* d_rec_mi = nullptr;     // split output (LGMI_MODE_SPLIT_RECORDS)
     uint32_t* d_rec_ij = nullptr;
     uint64_t base = 0;              // first row of the group in the merged output of the current step
@@ -1081,8 +1243,10 @@ struct lgmi_pipeline {
   uint64_t h_counts_cap = 0;
   double* h_rec_mi = nullptr;
   uint64_t h_rec_mi_cap = 0;
-  uint32_t* h_rec_ij = nullptr;
+  uint32_t* h_rec_ij = nullptr;   // (2-byte entries under LGMI_MODE_COMPACT_OUTPUT when every unit has <= 256 sites)
   uint64_t h_rec_ij_cap = 0;
+  uint32_t max_sites = 0;
+  std::vector<uint64_t> tight_off;  // per unit: first word in the tight two-plane input
   double* h_site_mean = nullptr;
   uint32_t* h_site_cnt = nullptr;
   unsigned long long* h_unit_rec_off = nullptr;
@@ -1090,7 +1254,11 @@ struct lgmi_pipeline {
 
 extern "C" void lgmi_pipeline_destroy(lgmi_pipeline_t* p) {
   if (!p) return;
+  lgmi_ctx* ctx = p->ctx;
   if (p->ctx) cudaSetDevice(p->ctx->device);
+  // copies into the pinned output arrays must have landed before the arrays go back to the cache
+  if (p->d2h) cudaStreamSynchronize(p->d2h);
+  if (p->h2d) cudaStreamSynchronize(p->h2d);
   for (lgmi_pipeline::Chunk& c : p->chunks) {
     if (c.b) {
       cudaStream_t st = c.b->own_stream;
@@ -1099,19 +1267,20 @@ extern "C" void lgmi_pipeline_destroy(lgmi_pipeline_t* p) {
     }
     if (c.done) cudaEventDestroy(c.done);
     if (c.landed) cudaEventDestroy(c.landed);
-    cudaFree(c.d_packed);
-    cudaFree(c.d_rec_mi);
-    cudaFree(c.d_rec_ij);
+    ctx->dev_pool.release(c.d_packed);
+    ctx->dev_pool.release(c.d_tight_off);
+    ctx->dev_pool.release(c.d_rec_mi);
+    ctx->dev_pool.release(c.d_rec_ij);
   }
   if (p->h2d) cudaStreamDestroy(p->h2d);
   if (p->d2h) cudaStreamDestroy(p->d2h);
-  cudaFreeHost(p->h_rec_mi);
-  cudaFreeHost(p->h_rec_ij);
-  cudaFreeHost(p->h_records);
-  cudaFreeHost(p->h_counts);
-  cudaFreeHost(p->h_site_mean);
-  cudaFreeHost(p->h_site_cnt);
-  cudaFreeHost(p->h_unit_rec_off);
+  ctx->host_pool.release(p->h_rec_mi);
+  ctx->host_pool.release(p->h_rec_ij);
+  ctx->host_pool.release(p->h_records);
+  ctx->host_pool.release(p->h_counts);
+  ctx->host_pool.release(p->h_site_mean);
+  ctx->host_pool.release(p->h_site_cnt);
+  ctx->host_pool.release(p->h_unit_rec_off);
   delete p;
 }
 
@@ -1148,6 +1317,17 @@ extern "C" int lgmi_pipeline_create(lgmi_t* ctx, const lgmi_unit_desc* units, ui
       return rc__;                                                                             \
     }                                                                                          \
   } while (0)
+  // the tight two-plane form (LGMI_MODE_TIGHT_INPUT): rows of ceil(R/32) words, units back to back
+  p->tight_off.resize((size_t)n_units + 1);
+  {
+    uint64_t off = 0;
+    for (uint32_t k = 0; k < n_units; ++k) {
+      p->tight_off[k] = off;
+      off += 2ull * units[k].n_sites * ((units[k].n_reads + 31u) / 32u);
+      p->max_sites = std::max(p->max_sites, units[k].n_sites);
+    }
+    p->tight_off[n_units] = off;
+  }
   // equal shares of the work: candidate pairs plus a term for the bytes to move
   std::vector<uint64_t> cost(n_units);
   uint64_t cost_total = 0;
@@ -1184,15 +1364,23 @@ extern "C" int lgmi_pipeline_create(lgmi_t* ctx, const lgmi_unit_desc* units, ui
     p->chunks.push_back(ch);
     lgmi_pipeline::Chunk& ref = p->chunks.back();
     ref.b->unit_base = ref.unit0;  // records carry the unit's index in the whole batch
+    ref.tight0 = p->tight_off[ref.unit0];
+    ref.tight_words = p->tight_off[ref.unit0 + ref.n_units] - ref.tight0;
+    if (ref.n_units) {
+      std::vector<unsigned long long> rel(ref.n_units);
+      for (uint32_t q = 0; q < ref.n_units; ++q) rel[q] = p->tight_off[ref.unit0 + q] - ref.tight0;
+      PCU(pool_malloc(ctx, &ref.d_tight_off, rel.size() * sizeof(unsigned long long)));
+      PCU(cudaMemcpy(ref.d_tight_off, rel.data(), rel.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
     PCU(cudaStreamCreateWithFlags(&ref.b->own_stream, cudaStreamNonBlocking));
     PCU(cudaEventCreateWithFlags(&ref.done, cudaEventDisableTiming));
     PCU(cudaEventCreateWithFlags(&ref.landed, cudaEventDisableTiming));
   }
   PCU(cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking));
   PCU(cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking));
-  PCU(cudaHostAlloc(&p->h_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double), cudaHostAllocDefault));
-  PCU(cudaHostAlloc(&p->h_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t), cudaHostAllocDefault));
-  PCU(cudaHostAlloc(&p->h_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
+  PCU(pool_host_alloc(ctx, &p->h_site_mean, std::max<uint64_t>(1, n_sites) * sizeof(double)));
+  PCU(pool_host_alloc(ctx, &p->h_site_cnt, std::max<uint64_t>(1, n_sites) * sizeof(uint32_t)));
+  PCU(pool_host_alloc(ctx, &p->h_unit_rec_off, ((size_t)n_units + 1) * sizeof(unsigned long long)));
 #undef PCU
   *out = p;
   return LGMI_OK;
@@ -1206,9 +1394,9 @@ static int grow_pinned(lgmi_pipeline* p, T*& buf, uint64_t& cap, uint64_t need, 
   CU(ctx, cudaStreamSynchronize(p->d2h));  // copies into the old array
   const uint64_t new_cap = std::max<uint64_t>(need + need / 4, 1024);
   T* fresh = nullptr;
-  CU(ctx, cudaHostAlloc(&fresh, new_cap * elem, cudaHostAllocDefault));
+  CU(ctx, pool_host_alloc(ctx, &fresh, new_cap * elem));
   if (keep) memcpy(fresh, buf, keep * elem);
-  if (buf) CU(ctx, cudaFreeHost(buf));
+  if (buf) ctx->host_pool.release(buf);
   buf = fresh;
   cap = new_cap;
   return LGMI_OK;
@@ -1222,8 +1410,13 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
     return fail(ctx, LGMI_ERR_ARG, "lgmi_pipeline_step: NULL input");
   CU(ctx, cudaSetDevice(ctx->device));
   const bool want_counts = (mode & LGMI_MODE_EMIT_COUNTS) != 0u;
-  const bool split = (mode & LGMI_MODE_SPLIT_RECORDS) != 0u;
-  mode &= ~LGMI_MODE_SPLIT_RECORDS;  // a matter of the output copies, not of the kernels
+  const bool compact = (mode & LGMI_MODE_COMPACT_OUTPUT) != 0u;  // split rows with 2-byte (i, j) where possible, no site_cnt
+  const bool split = (mode & LGMI_MODE_SPLIT_RECORDS) != 0u || compact;
+  const bool ij16 = compact && p->max_sites <= 256u;
+  const bool tight = (mode & LGMI_MODE_TIGHT_INPUT) != 0u;
+  if (tight && !packed) return fail(ctx, LGMI_ERR_ARG, "LGMI_MODE_TIGHT_INPUT is a form of the two-plane input (lgmi_pipeline_step_packed)");
+  mode &= ~(LGMI_MODE_SPLIT_RECORDS | LGMI_MODE_COMPACT_OUTPUT | LGMI_MODE_TIGHT_INPUT);  // a matter of the copies, not of the kernels
+  const size_t ij_bytes = ij16 ? sizeof(uint16_t) : sizeof(uint32_t);
   static const bool debug = getenv("LGMI_PIPE_DEBUG") != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
@@ -1236,12 +1429,13 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
     int rc = LGMI_OK;
     // input on the upload stream, in group order; the group's own stream picks up when it has landed
     if (b->n_sites) CU(ctx, cudaMemcpyAsync(b->d_flags, site_flags + c.site0, b->n_sites, cudaMemcpyHostToDevice, p->h2d));
-    const uint64_t words2 = b->plane_words / 3u * 2u;
+    const uint64_t words2 = b->plane_words / 3u * 2u;           // staging sized for the padded form: either fits
+    const uint64_t words_in = tight ? c.tight_words : words2;
     if (packed) {  // two planes per site over PCIe, expanded on the device
-      if (!c.d_packed && words2) CU(ctx, cudaMalloc(&c.d_packed, words2 * sizeof(uint32_t)));
-      if (words2)
-        CU(ctx, cudaMemcpyAsync(c.d_packed, planes + c.plane0 / 3u * 2u, words2 * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                                p->h2d));
+      if (!c.d_packed && words2) CU(ctx, pool_malloc(ctx, &c.d_packed, words2 * sizeof(uint32_t)));
+      if (words_in)
+        CU(ctx, cudaMemcpyAsync(c.d_packed, planes + (tight ? c.tight0 : c.plane0 / 3u * 2u), words_in * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, p->h2d));
     } else if (b->plane_words) {
       CU(ctx, cudaMemcpyAsync(b->d_planes, planes + c.plane0, b->plane_words * sizeof(uint32_t), cudaMemcpyHostToDevice,
                               p->h2d));
@@ -1249,8 +1443,8 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
     CU(ctx, cudaEventRecord(c.landed, p->h2d));
     CU(ctx, cudaStreamWaitEvent(st, c.landed, 0));
     if (packed && words2) {
-      k_unpack2<<<std::min<uint32_t>(b->n_units, (uint32_t)ctx->num_sms * 16u), 256, 0, st>>>(b->d_units, b->n_units,
-                                                                                            c.d_packed, b->d_planes);
+      k_unpack2<<<std::min<uint32_t>(b->n_units, (uint32_t)ctx->num_sms * 16u), 256, 0, st>>>(
+          b->d_units, b->n_units, c.d_packed, b->d_planes, tight ? c.d_tight_off : nullptr);
       ++ctx->launches;
     }
     b->uploaded = true;
@@ -1262,10 +1456,11 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
     if (rc) return rc;
     if (split) {
       if (!c.d_rec_mi) {
-        CU(ctx, cudaMalloc(&c.d_rec_mi, b->rec_cap * sizeof(double)));
-        CU(ctx, cudaMalloc(&c.d_rec_ij, b->rec_cap * sizeof(uint32_t)));
+        CU(ctx, pool_malloc(ctx, &c.d_rec_mi, b->rec_cap * sizeof(double)));
+        CU(ctx, pool_malloc(ctx, &c.d_rec_ij, b->rec_cap * sizeof(uint32_t)));
       }
-      k_split_records<<<(unsigned)ctx->num_sms * 8u, 256, 0, st>>>(b->d_header, b->d_records, c.d_rec_mi, c.d_rec_ij);
+      k_split_records<<<(unsigned)ctx->num_sms * 8u, 256, 0, st>>>(b->d_header, b->d_records, c.d_rec_mi, c.d_rec_ij,
+                                                                   ij16 ? reinterpret_cast<uint16_t*>(c.d_rec_ij) : nullptr);
       ++ctx->launches;
     }
     CU(ctx, cudaEventRecord(c.done, st));  // the group's record count is in its (host-resident) header by then
@@ -1292,7 +1487,8 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
     if (nrec) {
       if (split) {
         CU(ctx, cudaMemcpyAsync(p->h_rec_mi + base, c.d_rec_mi, nrec * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CU(ctx, cudaMemcpyAsync(p->h_rec_ij + base, c.d_rec_ij, nrec * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(p->h_rec_ij) + base * ij_bytes, c.d_rec_ij, nrec * ij_bytes,
+                                cudaMemcpyDeviceToHost, st));
       } else {
         CU(ctx, cudaMemcpyAsync(p->h_records + base, b->d_records, nrec * sizeof(lgmi_pair_rec), cudaMemcpyDeviceToHost, st));
       }
@@ -1303,7 +1499,8 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
                             cudaMemcpyDeviceToHost, st));
     if (b->n_sites) {
       CU(ctx, cudaMemcpyAsync(p->h_site_mean + c.site0, b->d_site_mean, b->n_sites * sizeof(double), cudaMemcpyDeviceToHost, st));
-      CU(ctx, cudaMemcpyAsync(p->h_site_cnt + c.site0, b->d_site_cnt, b->n_sites * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      if (!compact)
+        CU(ctx, cudaMemcpyAsync(p->h_site_cnt + c.site0, b->d_site_cnt, b->n_sites * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
     c.base = base;
     base += nrec;
@@ -1331,10 +1528,11 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
   out->records = split ? nullptr : p->h_records;
   out->rec_mi = split ? p->h_rec_mi : nullptr;
   out->rec_ij = split ? p->h_rec_ij : nullptr;
+  out->rec_ij_bytes = split ? (uint32_t)ij_bytes : 0u;
   out->counts = want_counts ? p->h_counts : nullptr;
   out->n_sites = p->n_sites;
   out->site_mean = p->h_site_mean;
-  out->site_cnt = p->h_site_cnt;
+  out->site_cnt = compact ? nullptr : p->h_site_cnt;
   out->unit_rec_off = reinterpret_cast<const uint64_t*>(p->h_unit_rec_off);
   for (lgmi_pipeline::Chunk& c : p->chunks) {
     lgmi_result r;

@@ -762,12 +762,31 @@ __global__ void __launch_bounds__(kMeanThreads) k_site_mean_dense(const DevUnit*
 }
 
 // Input in the packed two-plane form (2 bits per site and read: 00 not covered, 01 major,
-// 10 minor, 11 other; row of site s = [b0 | b1], W words each): a third fewer bytes over PCIe.
+// 10 minor, 11 other; row of site s = [b0 | b1]): a third fewer bytes over PCIe than [M | m | C].
 // Expanded on the device into the [M | m | C] rows every kernel reads.  One CTA per unit.
+// tight_off == NULL: plane rows keep their padded width W (unit k starts at 2/3 of its plane_off);
+// else the rows are ceil(R/32) words wide and unit k starts at word tight_off[k] (LGMI_MODE_TIGHT_INPUT:
+// no 128-read padding on the wire -- 56 instead of 64 bytes per site at 200 reads).
 __global__ void __launch_bounds__(256) k_unpack2(const DevUnit* __restrict__ units, uint32_t n_units,
-                                                 const uint32_t* __restrict__ packed, uint32_t* __restrict__ planes) {
+                                                 const uint32_t* __restrict__ packed, uint32_t* __restrict__ planes,
+                                                 const unsigned long long* __restrict__ tight_off) {
   for (uint32_t k = blockIdx.x; k < n_units; k += gridDim.x) {
     const DevUnit u = units[k];
+    if (tight_off) {
+      const uint32_t W = u.W, Wt = (u.R + 31u) >> 5;
+      const uint32_t* __restrict__ src = packed + tight_off[k];
+      uint32_t* __restrict__ dst = planes + u.plane_off;
+      for (uint32_t e = threadIdx.x; e < u.S * W; e += blockDim.x) {
+        const uint32_t s = e / W, q = e - s * W;
+        const uint32_t b0 = q < Wt ? __ldg(src + (size_t)s * 2u * Wt + q) : 0u;
+        const uint32_t b1 = q < Wt ? __ldg(src + (size_t)s * 2u * Wt + Wt + q) : 0u;
+        uint32_t* row = dst + (size_t)s * 3u * W + q;
+        row[0] = b0 & ~b1;
+        row[W] = b1 & ~b0;
+        row[2u * W] = b0 | b1;
+      }
+      continue;
+    }
     const uint32_t W4 = u.W >> 2;
     const uint4* __restrict__ src = reinterpret_cast<const uint4*>(packed + u.plane_off / 3u * 2u);
     uint4* __restrict__ dst = reinterpret_cast<uint4*>(planes + u.plane_off);
@@ -782,16 +801,19 @@ __global__ void __launch_bounds__(256) k_unpack2(const DevUnit* __restrict__ uni
   }
 }
 
-// Output in split form: MI values and (i | j << 16) of the emitted pairs as two arrays (12 bytes
-// per row over PCIe instead of 16; the unit of a row follows from unit_rec_off).
+// Output in split form: MI values and the site indices of the emitted pairs as two arrays (12 bytes
+// per row over PCIe instead of 16; the unit of a row follows from unit_rec_off).  rec_ij: i | j << 16;
+// rec_ij16 (units of at most 256 sites): i | j << 8 -- 10 bytes per row.
 __global__ void __launch_bounds__(256) k_split_records(const Header* __restrict__ header,
                                                        const lgmi_pair_rec* __restrict__ records,
-                                                       double* __restrict__ rec_mi, uint32_t* __restrict__ rec_ij) {
+                                                       double* __restrict__ rec_mi, uint32_t* __restrict__ rec_ij,
+                                                       uint16_t* __restrict__ rec_ij16) {
   const unsigned long long n = header->n_records;
   for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n;
        r += (unsigned long long)gridDim.x * blockDim.x) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(records) + r);  // {unit, i | j << 16, mi}
-    rec_ij[r] = v.y;
+    if (rec_ij16) rec_ij16[r] = (uint16_t)((v.y & 0xffu) | ((v.y >> 16) << 8));
+    else rec_ij[r] = v.y;
     rec_mi[r] = __hiloint2double((int)v.w, (int)v.z);
   }
 }

@@ -119,24 +119,33 @@ class PlaneBatch:
         s = self.units['n_sites'].astype(np.int64)
         return int((s * (s - 1) // 2).sum())
 
-    def packed2(self) -> np.ndarray:
+    def packed2(self, tight=False) -> np.ndarray:
         """The planes in the two-plane form of lgmi_pipeline_step_packed: per site row [b0 | b1]
         with b0 = major | other, b1 = minor | other (2 bits per read: 00 not covered, 01 major,
-        10 minor, 11 other).  Two thirds of the bytes of the [M | m | C] form."""
-        out = np.empty(self.planes.size // 3 * 2, dtype=np.uint32)
+        10 minor, 11 other).  Two thirds of the bytes of the [M | m | C] form; with tight=True
+        (LGMI_MODE_TIGHT_INPUT) the rows are ceil(R/32) words wide instead of W = 4*ceil(R/128) and the
+        units lie back to back: no 128-read padding on the wire."""
         S = self.units['n_sites'].astype(np.int64)
         W = self.units['row_words'].astype(np.int64)
+        Wt = (self.units['n_reads'].astype(np.int64) + 31) // 32
         off = self.units['plane_off'].astype(np.int64)
-        for w in np.unique(W[S > 0]):                         # all units of one row width at once
-            sel = np.flatnonzero((W == w) & (S > 0))
+        if tight:
+            dst_off = np.concatenate(([0], np.cumsum(2 * S * Wt)))
+            out = np.empty(int(dst_off[-1]), dtype=np.uint32)
+        else:
+            dst_off = off // 3 * 2
+            out = np.empty(self.planes.size // 3 * 2, dtype=np.uint32)
+        for w, wt in sorted(set(zip(W[S > 0].tolist(), Wt[S > 0].tolist()))):   # all units of one row width at once
+            sel = np.flatnonzero((W == w) & (Wt == wt) & (S > 0))
+            wo = wt if tight else w                                              # words per output plane row
             rows = np.concatenate([off[k] + 3 * w * np.arange(S[k]) for k in sel])
-            idx = rows[:, None] + np.arange(w)[None, :]
+            drow = np.concatenate([dst_off[k] + 2 * wo * np.arange(S[k]) for k in sel])
+            idx = rows[:, None] + np.arange(wo)[None, :]
             M, m, C = self.planes[idx], self.planes[idx + w], self.planes[idx + 2 * w]
             other = C & ~M & ~m
-            dst = rows // 3 * 2
-            didx = dst[:, None] + np.arange(w)[None, :]
+            didx = drow[:, None] + np.arange(wo)[None, :]
             out[didx] = M | other
-            out[didx + w] = m | other
+            out[didx + wo] = m | other
         return out
 
     def site_types(self, unit):

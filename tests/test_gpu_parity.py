@@ -434,8 +434,34 @@ def test_pipelined_step_equals_one_submit(lg, gpu_ctx, n_chunks):
             assert np.array_equal(packed.unit_rec_off, want.unit_rec_off)
             if mode & lg.MODE_EMIT_COUNTS:
                 assert np.array_equal(packed.counts, want.counts)
+            # the tight two-plane input (no 128-read padding) and the compact output (4-byte (i, j) here: a unit
+            # has more than 256 sites... or not; no per-site count over the wire: recounted from the rows)
+            tight = pipe.step(mc, mode | lg.MODE_COMPACT_OUTPUT, tight=True)
+            assert tight.rec_ij.dtype == (np.uint16 if int(pb.units['n_sites'].max()) <= 256 else np.uint32)
+            assert np.array_equal(tight.records, want.records)
+            assert np.array_equal(tight.site_mean, want.site_mean, equal_nan=True)
+            if mode & lg.MODE_HET_ONLY:                         # site_cnt counts het-kept rows: the rows of these modes
+                assert np.array_equal(tight.site_cnt, want.site_cnt)
+            # the launch chain as a CUDA graph: same bits, replayed
+            for _ in range(2):
+                b.run(mc, mode | lg.MODE_GRAPH)
+                g = b.download()
+                assert np.array_equal(g.records, want.records) and np.array_equal(g.site_mean, want.site_mean, equal_nan=True)
+                assert g.kernel_ms == 0.0
     pipe.close()
     b.close()
+
+
+def test_compact_rows_use_two_byte_site_indices(lg, gpu_ctx):
+    """MODE_COMPACT_OUTPUT with no unit above 256 sites: (i, j) as i | j << 8 in a uint16 array."""
+    pb = synth.make_uniform_planes(77, 300, 50, 200, 0.5)
+    pipe = lg.Pipeline(gpu_ctx, pb, 3)
+    want = pipe.step(6, lg.MODE_HET_ONLY)
+    got = pipe.step(6, lg.MODE_HET_ONLY | lg.MODE_COMPACT_OUTPUT, tight=True)
+    assert got.rec_ij.dtype == np.uint16 and got._site_cnt is None
+    assert np.array_equal(got.records, want.records)
+    assert np.array_equal(got.site_cnt, want.site_cnt) and np.array_equal(got.site_mean, want.site_mean, equal_nan=True)
+    pipe.close()
 
 
 def test_pipeline_needs_back_to_back_units(lg, gpu_ctx):
@@ -488,6 +514,98 @@ def test_cfg2_full_size_properties(lg, gpu_ctx, cfg2):
         assert u['i'].tolist() == i.tolist() and u['j'].tolist() == j.tolist()
         assert_mi_close(u['mi'], mi)
         assert_mi_close(r1.site_mean[g * 50:(g + 1) * 50], mean)
+    b.close()
+
+
+def _order_and_mean_properties(pb, res):
+    """Size-independent checks on a full-size result: reference row order, offsets, MI range, and the
+    per-site counts / means recomputed on the host from the emitted rows."""
+    rec = res.records
+    key = rec['unit'].astype(np.int64) * (1 << 32) + rec['i'].astype(np.int64) * (1 << 16) + rec['j']
+    assert np.all(np.diff(key) > 0)
+    S = pb.units['n_sites'].astype(np.int64)
+    assert np.all(rec['i'] < rec['j']) and np.all(rec['j'] < S[rec['unit']])
+    assert np.array_equal(np.searchsorted(rec['unit'], np.arange(pb.n_units + 1)), res.unit_rec_off.astype(np.int64))
+    assert np.all(rec['mi'] >= 0.0) and np.all(rec['mi'] <= math.log(3) + 1e-12)
+    off = pb.units['site_off'].astype(np.int64)
+    flags = pb.site_flags & 3
+    gi, gj = off[rec['unit']] + rec['i'], off[rec['unit']] + rec['j']
+    keep = (flags[gi] == 2) | (flags[gj] == 2)
+    tot = np.bincount(gi[keep], rec['mi'][keep], pb.n_sites) + np.bincount(gj[keep], rec['mi'][keep], pb.n_sites)
+    cnt = np.bincount(gi[keep], minlength=pb.n_sites) + np.bincount(gj[keep], minlength=pb.n_sites)
+    assert np.array_equal(cnt, res.site_cnt)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        assert np.allclose(tot / cnt, res.site_mean, rtol=1e-12, atol=1e-15, equal_nan=True)
+
+
+def test_cfg4_full_size_properties_and_oracle_sample(lg, gpu_ctx):
+    """BASELINE.json configs[3] at full size (20 000 heavy-tailed units, 32 M pairs, every kernel path in one
+    batch): order / offsets / means as properties, deterministic, mid-depth units identical on the tensor-core
+    and the popcount path, and a sample of units of every path against the oracle."""
+    pb, raw = synth.make_heavy_tail(20261023, 20000, keep_raw=True)
+    S, R = pb.units['n_sites'].astype(np.int64), pb.units['n_reads'].astype(np.int64)
+    out = {}
+    try:
+        for tensor in (True, False):
+            gpu_ctx.set_tile_path(tensor)
+            b = lg.Batch(gpu_ctx, pb)
+            b.upload()
+            b.run(6, lg.MODE_ALL_PAIRS)
+            out[tensor] = b.download()
+            if tensor:
+                b.run(6, lg.MODE_ALL_PAIRS)
+                again = b.download()
+                assert np.array_equal(again.records, out[True].records)                  # deterministic
+            b.close()
+    finally:
+        gpu_ctx.set_tile_path(True)
+    res = out[True]
+    assert np.array_equal(res.records, out[False].records)
+    assert np.array_equal(res.site_mean, out[False].site_mean, equal_nan=True)
+    assert np.array_equal(res.site_cnt, out[False].site_cnt)
+    _order_and_mean_properties(pb, res)
+    rng = np.random.default_rng(2)
+    small = np.flatnonzero((S <= 64) & (R <= 256) & (S >= 2))
+    mid = np.flatnonzero(((S > 64) | (R > 256)) & (S * S * R < 4e8) & (S >= 2))
+    big = np.flatnonzero(((S > 64) | (R > 256)) & (S * S * R >= 4e8) & (S * S * R < 6e9))
+    picks = rng.choice(small, 12, replace=False).tolist() + rng.choice(mid, 16, replace=False).tolist() + \
+        rng.choice(big, min(4, len(big)), replace=False).tolist()
+    for g in picks:
+        a, k = raw[g]
+        eu = enc.EncodedUnit([1000 + 37 * s for s in range(a.shape[0])],
+                             [("mismatch", "snp", "het_snp")[int(x)] for x in k], synth.labels_from_alleles(a))
+        i, j, mi, tab, mean, cnt_o = oracle_unit(eu, 6)
+        u = res.unit_records(g)
+        assert u['i'].tolist() == i.tolist() and u['j'].tolist() == j.tolist(), "pair set of unit %d" % g
+        assert_mi_close(u['mi'], mi)
+        o = int(pb.units['site_off'][g])
+        assert_mi_close(res.site_mean[o:o + eu.n_sites], mean)
+        assert res.site_cnt[o:o + eu.n_sites].tolist() == cnt_o.tolist()
+
+
+@pytest.mark.parametrize("cov", [0.01, 0.05, 0.1, 0.25, 0.5])
+def test_cfg5_full_size_oracle_sample(lg, gpu_ctx, cov):
+    """BASELINE.json configs[4] at full size: 20 000 units per grid point; per point the size-independent
+    properties, and 6 sampled units against the oracle (pair set, MI, means)."""
+    sb = synth.make_uniform(20261030 + int(cov * 1000), 20000, 50, 200, cov)
+    pb = sb.plane_batch()
+    b = lg.Batch(gpu_ctx, pb)
+    b.upload()
+    rng = np.random.default_rng(int(cov * 1000))
+    picks = rng.choice(20000, 6, replace=False).tolist()
+    survivors = []
+    for mc in (6, 10, 20, 50):
+        b.run(mc, lg.MODE_ALL_PAIRS)
+        res = b.download()
+        survivors.append(res.n_records)
+        _order_and_mean_properties(pb, res)
+        for g in picks:
+            i, j, mi, tab, mean, cnt_o = oracle_unit(sb.encoded(g), mc)
+            u = res.unit_records(g)
+            assert u['i'].tolist() == i.tolist() and u['j'].tolist() == j.tolist()
+            assert_mi_close(u['mi'], mi)
+            assert_mi_close(res.site_mean[g * 50:(g + 1) * 50], mean)
+    assert survivors == sorted(survivors, reverse=True)
     b.close()
 
 
