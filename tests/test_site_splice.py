@@ -1,12 +1,14 @@
 """Site x splice-site MI: the reference's second mutual_info_score call
 site, giremi/script/calculate_site_splice_mi.py:106-125."""
+import importlib
 import os
 import sys
 
 import numpy as np
+import pandas as pd
 import pytest
 
-from conftest import ROOT, assert_mi_close
+from conftest import ROOT, assert_mi_close, unhex
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import oracle  # noqa: E402
@@ -33,6 +35,46 @@ def random_case(rng, n_sites=30, n_splices=12):
                 pairs.append((label, seq, str(sp)))
     pairs.append((label, seq, "chr1:999999"))                 # a splice label nobody has: one class -> 0.0
     return sites, splices, pairs
+
+
+def golden_tables(golden, tmp_path):
+    """The two TSVs the golden vectors were generated from (tests/golden/make_site_splice_golden.py)."""
+    g = golden("site_splice.json")
+    sf, pf = str(tmp_path / "site.tsv"), str(tmp_path / "splice.tsv")
+    pd.DataFrame(g["site_rows"], columns=["read_name", "chromosome", "pos", "seq"]).to_csv(sf, sep="\t", index=False)
+    pd.DataFrame(g["splice_rows"], columns=["read_name", "chromosome", "pos", "type", "corrected_pos", "annotation"]
+                 ).to_csv(pf, sep="\t", index=False)
+    return g, sf, pf
+
+
+def test_oracle_and_table_builder_against_the_reference_script(golden, tmp_path):
+    """PIN: tests/golden/site_splice.json holds what the reference's own calculate_site_splice_mi.py main()
+    wrote for these two tables.  The host-side table builder must list the same pairs with the same counts in
+    the same order, and the oracle must reproduce every MI bit for bit."""
+    ss = importlib.import_module("l-giremi_b200.site_splice")
+    g, sf, pf = golden_tables(golden, tmp_path)
+    rows, sites, splices = ss.read_tables(sf, pf)
+    want = g["pairs"]
+    assert [[r[0], int(r[1]), r[2], int(r[3]), r[4]] for r in rows] == [p[:5] for p in want]
+    triples = [(r[0] + ':' + r[1], r[2], r[0] + ':' + r[3]) for r in rows]
+    got = oracle.site_splice_mutual_info(sites, splices, triples)
+    assert got == [unhex(p[5]) for p in want]
+    assert max(got) == pytest.approx(np.log(2), abs=1e-3) and min(got) == 0.0     # an exact link and a one-class pair
+
+
+@pytest.mark.gpu
+def test_site_splice_cli_drop_in_against_the_reference_script(lg, gpu_ctx, golden, tmp_path):
+    """The drop-in for the console script: same output table as the reference wrote."""
+    ss = importlib.import_module("l-giremi_b200.site_splice")
+    g, sf, pf = golden_tables(golden, tmp_path)
+    prefix = str(tmp_path / "out")
+    ss.main(["-m", sf, "-s", pf, "-o", prefix])
+    table = pd.read_table(prefix + ".site_splice_pair", dtype={"chromosome": str, "seq": str}, float_precision="round_trip")
+    assert list(table.columns) == g["pair_columns"]
+    want = g["pairs"]
+    assert [[str(r.chromosome), int(r.site_pos), str(r.seq), int(r.splice_pos), int(r["count"])]
+            for _, r in table.iterrows()] == [p[:5] for p in want]
+    assert_mi_close(table["mi"].to_numpy(), [unhex(p[5]) for p in want], 0.9, "site x splice MI")
 
 
 def test_oracle_follows_the_script_literally():
