@@ -32,6 +32,7 @@ import pandas as pd
 
 from . import api
 from .encode import concat_plane_batches, encode_mismatches_native
+from .extract import encode_indexed, get_region_sites
 
 _PAIR_COLUMNS = ['chromosome', 'strand', 'site1_pos', 'site1_type', 'site2_pos', 'site2_type', 'mi']
 _SITE_COLUMNS = ['type', 'chromosome', 'strand', 'pos', 'ref', 'change_type', 'ratio', 'allelic_ratio_diff',
@@ -48,12 +49,13 @@ class RegionExtract:
 
     __slots__ = ("chromosome", "encoded", "site_rows", "site_pos", "removed_rows", "mismatches", "removed")
 
-    def __init__(self, chromosome, mismatches, removed, keep_dicts=True):
+    def __init__(self, chromosome, mismatches, removed, keep_dicts=True, indexed=False):
         self.chromosome = chromosome
         # a strand enters the MI step only with at least two sites (mismatch.py:388)
-        # (native encoder, csrc/lgmi_host.inl: one PlaneBatch of one unit per strand)
-        self.encoded = {s: (encode_mismatches_native(mismatches[s]) if len(mismatches[s]) > 1 else None)
-                        for s in _STRANDS}
+        # indexed: the allele lists hold read indices (extract.get_region_sites) and the planes are written from
+        # them directly; else read names through the native dict encoder (csrc/lgmi_host.inl, lgmi_encode_unit)
+        encode = encode_indexed if indexed else encode_mismatches_native
+        self.encoded = {s: (encode(mismatches[s]) if len(mismatches[s]) > 1 else None) for s in _STRANDS}
         self.site_rows, self.site_pos = {}, {}
         for s in _STRANDS:
             self.site_rows[s], self.site_pos[s] = _site_frame_rows(chromosome, s, mismatches[s])
@@ -62,10 +64,24 @@ class RegionExtract:
         self.removed = removed if keep_dicts else None
 
 
-def extract_region(chromosome, start_pos, end_pos, sam, genome, keep_dicts=True, **filters) -> RegionExtract:
-    """Extraction and site filters by the reference's own code (mismatch.py:11-342), then encode."""
-    from giremi.mismatch import get_region_mismatches_with_filters
+def native_extraction_enabled():
+    """LGMI_NATIVE_EXTRACT=0 keeps the reference's own extraction inside the batched seam."""
+    import os
+    return os.environ.get("LGMI_NATIVE_EXTRACT", "1") != "0"
+
+
+def extract_region(chromosome, start_pos, end_pos, sam, genome, keep_dicts=True, native=None, **filters) -> RegionExtract:
+    """Extraction, site filters and encoding of one footprint.  For cs-tag input (the reference's default mode)
+    the reads go through the C++ cs scanner and the planes are written from interned read indices
+    (extract.get_region_sites, the same sites as mismatch.py:11-342 field for field); for MD / CIGAR input
+    (mode='cigar') or native=False, the reference's own function runs and its dicts are encoded."""
     filters.pop('min_common_reads', None)
+    if native is None:
+        native = native_extraction_enabled()
+    if native and filters.get('mode', 'cs') == 'cs':
+        sites, removed, _names = get_region_sites(chromosome, start_pos, end_pos, sam, genome, **filters)
+        return RegionExtract(chromosome, sites, removed, keep_dicts=keep_dicts, indexed=True)
+    from giremi.mismatch import get_region_mismatches_with_filters
     mismatches, removed = get_region_mismatches_with_filters(
         chromosome=chromosome, start_pos=start_pos, end_pos=end_pos, sam=sam, genome=genome, **filters)
     return RegionExtract(chromosome, mismatches, removed, keep_dicts=keep_dicts)

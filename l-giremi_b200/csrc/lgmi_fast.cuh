@@ -49,6 +49,21 @@ struct __align__(16) FastLn {
 struct FastTab {
   FastLn ln[kFastMaxR + 1];   // 4112 B
   double inv[kFastMaxR + 1];  // RN(1/k), inv[0] = 0
+  __device__ __forceinline__ const FastLn& ln_at(uint32_t k) const { return ln[k]; }
+  __device__ __forceinline__ double inv_at(uint32_t k) const { return inv[k]; }
+};
+// the same two look-ups for counts of any size: ln k from the context's global table, 1/k by the correctly
+// rounded reciprocal (what the shared-memory table holds for k <= 256)
+struct GlobalTab {
+  const lg_dd* ln;
+  __device__ __forceinline__ FastLn ln_at(uint32_t k) const {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(ln) + k);
+    FastLn r;
+    r.hi = v.x;
+    r.lo = v.y;
+    return r;
+  }
+  __device__ __forceinline__ double inv_at(uint32_t k) const { return k ? __drcp_rn((double)k) : 0.0; }
 };
 
 // one work item of the fast kernel == one whole unit
@@ -192,27 +207,29 @@ __device__ __forceinline__ double cell_term(double ln_n, double dn, const CellCt
   return (fabs(t) < LG_EPS) ? 0.0 : t;
 }
 
-__device__ __forceinline__ double cell_of(const FastTab& tab, uint32_t n, const CellCtx& cx, const FastLn& er,
+template <class Tab>
+__device__ __forceinline__ double cell_of(const Tab& tab, uint32_t n, const CellCtx& cx, const FastLn& er,
                                           const FastLn& ec) {
-  return cell_term(tab.ln[n].hi, u32_to_double(n), cx, ln_prod(er, ec));
+  return cell_term(tab.ln_at(n).hi, u32_to_double(n), cx, ln_prod(er, ec));
 }
 
 // 2x2 table (no "other" label among the common reads).  Cell order mm, mM, Mm, MM.
-__device__ __forceinline__ double mi_2x2(const FastTab& tab, uint32_t n_mm, uint32_t n_mM, uint32_t n_Mm,
+template <class Tab>
+__device__ __forceinline__ double mi_2x2(const Tab& tab, uint32_t n_mm, uint32_t n_mM, uint32_t n_Mm,
                                          uint32_t n_MM) {
   const uint32_t r_m = n_mm + n_mM, r_M = n_Mm + n_MM;
   const uint32_t c_m = n_mm + n_Mm, c_M = n_mM + n_MM;
   const uint32_t N = r_m + r_M;
-  const CellCtx cx{u32_to_double(N), tab.inv[N], tab.ln[N].hi};
-  const FastLn ecm = tab.ln[c_m], ecM = tab.ln[c_M];
+  const CellCtx cx{u32_to_double(N), tab.inv_at(N), tab.ln_at(N).hi};
+  const FastLn ecm = tab.ln_at(c_m), ecM = tab.ln_at(c_M);
   double s = 0.0;
   {
-    const FastLn erm = tab.ln[r_m];
+    const FastLn erm = tab.ln_at(r_m);
     s = __dadd_rn(s, cell_of(tab, n_mm, cx, erm, ecm));
     s = __dadd_rn(s, cell_of(tab, n_mM, cx, erm, ecM));
   }
   {
-    const FastLn erM = tab.ln[r_M];
+    const FastLn erM = tab.ln_at(r_M);
     s = __dadd_rn(s, cell_of(tab, n_Mm, cx, erM, ecm));
     s = __dadd_rn(s, cell_of(tab, n_MM, cx, erM, ecM));
   }
@@ -221,7 +238,8 @@ __device__ __forceinline__ double mi_2x2(const FastTab& tab, uint32_t n_mm, uint
 }
 
 // 3x3 table T[a*3+b] (label order other, minor, major)
-__device__ __forceinline__ double mi_3x3(const FastTab& tab, const uint32_t T[9]) {
+template <class Tab>
+__device__ __forceinline__ double mi_3x3(const Tab& tab, const uint32_t T[9]) {
   uint32_t r[3], c[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) r[a] = T[3 * a] + T[3 * a + 1] + T[3 * a + 2];
@@ -233,16 +251,16 @@ __device__ __forceinline__ double mi_3x3(const FastTab& tab, const uint32_t T[9]
   int nnz = 0;
 #pragma unroll
   for (int k = 0; k < 9; ++k) nnz += (T[k] != 0u);
-  const CellCtx cx{u32_to_double(N), tab.inv[N], tab.ln[N].hi};
+  const CellCtx cx{u32_to_double(N), tab.inv_at(N), tab.ln_at(N).hi};
   FastLn ec[3];
 #pragma unroll
-  for (int b = 0; b < 3; ++b) ec[b] = tab.ln[c[b]];
+  for (int b = 0; b < 3; ++b) ec[b] = tab.ln_at(c[b]);
   double s;
   if (nnz < 8) {  // ndarray.sum(): plain loop below 8 elements; absent cells add an exact 0.0
     s = 0.0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const FastLn er = tab.ln[r[a]];
+      const FastLn er = tab.ln_at(r[a]);
 #pragma unroll
       for (int b = 0; b < 3; ++b) s = __dadd_rn(s, cell_of(tab, T[3 * a + b], cx, er, ec[b]));
     }
@@ -251,7 +269,7 @@ __device__ __forceinline__ double mi_3x3(const FastTab& tab, const uint32_t T[9]
     int z = 9;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const FastLn er = tab.ln[r[a]];
+      const FastLn er = tab.ln_at(r[a]);
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
         t[3 * a + b] = cell_of(tab, T[3 * a + b], cx, er, ec[b]);

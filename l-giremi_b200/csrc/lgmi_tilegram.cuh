@@ -35,14 +35,20 @@ namespace lgmi {
 
 constexpr int kTgSitesI = 128;                        // sites per row block: one per TMEM lane
 constexpr int kTgSitesJ = 48;                         // partner sites per column block
+constexpr int kTgSites = kTgSitesI + kTgSitesJ;       // plane rows a tile reads per k-block
 constexpr int kTgN = 3 * kTgSitesJ;                   // 144 columns per accumulator (label-major)
-constexpr int kTgThreads = 256;
+constexpr int kTgThreads = 384;                       // 12 warps: readout = 4 lane quarters x 3 groups of 16 partners
 constexpr uint32_t kTgATile = 128u * 128u;            // one label tile of A: 128 rows x 128 reads, 16 KB
 constexpr uint32_t kTgABytes = 3u * kTgATile;         // 48 KB
 constexpr uint32_t kTgBBytes = (uint32_t)kTgN * 128u; // 18 KB
 constexpr uint32_t kTgStageBytes = kTgABytes + kTgBBytes;
-constexpr int kTgStages = 2;
-constexpr uint32_t kTgSmemBytes = kTgStages * kTgStageBytes + 1024u /*align*/ + 256u /*barriers*/;
+constexpr int kTgStages = 2;                          // expanded operand stages
+constexpr int kTgAhead = 2;                           // k-blocks of raw planes requested ahead (cp.async)
+constexpr int kTgRawStages = kTgAhead + 1;
+constexpr uint32_t kTgRawBytes = (uint32_t)kTgSites * 3u * 16u;  // [site][plane M, m, C][4 words] = 8448 B
+constexpr int kTgRing = 8;                            // ring of tile ids; kTgAhead + 2 of them are fetched ahead of the
+constexpr int kTgRingAhead = kTgAhead + 2;            // tile being computed (the request cursor can be that many tiles on)
+constexpr uint32_t kTgSmemBytes = kTgStages * kTgStageBytes + kTgRawStages * kTgRawBytes + 1024u /*align*/ + 256u /*barriers*/;
 constexpr uint32_t kTgTmemCols = 512;                 // 3 x 144 used
 constexpr uint32_t kTgMaxReads = 65535;               // counts are stored as u16
 
@@ -65,21 +71,74 @@ __device__ __forceinline__ void tmem_wait_x8(uint32_t (&r)[8]) {
                : "memory");
 }
 
-// one k-block (128 reads) of the tile's operands: thread item = (site, 32-read word) -> the three
-// label rows' 2 x 16 bytes each.  Rows of absent sites (>= S) are left as they are: their products
-// land in accumulator rows / columns nobody reads.
-__device__ __forceinline__ void tg_expand(uint8_t* __restrict__ stage, const uint32_t* __restrict__ unit_planes, uint32_t W,
-                                          uint32_t S, uint32_t i0, uint32_t j0, uint32_t kb) {
-  constexpr uint32_t kItemsA = (uint32_t)kTgSitesI * 4u, kItems = kItemsA + (uint32_t)kTgSitesJ * 4u;
-#pragma unroll 3
+struct TileGramParams {
+  const DevUnit* units;
+  const uint32_t* planes;
+  const uint8_t* site_flags;
+  uint32_t mode;
+  const TileItem* tiles;   // I: block of 128 sites, J: block of 48 sites
+  uint32_t n_tiles;
+  uint2* cnt;              // three 8-byte words per pair slot (DevUnit::dense_off + pair index)
+  uint32_t* next;          // work counter (zeroed by k_run_init)
+  uint32_t* error;
+};
+
+// position in this CTA's stream of (tile, k-block) steps; `seq` counts the CTA's tiles, the tile id comes from the ring
+struct TgCursor {
+  uint32_t seq, kb, nkb;        // nkb == 0: past the end
+  uint32_t i0, j0, S, W, site_off;
+  const uint32_t* planes;       // the unit's first word
+  uint64_t dense_off;
+  __device__ __forceinline__ bool valid() const { return nkb != 0u; }
+  __device__ __forceinline__ void load(const TileGramParams& P, const uint32_t* ring) {
+    const uint32_t t = ring[seq % (uint32_t)kTgRing];
+    nkb = 0u;
+    kb = 0u;
+    if (t >= P.n_tiles) return;
+    const TileItem tile = P.tiles[t];
+    const DevUnit u = P.units[tile.unit];
+    i0 = (uint32_t)tile.I * (uint32_t)kTgSitesI;
+    j0 = (uint32_t)tile.J * (uint32_t)kTgSitesJ;
+    S = u.S;
+    W = u.W;
+    site_off = u.site_off;
+    planes = P.planes + u.plane_off;
+    dense_off = u.dense_off;
+    nkb = u.W >> 2;  // whole k-blocks of 128 reads (W is a multiple of 4; pad bits are zero)
+  }
+  __device__ __forceinline__ void advance(const TileGramParams& P, const uint32_t* ring) {
+    if (!valid()) return;
+    if (++kb < nkb) return;
+    ++seq;
+    load(P, ring);
+  }
+};
+
+// request the raw plane words of one k-block of a tile: 16 bytes per (site, plane); absent sites are skipped
+__device__ __forceinline__ void tg_request(uint8_t* __restrict__ raw, const TgCursor& c) {
+  if (!c.valid()) return;
+#pragma unroll
+  for (uint32_t e = threadIdx.x; e < (uint32_t)kTgSites * 3u; e += kTgThreads) {
+    const uint32_t sl = e / 3u, plane = e - 3u * sl;
+    const uint32_t s = (sl < (uint32_t)kTgSitesI) ? c.i0 + sl : c.j0 + (sl - (uint32_t)kTgSitesI);
+    if (s < c.S) cp_async16(raw + (size_t)e * 16u, c.planes + ((size_t)s * 3u + plane) * c.W + c.kb * 4u, true);
+  }
+}
+
+// one k-block (128 reads) of the tile's operands from the staged raw words: thread item = (site, 32-read word)
+// -> the three label rows' 2 x 16 bytes each, straight into the swizzled K-major layout.  Rows of absent sites
+// (>= S) are left as they are: their products land in accumulator rows / columns nobody reads.
+__device__ __forceinline__ void tg_expand(uint8_t* __restrict__ stage, const uint8_t* __restrict__ raw, const TgCursor& c) {
+  constexpr uint32_t kItemsA = (uint32_t)kTgSitesI * 4u, kItems = (uint32_t)kTgSites * 4u;
+#pragma unroll
   for (uint32_t e = threadIdx.x; e < kItems; e += kTgThreads) {
     const bool is_a = e < kItemsA;
-    const uint32_t local = is_a ? e : e - kItemsA;
-    const uint32_t sl = local >> 2, w = local & 3u;
-    const uint32_t s = (is_a ? i0 : j0) + sl;
-    if (s >= S) continue;
-    const uint32_t* __restrict__ src = unit_planes + (size_t)s * 3u * W + kb * 4u + w;
-    const uint32_t M = __ldg(src), m = __ldg(src + W), C = __ldg(src + 2u * W);
+    const uint32_t sl_all = e >> 2, w = e & 3u;               // site row of the raw stage
+    const uint32_t sl = is_a ? sl_all : sl_all - (uint32_t)kTgSitesI;
+    const uint32_t s = (is_a ? c.i0 : c.j0) + sl;
+    if (s >= c.S) continue;
+    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(raw) + sl_all * 12u + w;
+    const uint32_t M = src[0], m = src[4], C = src[8];
     const uint32_t L2 = M & C, L1 = m & C & ~M, L0 = C & ~M & ~m;
     uint8_t* t0 = is_a ? stage : stage + kTgABytes;                 // label "other"
     uint8_t* t1 = is_a ? stage + kTgATile : t0;                     // minor
@@ -94,33 +153,22 @@ __device__ __forceinline__ void tg_expand(uint8_t* __restrict__ stage, const uin
   }
 }
 
-struct TileGramParams {
-  const DevUnit* units;
-  const uint32_t* planes;
-  const uint8_t* site_flags;
-  uint32_t mode;
-  const TileItem* tiles;   // I: block of 128 sites, J: block of 48 sites
-  uint32_t n_tiles;
-  uint2* cnt;              // three 8-byte words per pair slot (DevUnit::dense_off + pair index)
-  uint32_t* next;          // work counter (zeroed by k_run_init)
-  uint32_t* error;
-};
-
 __global__ void __launch_bounds__(kTgThreads, 1) k_tile_gram(const TileGramParams P) {
   extern __shared__ uint8_t tg_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tg_raw) + 1023u) & ~uintptr_t(1023));
-  uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + kTgStages * kTgStageBytes);  // [stages]
+  uint8_t* raw0 = smem + kTgStages * kTgStageBytes;
+  uint64_t* mma_done = reinterpret_cast<uint64_t*>(raw0 + kTgRawStages * kTgRawBytes);  // [stages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + kTgStages);
-  uint32_t* s_next = tmem_slot + 1;
+  uint32_t* ring = tmem_slot + 1;                                                       // [kTgRing] tile ids
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
   if (tid == 0) {
     for (int s = 0; s < kTgStages; ++s) mbar_init(&mma_done[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    *s_next = atomicAdd(P.next, 1u);
+    for (int q = 0; q < kTgRingAhead; ++q) ring[q] = atomicAdd(P.next, 1u);  // this CTA's first tiles
   }
+  __syncwarp();
   if (warp == 0) {
-    __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(kTgTmemCols)
                  : "memory");
@@ -144,57 +192,64 @@ __global__ void __launch_bounds__(kTgThreads, 1) k_tile_gram(const TileGramParam
     }
   };
 
-  uint32_t t = *s_next;
-  while (t < P.n_tiles) {
-    const TileItem tile = P.tiles[t];
-    const DevUnit u = P.units[tile.unit];
-    const uint32_t* __restrict__ unit_planes = P.planes + u.plane_off;
-    const uint32_t i0 = (uint32_t)tile.I * (uint32_t)kTgSitesI, j0 = (uint32_t)tile.J * (uint32_t)kTgSitesJ;
-    const uint32_t nkb = u.W >> 2;  // whole k-blocks of 128 reads (W is a multiple of 4; pad bits are zero)
+  // two cursors over the CTA's (tile, k-block) steps: `cur` is computed, `pre` runs kTgAhead steps ahead and only
+  // requests raw plane words (cp.async), across tile boundaries
+  TgCursor cur, pre;
+  cur.seq = 0u;
+  cur.load(P, ring);
+  pre = cur;
+#pragma unroll
+  for (int d = 0; d < kTgAhead; ++d) {
+    tg_request(raw0 + (uint32_t)d * kTgRawBytes, pre);
+    cp_async_commit();
+    pre.advance(P, ring);
+  }
 
-    for (uint32_t kb = 0; kb < nkb; ++kb) {
-      wait_stage(stage);  // the MMAs that read this stage two k-blocks ago
-      uint8_t* st = smem + stage * kTgStageBytes;
-      tg_expand(st, unit_planes, u.W, u.S, i0, j0, kb);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t sa = smem_u32(st), sb = sa + kTgABytes;
-        const uint64_t db = umma_desc_sw128(sb);
+  for (uint32_t step = 0; cur.valid(); ++step) {
+    tg_request(raw0 + ((step + (uint32_t)kTgAhead) % (uint32_t)kTgRawStages) * kTgRawBytes, pre);
+    cp_async_commit();            // (possibly empty: exactly one group per step)
+    pre.advance(P, ring);
+    cp_async_wait<kTgAhead>();    // this thread's part of step `step` has landed
+    wait_stage(stage);            // the MMAs that read this operand stage two steps ago
+    __syncthreads();              // ... everybody's part
+    uint8_t* st = smem + stage * kTgStageBytes;
+    tg_expand(st, raw0 + (step % (uint32_t)kTgRawStages) * kTgRawBytes, cur);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+    __syncthreads();              // (also: the raw stage is consumed; it is requested again next step)
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t sa = smem_u32(st), sb = sa + kTgABytes;
+      const uint64_t db = umma_desc_sw128(sb);
 #pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) {  // K = 32 reads per instruction: +32 B on both operands
+      for (uint32_t k = 0; k < 4; ++k) {  // K = 32 reads per instruction: +32 B on both operands
 #pragma unroll
-          for (uint32_t a = 0; a < 3; ++a)
-            umma_i8(tmem_base + a * (uint32_t)kTgN, umma_desc_sw128(sa + a * kTgATile) + 2ull * k, db + 2ull * k, idesc,
-                    (kb | k) != 0u);
-        }
-        umma_commit(&mma_done[stage]);
+        for (uint32_t a = 0; a < 3; ++a)
+          umma_i8(tmem_base + a * (uint32_t)kTgN, umma_desc_sw128(sa + a * kTgATile) + 2ull * k, db + 2ull * k, idesc,
+                  (cur.kb | k) != 0u);
       }
-      pending |= 1u << stage;
-      stage ^= 1u;
+      umma_commit(&mma_done[stage]);
     }
-    if (tid == 0) *s_next = atomicAdd(P.next, 1u);  // (read after the barrier that ends the readout)
-    // all MMAs of the tile: the commits complete in issue order
-    wait_stage(stage);  // older commit first
-    wait_stage(stage ^ 1u);
-    tc_fence_after();
+    pending |= 1u << stage;
+    stage ^= 1u;
 
-    // ---- readout: lane = site i; this warp's lane quarter and column half
-    {
-      const uint32_t lq = warp & 3u, half = warp >> 2;
-      const uint32_t i = i0 + lq * 32u + lane;
-      const uint8_t* __restrict__ flags = P.site_flags + u.site_off;
-      const bool i_ok = i < u.S;
-      const bool het_i = i_ok && (flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
-      const uint64_t row = u.dense_off + lg_row_off(i_ok ? i : 0u, u.S);
-      // nothing of this warp's 32 rows pairs with a column of this half: skip the loads
-      const uint32_t j_hi = min(j0 + (half + 1u) * 24u, u.S);  // exclusive
-      if (i0 + lq * 32u + 1u < j_hi) {
+    if (cur.kb + 1u == cur.nkb) {
+      // ---- the tile's MMAs are all issued: wait for them (commits complete in issue order), then read out
+      wait_stage(stage);  // older commit first
+      wait_stage(stage ^ 1u);
+      tc_fence_after();
+      {
+        // lane = site i; this warp's lane quarter and its 16 partner columns
+        const uint32_t lq = warp & 3u, cg = warp >> 2;
+        const uint32_t i = cur.i0 + lq * 32u + lane;
+        const uint8_t* __restrict__ flags = P.site_flags + cur.site_off;
+        const bool i_ok = i < cur.S;
+        const bool het_i = i_ok && (flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
+        const uint64_t row = cur.dense_off + lg_row_off(i_ok ? i : 0u, cur.S);
 #pragma unroll 1
-        for (uint32_t c = 0; c < 3u; ++c) {
-          const uint32_t jl = half * 24u + c * 8u;  // first of eight partner columns
-          if (j0 + jl >= u.S || i0 + lq * 32u >= j0 + jl + 7u) continue;  // (warp-uniform) no pair i < j here
+        for (uint32_t c = 0; c < 2u; ++c) {
+          const uint32_t jl = cg * 16u + c * 8u;  // first of eight partner columns
+          // (warp-uniform) no pair i < j among these rows and columns: skip the loads
+          if (cur.j0 + jl >= cur.S || cur.i0 + lq * 32u >= cur.j0 + jl + 7u) continue;
           uint32_t r[3][3][8];
 #pragma unroll
           for (uint32_t a = 0; a < 3; ++a)
@@ -207,8 +262,8 @@ __global__ void __launch_bounds__(kTgThreads, 1) k_tile_gram(const TileGramParam
             for (uint32_t b = 0; b < 3; ++b) tmem_wait_x8(r[a][b]);
 #pragma unroll
           for (uint32_t q = 0; q < 8; ++q) {
-            const uint32_t j = j0 + jl + q;
-            if (!i_ok || j >= u.S || i >= j) continue;
+            const uint32_t j = cur.j0 + jl + q;
+            if (!i_ok || j >= cur.S || i >= j) continue;
             const bool het = het_i || (flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
             const uint32_t fl = (het ? kTgHetPair : 0u) | ((skip_nonhet && !het) ? kTgNotEvaluated : 0u);
             uint2 w0, w1, w2;
@@ -225,13 +280,16 @@ __global__ void __launch_bounds__(kTgThreads, 1) k_tile_gram(const TileGramParam
           }
         }
       }
+      tc_fence_before();
+      __syncthreads();  // accumulators read: TMEM may be overwritten by the next tile's first MMA
+      tc_fence_after();
+      // one more tile id into the ring (a slot whose previous tile finished long ago); its first reader is the
+      // request cursor, at the earliest one step -- two barriers -- from here
+      if (tid == 0) ring[(cur.seq + (uint32_t)kTgRingAhead) % (uint32_t)kTgRing] = atomicAdd(P.next, 1u);
     }
-    tc_fence_before();
-    __syncthreads();  // accumulators read: TMEM may be overwritten; s_next is the next tile
-    tc_fence_after();
-    t = *s_next;
-    __syncthreads();  // everybody has read s_next before thread 0 replaces it
+    cur.advance(P, ring);
   }
+  cp_async_wait<0>();
 
   tc_fence_before();
   __syncthreads();
@@ -241,52 +299,97 @@ __global__ void __launch_bounds__(kTgThreads, 1) k_tile_gram(const TileGramParam
 }
 
 // ---------------------------------------------------------------------------
-// MI of the pairs k_tile_gram counted: one CTA per work item (<= 2048 consecutive pairs of a unit),
-// one thread per pair.  Writes the unit's dense MI scratch (what k_tile_mi writes) and the item's
-// number of emitted pairs (what k_count computes for the other paths).
-__global__ void __launch_bounds__(kThreads) k_tile_finish(const RunParams P, const uint2* __restrict__ cnt) {
-  __shared__ uint32_t s_warp[kThreads / 32];
+// MI of the pairs k_tile_gram counted: one CTA per work item (<= 2048 consecutive pairs of a unit).
+// Pass 1 (one thread per pair): min-common filter, emitted-pair count of the item (what k_count computes for
+// the other paths), NaN into the dense MI scratch for the pairs without MI, and the others listed as "2x2"
+// (no "other" label among the common reads) or "3x3".  Pass 2: the branch-free fp64 epilogues of lgmi_fast.cuh
+// (same operations and roundings as lgmi_math.cuh: Markstein quotient from the correctly rounded reciprocal,
+// double-double logs from the context's table) over warp-sized chunks of each list -- full warps, no divergence.
+__device__ __forceinline__ uint32_t tile_cnt_load(const uint2* __restrict__ cnt, uint64_t slot, uint32_t T[9]) {
+  const uint2 w0 = __ldg(cnt + slot * 3ull), w1 = __ldg(cnt + slot * 3ull + 1), w2 = __ldg(cnt + slot * 3ull + 2);
+  T[0] = w0.x & 0xffffu; T[1] = w0.x >> 16; T[2] = w0.y & 0xffffu; T[3] = w0.y >> 16;
+  T[4] = w1.x & 0xffffu; T[5] = w1.x >> 16; T[6] = w1.y & 0xffffu; T[7] = w1.y >> 16;
+  T[8] = w2.x & 0xffffu;
+  return w2.x >> 16;  // flag bits
+}
+
+__global__ void __launch_bounds__(kThreads, 3) k_tile_finish(const RunParams P, const uint2* __restrict__ cnt) {
+  __shared__ uint16_t s_list[kPairsMax];  // pairs with a 2x2 table from the front, with "other" cells from the back
+  __shared__ uint32_t s_n2, s_n3, s_emit;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const LnGlobal ln{P.lntab};
+  const uint32_t lt = (1u << lane) - 1u;
+  const GlobalTab tab{P.lntab};
   const bool het_only = (P.mode & LGMI_MODE_HET_ONLY) != 0u;
   for (uint32_t item_idx = blockIdx.x; item_idx < P.n_items; item_idx += gridDim.x) {
     const Item it = P.items[item_idx];
     if (!(it.flags & ITEM_TILED_GRAM)) continue;
     const DevUnit u = P.units[it.unit];
+    const uint64_t slot0 = u.dense_off + it.pair_begin;
+    __syncthreads();  // the previous item's lists have been consumed
+    if (tid == 0) {
+      s_n2 = 0u;
+      s_n3 = 0u;
+      s_emit = 0u;
+    }
+    __syncthreads();
     uint32_t mine = 0;
-    for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
-      const uint64_t slot = u.dense_off + it.pair_begin + pl;
-      const uint2 w0 = __ldg(cnt + slot * 3ull), w1 = __ldg(cnt + slot * 3ull + 1), w2 = __ldg(cnt + slot * 3ull + 2);
-      uint32_t T[9];
-      T[0] = w0.x & 0xffffu; T[1] = w0.x >> 16; T[2] = w0.y & 0xffffu; T[3] = w0.y >> 16;
-      T[4] = w1.x & 0xffffu; T[5] = w1.x >> 16; T[6] = w1.y & 0xffffu; T[7] = w1.y >> 16;
-      T[8] = w2.x & 0xffffu;
-      const uint32_t fl = w2.x >> 16;
-      uint32_t N = 0;
+    const uint32_t n_slots = (it.pair_cnt + 31u) & ~31u;
+    for (uint32_t pl = tid; pl < n_slots; pl += kThreads) {
+      uint32_t cls = 0u;  // 0 no MI, 2 -> 2x2 list, 3 -> 3x3 list
+      if (pl < it.pair_cnt) {
+        uint32_t T[9];
+        const uint32_t fl = tile_cnt_load(cnt, slot0 + pl, T);
+        uint32_t N = 0;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) N += T[k];
-      double v = lg_nan();
-      if (!(fl & kTgNotEvaluated) && (int)N >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
-        if ((T[0] | T[1] | T[2] | T[3] | T[6]) == 0u) v = lg_mi_from_2x2(T[4], T[5], T[7], T[8], ln);
-        else v = lg_mi_from_table(T, ln);
-        mine += ((fl & kTgHetPair) || !het_only) ? 1u : 0u;
-      }
-      P.dense[slot] = v;
-      if (P.mode & LGMI_MODE_EMIT_COUNTS) {
+        for (int k = 0; k < 9; ++k) N += T[k];
+        if (!(fl & kTgNotEvaluated) && (int)N >= P.min_common) {  // strict '<' drops (mutual_information.py:19)
+          cls = (T[0] | T[1] | T[2] | T[3] | T[6]) ? 3u : 2u;
+          mine += ((fl & kTgHetPair) || !het_only) ? 1u : 0u;
+        } else {
+          P.dense[slot0 + pl] = lg_nan();
+        }
+        if (P.mode & LGMI_MODE_EMIT_COUNTS) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) P.tile_counts[slot * 9ull + k] = T[k];
+          for (int k = 0; k < 9; ++k) P.tile_counts[(slot0 + pl) * 9ull + k] = T[k];
+        }
       }
+      const uint32_t m2 = __ballot_sync(0xffffffffu, cls == 2u);
+      const uint32_t m3 = __ballot_sync(0xffffffffu, cls == 3u);
+      uint32_t b2 = 0u, b3 = 0u;
+      if (lane == 0) {
+        if (m2) b2 = atomicAdd(&s_n2, (uint32_t)__popc(m2));
+        if (m3) b3 = atomicAdd(&s_n3, (uint32_t)__popc(m3));
+      }
+      b2 = __shfl_sync(0xffffffffu, b2, 0);
+      b3 = __shfl_sync(0xffffffffu, b3, 0);
+      if (cls == 2u) s_list[b2 + __popc(m2 & lt)] = (uint16_t)pl;
+      if (cls == 3u) s_list[kPairsMax - 1u - (b3 + __popc(m3 & lt))] = (uint16_t)pl;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    __syncthreads();  // s_warp of the previous item has been read
-    if (lane == 0) s_warp[warp] = mine;
+    if (lane == 0 && mine) atomicAdd(&s_emit, mine);
     __syncthreads();
-    if (tid == 0) {
-      uint32_t tot = 0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) tot += s_warp[w];
-      P.item_cnt[item_idx] = tot;
+    if (tid == 0) P.item_cnt[item_idx] = s_emit;
+    const uint32_t n2 = s_n2, n3 = s_n3;
+    const uint32_t nc2 = (n2 + 31u) >> 5, nc3 = (n3 + 31u) >> 5;
+    for (uint32_t c = warp; c < nc2 + nc3; c += kThreads / 32) {
+      if (c < nc2) {
+        const uint32_t q = c * 32u + lane;
+        if (q < n2) {
+          const uint32_t pl = s_list[q];
+          uint32_t T[9];
+          tile_cnt_load(cnt, slot0 + pl, T);
+          P.dense[slot0 + pl] = mi_2x2(tab, T[4], T[5], T[7], T[8]);
+        }
+      } else {
+        const uint32_t q = (c - nc2) * 32u + lane;
+        if (q < n3) {
+          const uint32_t pl = s_list[kPairsMax - 1u - q];
+          uint32_t T[9];
+          tile_cnt_load(cnt, slot0 + pl, T);
+          P.dense[slot0 + pl] = mi_3x3(tab, T);
+        }
+      }
     }
   }
 }

@@ -134,6 +134,9 @@ def fast_host(liblgmi_path):
     lib.f_mi_2x2_many.argtypes = [vp, ctypes.c_int64, vp, u32, vp]
     lib.f_mi_3x3_many.restype = None
     lib.f_mi_3x3_many.argtypes = [vp, ctypes.c_int64, vp, u32, vp]
+    for name in ("g_mi_2x2_many", "g_mi_3x3_many"):
+        getattr(lib, name).restype = None
+        getattr(lib, name).argtypes = [vp, ctypes.c_int64, vp, vp]
     lib.f_markstein_mismatches.restype = ctypes.c_int64
     lib.f_markstein_mismatches.argtypes = [u32]
     lib.f_and_popc.restype = u32

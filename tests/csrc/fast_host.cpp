@@ -18,6 +18,9 @@ static inline double __hiloint2double(int hi, int lo) {
   double d; __builtin_memcpy(&d, &v, 8); return d;
 }
 
+static inline double __drcp_rn(double a) { return 1.0 / a; }   // IEEE division is correctly rounded
+static inline double2 __ldg(const double2* p) { return *p; }
+
 #include "../../l-giremi_b200/csrc/lgmi_fast.cuh"
 
 using namespace lgmi;
@@ -49,6 +52,15 @@ void f_mi_2x2_many(const uint32_t* cells, int64_t m, const double* lntab, uint32
 }
 void f_mi_3x3_many(const uint32_t* T, int64_t m, const double* lntab, uint32_t n, double* out) {
   auto t = make_tab(lntab, n);
+  for (int64_t k = 0; k < m; ++k) out[k] = mi_3x3(t, T + 9 * k);
+}
+// the same epilogues over the context's full ln table and the computed reciprocal (k_tile_finish: counts of any size)
+void g_mi_2x2_many(const uint32_t* cells, int64_t m, const double* lntab, double* out) {
+  const GlobalTab t{reinterpret_cast<const lg_dd*>(lntab)};
+  for (int64_t k = 0; k < m; ++k) out[k] = mi_2x2(t, cells[4 * k], cells[4 * k + 1], cells[4 * k + 2], cells[4 * k + 3]);
+}
+void g_mi_3x3_many(const uint32_t* T, int64_t m, const double* lntab, double* out) {
+  const GlobalTab t{reinterpret_cast<const lg_dd*>(lntab)};
   for (int64_t k = 0; k < m; ++k) out[k] = mi_3x3(t, T + 9 * k);
 }
 // number of (n, N) with 0 <= n <= N <= n_max where the Markstein quotient differs from n / N

@@ -113,3 +113,44 @@ def test_fast_paths_match_sklearn_golden(fast_host, lntab, golden):
                 unhex(case["mi"]), case
         n += 1
     assert n > 1000
+
+
+def test_global_table_epilogues_same_bits_for_large_counts(fast_host, math_host, lntab, golden):
+    """k_tile_finish runs the same branch-free epilogues over the context's full ln table and the correctly
+    rounded reciprocal (GlobalTab): counts far beyond the 256 of the shared-memory table must still give the
+    bits of the straightforward arithmetic, and the golden sklearn tables of any size must reproduce."""
+    big = lntab                                       # 2^17 entries
+    rng = np.random.default_rng(9)
+    tabs = []
+    for _ in range(30000):
+        scale = int(rng.choice([3, 40, 300, 2000, 7000]))
+        t = rng.integers(0, scale, 9)
+        if rng.random() < 0.6:
+            t[[0, 1, 2, 3, 6]] = rng.integers(0, 4, 5)
+        t[rng.random(9) < rng.choice([0.0, 0.3, 0.6])] = 0
+        if 0 < t.sum() < 65536:
+            tabs.append(t)
+    tabs.append(np.array([0, 0, 0, 0, 65535, 0, 0, 0, 0]))
+    tabs.append(np.array([0, 0, 0, 0, 30000, 2, 0, 1, 35000]))
+    tabs = u32(np.array(tabs))
+    out = np.empty(len(tabs))
+    fast_host.g_mi_3x3_many(tabs.ctypes.data, len(tabs), big.ctypes.data, out.ctypes.data)
+    for t, got in zip(tabs, out.tolist()):
+        assert got == math_host.t_mi_from_table(t.ctypes.data, big.ctypes.data), t
+    two = tabs[~tabs[:, [0, 1, 2, 3, 6]].any(axis=1)]
+    cells = u32(two[:, [4, 5, 7, 8]])
+    out2 = np.empty(len(cells))
+    fast_host.g_mi_2x2_many(cells.ctypes.data, len(cells), big.ctypes.data, out2.ctypes.data)
+    for c, got in zip(cells.tolist(), out2.tolist()):
+        assert got == math_host.t_mi_from_2x2(c[0], c[1], c[2], c[3], big.ctypes.data), c
+    assert len(cells) > 100
+    n = 0
+    for case in golden("tables.json"):
+        t = u32(case["table"])
+        if int(t.sum()) >= (1 << 17):
+            continue
+        one = np.empty(1)
+        fast_host.g_mi_3x3_many(t.ctypes.data, 1, big.ctypes.data, one.ctypes.data)
+        assert one[0] == unhex(case["mi"]), case
+        n += 1
+    assert n > 2000
