@@ -11,8 +11,8 @@ Public surface (same names as the reference where one exists):
     partition_lpt, unit_costs, DevicePool, merge_shards                -- multi-GPU sharding
     install / uninstall                                                -- patch a loaded `giremi`
 """
-from ._lib import (DENSE_DEFAULT, LIB_PATH, MODE_ALL_PAIRS, MODE_EMIT_COUNTS, MODE_HET_ONLY, MODE_GRAPH, MODE_SKIP_NONHET,
-                   MODE_SPLIT_RECORDS,
+from ._lib import (DENSE_DEFAULT, LIB_PATH, MODE_ALL_PAIRS, MODE_COMPACT_OUTPUT, MODE_EMIT_COUNTS, MODE_HET_ONLY, MODE_GRAPH,
+                   MODE_SKIP_NONHET, MODE_SPLIT_RECORDS, MODE_TIGHT_INPUT,
                    PAIR_REC, SITE_HET_SNP, SITE_MISMATCH, SITE_SNP, UNIT_DESC, LgmiError)
 from .api import (Batch, Context, Pipeline, StepResult, default_device, device_count, ecdf, get_context,
                   mean_mismatch_pair_mutual_info, mi_step_batched, mip_and_calls, mismatch_pair_mutual_info,

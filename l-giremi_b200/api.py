@@ -60,8 +60,9 @@ class Context:
         check(self._lib.lgmi_set_small_path(self.handle, 1 if tensor_cores else 0), self.handle)
 
     def set_tile_path(self, tensor_cores):
-        """Mid-depth units counted on the tensor cores (True, default: k_tile_gram) or by tiled popcount (False)."""
-        check(self._lib.lgmi_set_tile_path(self.handle, 1 if tensor_cores else 0), self.handle)
+        """Mid-depth units counted on the tensor cores (True / 1, default: k_tile_gram; 2: the warp-specialised
+        k_tile_gram_ws) or by tiled popcount (False / 0)."""
+        check(self._lib.lgmi_set_tile_path(self.handle, int(tensor_cores)), self.handle)
 
     @property
     def launch_count(self):

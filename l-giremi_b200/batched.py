@@ -189,8 +189,11 @@ def analyse_extracted(regions, min_common_reads=5, ctx=None, pool=None):
         first = pool.contexts[0] if pool is not None else ctx
         _check_bad_sites(units, metas, min_common_reads, first)
         pb = concat_plane_batches(units)
+        import time
+        t0 = time.perf_counter()
         res = pool.run(pb, min_common_reads, mode) if pool is not None else \
             api.mi_step_batched(pb, min_common_reads, mode, ctx=ctx)
+        last_step_times['submit_s'] = time.perf_counter() - t0
     pair_rows = [{'+': None, '-': None} for _ in regions]
     mean_of = [{'+': {}, '-': {}} for _ in regions]
     site_off = 0
@@ -301,6 +304,8 @@ _VARIABLE_OF_ARG = {
 
 # wall-clock seconds of the last main(): what tools/run_cli.py reports as the MI-step time of the patched CLI
 last_run_times = {}
+# ... and of the last analyse_extracted(): the GPU submit alone (encode and frames excluded)
+last_step_times = {}
 
 
 def main():
@@ -330,10 +335,13 @@ def main():
     chunks = [footprints[i:(i + n)] for i in range(0, len(footprints), n)]
     logging.info('Calculate mismatches in each region.')
     t0 = time.perf_counter()
-    with mp.Pool(args.thread) as p:
-        extracted = p.map(partial(extract_footprints, variables=variables), chunks)
+    with mp.Pool(args.thread) as p:                                     # (the workers are forked here ...)
+        pending = p.map_async(partial(extract_footprints, variables=variables), chunks)
+        # ... so CUDA can start in the parent while they extract: context creation, module load, ln table
+        pool = multigpu.get_pool()
+        t_cuda = time.perf_counter() - t0
+        extracted = pending.get()
     t1 = time.perf_counter()
-    pool = multigpu.get_pool()                                          # CUDA starts here, in the parent
     regions = [reg for _strand_rows, regs in extracted for reg in regs]
     frames = analyse_extracted(regions, variables['mi_min_common_reads'], pool=pool)
     t2 = time.perf_counter()
@@ -365,7 +373,8 @@ def main():
         del glmresult['id']
         glmresult.to_csv(args.output_prefix + '.mismatch.txt', sep='\t', index=False)
         scorepf.to_csv(args.output_prefix + '.score_performance.txt', sep='\t', index=False)
-    last_run_times.update({'extract_pool_s': t1 - t0, 'mi_step_s': t2 - t1, 'write_tables_s': t3 - t2, 'mip_s': mip_s,
+    last_run_times.update({'extract_pool_s': t1 - t0, 'cuda_start_s': t_cuda, 'mi_step_s': t2 - t1,
+                           'gpu_submit_s': last_step_times.get('submit_s'), 'write_tables_s': t3 - t2, 'mip_s': mip_s,
                            'n_gpus': len(pool), 'n_units': sum(1 for reg in regions for s in _STRANDS
                                                                if reg.encoded[s] is not None)})
     logging.info('All done!')

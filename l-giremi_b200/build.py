@@ -43,11 +43,17 @@ def find_nvcc():
     return nvcc
 
 
+last_build_compiled = None     # True: the last build_lib() ran nvcc; False: it found the library newer than every source
+
+
 def build_lib(force=False, verbose=False):
     """Compile csrc/ into l-giremi_b200/liblgmi.so.  Returns the path."""
+    global last_build_compiled
     srcs = sources()
     if not force and _newer(LIB, srcs):
+        last_build_compiled = False
         return LIB
+    last_build_compiled = True
     nvcc = find_nvcc()
     obj = os.path.join(CSRC, "lgmi_lntab.o")
     cmd_c = ["gcc", "-O2", "-fPIC", "-c", os.path.join(CSRC, "lgmi_lntab.c"), "-o", obj]

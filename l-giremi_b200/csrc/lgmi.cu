@@ -125,7 +125,8 @@ struct lgmi_ctx {
   int pairs_ctas_per_sm = 0;
   int pre_ctas_per_sm = 0;
   int small_path = 0;  // 0: popcount (k_pairs_fast, default: faster); 1: counted on the tensor cores
-  int tile_path = 1;   // mid-depth units: 1 tensor cores (k_tile_gram, default), 0 popcount (k_tile_mi)
+  int tile_path = 1;   // mid-depth units: 0 popcount (k_tile_mi), 1 tensor cores (k_tile_gram, default),
+                       // 2 tensor cores, warp-specialised (k_tile_gram_ws)
   // tensor-core path: units at least this large build their tables with k_gram_i8
   uint32_t dense_min_sites = 48, dense_min_reads = 8192;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
@@ -197,8 +198,9 @@ struct lgmi_batch {
   // tiled popcount path
   TileItem* d_tile_items = nullptr;
   uint32_t n_tile_items = 0;
-  TileItem* d_gram_tiles = nullptr;    // k_tile_gram's work items (128 x 48 site blocks)
+  TgTile* d_gram_tiles = nullptr;      // k_tile_gram's work items (128 x 48 site blocks)
   uint32_t n_gram_tiles = 0;
+  int gram_kernel = 1;                 // 1 k_tile_gram, 2 k_tile_gram_ws (the context's tile path when the batch was made)
   uint2* d_tile_cnt = nullptr;         // its output: 24 bytes of counts per pair slot
   uint32_t* d_tile_next = nullptr;     // its work counter
   uint32_t n_tiled_work_items = 0;     // work items (Item) of the k_tile_mi units: k_pairs_generic<true>'s
@@ -351,9 +353,10 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
     return rc;
   }
   if (const char* e = getenv("LGMI_SMALL_PATH")) ctx->small_path = atoi(e) ? 1 : 0;
-  if (const char* e = getenv("LGMI_TILE_PATH")) ctx->tile_path = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("LGMI_TILE_PATH")) ctx->tile_path = std::min(2, std::max(0, atoi(e)));
   if (const char* e = getenv("LGMI_GRAPHS")) ctx->pipeline_graphs = atoi(e) ? 1 : 0;
-  if (cudaFuncSetAttribute(k_tile_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTgSmemBytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_tile_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTgSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k_tile_gram_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTwSmemBytes) != cudaSuccess) {
     int rc = fail(nullptr, LGMI_ERR_CUDA, "lgmi_create: k_tile_gram cannot be resident (%s)",
                   cudaGetErrorString(cudaGetLastError()));
     lgmi_destroy(ctx);
@@ -431,18 +434,6 @@ extern "C" int lgmi_pinned_free(lgmi_t* ctx, void* ptr) {
 
 extern "C" uint64_t lgmi_launch_count(const lgmi_t* ctx) { return ctx ? ctx->launches : 0; }
 
-#ifdef LGMI_PHASE_CLOCKS
-// debug build only (tools/phase_clocks.py): read (and optionally clear) k_pairs_fast's per-barrier cycle sums
-extern "C" __attribute__((visibility("default"))) int lgmi_debug_phase_clocks(unsigned long long* out, int reset) {
-  if (out && cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(g_phase_clk)) != cudaSuccess) return LGMI_ERR_CUDA;
-  if (reset) {
-    static unsigned long long zero[8][kFastWarps][2];
-    if (cudaMemcpyToSymbol(g_phase_clk, zero, sizeof(zero)) != cudaSuccess) return LGMI_ERR_CUDA;
-  }
-  return LGMI_OK;
-}
-#endif
-
 extern "C" int lgmi_set_small_path(lgmi_t* ctx, int tensor_cores) {
   if (!ctx) return LGMI_ERR_ARG;
   ctx->small_path = tensor_cores ? 1 : 0;
@@ -451,7 +442,7 @@ extern "C" int lgmi_set_small_path(lgmi_t* ctx, int tensor_cores) {
 
 extern "C" int lgmi_set_tile_path(lgmi_t* ctx, int tensor_cores) {
   if (!ctx) return LGMI_ERR_ARG;
-  ctx->tile_path = tensor_cores ? 1 : 0;
+  ctx->tile_path = tensor_cores < 0 ? 0 : (tensor_cores > 2 ? 2 : tensor_cores);
   return LGMI_OK;
 }
 
@@ -531,7 +522,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   uint64_t val_slots = 0;
   std::vector<MeanItem> mean_items;
   std::vector<DenseTile> dense_tiles;
-  std::vector<TileItem> tile_items, gram_tiles;
+  std::vector<TileItem> tile_items;
+  std::vector<TgTile> gram_tiles;
   std::vector<uint32_t> tile_words, gram_words_of;  // W of each tile's unit (launch order: longest first)
   bool any_gram_tiled = false;
   uint64_t dense = 0, gram_words = 0, x_bytes = 0;
@@ -549,6 +541,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
                   "unit %u: inconsistent descriptor (S=%u R=%u W=%u plane_off=%llu site_off=%u)", k,
                   u.n_sites, u.n_reads, u.row_words, (unsigned long long)u.plane_off, u.site_off);
     }
+    const size_t first_gram_tile = gram_tiles.size();  // this unit's k_tile_gram work items start here
     DevUnit& d = du[k];
     d.plane_off = u.plane_off;
     d.S = u.n_sites;
@@ -636,7 +629,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
             // some pair i < j with i in row block I and j in column block J
             const uint32_t j_max = std::min((J + 1u) * (uint32_t)kTgSitesJ, u.n_sites) - 1u;
             if (I * (uint32_t)kTgSitesI >= j_max) continue;
-            gram_tiles.push_back(TileItem{k, (uint16_t)I, (uint16_t)J});
+            gram_tiles.push_back(TgTile{u.plane_off, 0ull /* set below */, u.n_sites, u.row_words, u.site_off, (uint16_t)I, (uint16_t)J});
             gram_words_of.push_back(u.row_words);
           }
       } else {
@@ -653,6 +646,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       dense += np;
       for (uint32_t s0 = 0; s0 < u.n_sites; s0 += (uint32_t)kMeanSites) mean_items.push_back(MeanItem{k, s0});
     }
+    for (size_t t = first_gram_tile; t < gram_tiles.size(); ++t) gram_tiles[t].dense_off = d.dense_off;  // known now
     for (uint32_t t = 0; t < nit; ++t) {
       Item it;
       it.unit = k;
@@ -684,12 +678,12 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       b->h_items.push_back(it);
     }
   }
-  auto deepest_first = [](std::vector<TileItem>& items, const std::vector<uint32_t>& words) {
+  auto deepest_first = [](auto& items, const std::vector<uint32_t>& words) {
     // the deepest tiles first: CTAs are handed out in order, so the long ones do not end up in the tail
     std::vector<uint32_t> order(items.size());
     for (uint32_t t = 0; t < order.size(); ++t) order[t] = t;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return words[x] > words[y]; });
-    std::vector<TileItem> sorted(items.size());
+    typename std::remove_reference<decltype(items)>::type sorted(items.size());
     for (uint32_t t = 0; t < order.size(); ++t) sorted[t] = items[order[t]];
     items.swap(sorted);
   };
@@ -697,6 +691,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   deepest_first(gram_tiles, gram_words_of);
   b->n_tile_items = (uint32_t)tile_items.size();
   b->n_gram_tiles = (uint32_t)gram_tiles.size();
+  b->gram_kernel = ctx->tile_path == 2 ? 2 : 1;
 
   b->n_items = (uint32_t)b->h_items.size();
   b->n_fast = (uint32_t)fast_items.size();
@@ -749,8 +744,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   }
   BCU(pool_malloc(ctx, &b->d_tile_next, sizeof(uint32_t)));
   if (!gram_tiles.empty()) {
-    BCU(pool_malloc(ctx, &b->d_gram_tiles, gram_tiles.size() * sizeof(TileItem)));
-    BCU(cudaMemcpyAsync(b->d_gram_tiles, gram_tiles.data(), gram_tiles.size() * sizeof(TileItem), cudaMemcpyHostToDevice,
+    BCU(pool_malloc(ctx, &b->d_gram_tiles, gram_tiles.size() * sizeof(TgTile)));
+    BCU(cudaMemcpyAsync(b->d_gram_tiles, gram_tiles.data(), gram_tiles.size() * sizeof(TgTile), cudaMemcpyHostToDevice,
                         bstream(b)));
   }
   if (any_gram_tiled) BCU(pool_malloc(ctx, &b->d_tile_cnt, std::max<uint64_t>(1, dense) * 3ull * sizeof(uint2)));
@@ -968,7 +963,6 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
   if (b->n_gram_tiles) {
     // K1 of the medium units on the tensor cores (batched, bits expanded in the kernel), then K2 per pair
     TileGramParams T;
-    T.units = b->d_units;
     T.planes = b->d_planes;
     T.site_flags = b->d_flags;
     T.mode = mode;
@@ -978,7 +972,8 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
     T.next = b->d_tile_next;
     T.error = reinterpret_cast<uint32_t*>(&b->d_header->pad);
     const unsigned ggrid = (unsigned)std::min<uint32_t>(b->n_gram_tiles, (uint32_t)ctx->num_sms);
-    k_tile_gram<<<ggrid, kTgThreads, kTgSmemBytes, bstream(b)>>>(T);
+    if (b->gram_kernel == 2) k_tile_gram_ws<<<ggrid, kTwThreads, kTwSmemBytes, bstream(b)>>>(T);
+    else k_tile_gram<<<ggrid, kTgThreads, kTgSmemBytes, bstream(b)>>>(T);
     ++ctx->launches;
     const unsigned fgrid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 8u);
     k_tile_finish<<<fgrid, kThreads, 0, bstream(b)>>>(P, b->d_tile_cnt);

@@ -95,14 +95,6 @@ struct FastSmem {
   uint8_t nonhet_list[kFastMaxS];                        // ... the other sites ascending
   unsigned long long het_mask;
   uint32_t n_list2, n_list3, next_chunk, total;
-#ifdef LGMI_HET_DEFERRED_MEANS
-  // experiment (k_pairs_fast_het only): the previous unit's site lists, for means that run one unit behind
-  struct Prev {
-    uint8_t het_list[kFastMaxS];
-    uint8_t nonhet_list[kFastMaxS];
-    unsigned long long het_mask;
-  } prev;
-#endif
   __device__ __forceinline__ uint32_t oth_count(uint32_t s) const {
     return n_oth[s] < (uint32_t)kOthCap ? n_oth[s] : (uint32_t)kOthCap;
   }

@@ -427,76 +427,7 @@ __device__ __forceinline__ void fast_means(const FastParams& P, SM& sm, const un
   P.site_cnt[it.site_off + s] = acc.n;
 }
 
-#ifdef LGMI_HET_DEFERRED_MEANS
-// The same per-site means by ONE warp, from a copy of the unit's site lists: lane q takes the q-th
-// site of [het sites | other sites], q = lane, lane + 32.
-template <class LISTS>
-__device__ __forceinline__ void fast_means_warp(const FastParams& P, const LISTS& L,
-                                                const unsigned long long* __restrict__ val, uint32_t S,
-                                                uint32_t site_off) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t n_het = __popcll(L.het_mask);
-  const double* s_mi = reinterpret_cast<const double*>(val);
-  for (uint32_t q = lane; q < S; q += 32u) {
-    MeanAcc acc{0.0, 0.0, 0u};
-    uint32_t s;
-    if (q < n_het) {
-      s = L.het_list[q];
-      uint32_t p = s - 1u;
-#pragma unroll 4
-      for (uint32_t t = 0; t < s; ++t) {
-        acc.add(s_mi, p);
-        p += S - t - 2u;
-      }
-      p = (s * (2u * S - s - 1u)) >> 1;
-#pragma unroll 4
-      for (uint32_t t = s + 1u; t < S; ++t, ++p) acc.add(s_mi, p);
-    } else {
-      s = L.nonhet_list[q - n_het];
-      const uint32_t row_s = (s * (2u * S - s - 1u)) >> 1;
-#pragma unroll 4
-      for (uint32_t k = 0; k < n_het; ++k) {
-        const uint32_t t = L.het_list[k];
-        acc.add(s_mi, (t < s) ? (((t * (2u * S - t - 1u)) >> 1) + (s - t - 1u)) : (row_s + (t - s - 1u)));
-      }
-    }
-    double mean = mi_nan();
-    if (acc.n) {
-      double tot = acc.s;
-      if (acc.c != 0.0) tot = __dadd_rn(tot, acc.c);
-      mean = __ddiv_rn(tot, (double)acc.n);
-    }
-    P.site_mean[site_off + s] = mean;
-    P.site_cnt[site_off + s] = acc.n;
-  }
-}
-#endif
 
-// Debug build only (-DLGMI_PHASE_CLOCKS, tools/phase_clocks.py): lane 0 of every warp accumulates, per
-// barrier of the unit loop, the cycles it worked before arriving and the cycles it then waited.
-#ifdef LGMI_PHASE_CLOCKS
-__device__ unsigned long long g_phase_clk[8][kFastWarps][2];
-__device__ __forceinline__ long long phase_clock() {
-  long long t;
-  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");  // "memory": stays on its side of the barrier
-  return t;
-}
-#define LG_PHASE_DECL long long ph_t = phase_clock();
-#define LG_PHASE_SYNC(k, stmt)                                                            \
-  {                                                                                       \
-    const long long ph_a = phase_clock();                                                 \
-    stmt;                                                                                 \
-    const long long ph_r = phase_clock();                                                 \
-    if ((threadIdx.x & 31u) == 0u) {                                                      \
-      atomicAdd(&g_phase_clk[k][threadIdx.x >> 5][0], (unsigned long long)(ph_a - ph_t)); \
-      atomicAdd(&g_phase_clk[k][threadIdx.x >> 5][1], (unsigned long long)(ph_r - ph_a)); \
-    }                                                                                     \
-    ph_t = ph_r;                                                                          \
-  }
-#else
-#define LG_PHASE_DECL
-#define LG_PHASE_SYNC(k, stmt) stmt;
-#endif
 
 // kHetPairsOnly: the HET_ONLY | SKIP_NONHET instantiation (k_pairs_fast_het): counts by fast_counts_het
 template <bool kHetPairsOnly>
@@ -504,7 +435,6 @@ __device__ __forceinline__ void pairs_fast_body(const FastParams& P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x;
-  LG_PHASE_DECL
 
   // per-CTA table: ln k (hi, lo) and RN(1/k) for k <= 256
   for (uint32_t k = tid; k <= (uint32_t)kFastMaxR; k += kFastThreads) {
@@ -561,15 +491,15 @@ __device__ __forceinline__ void pairs_fast_body(const FastParams& P) {
         if (tid < n_chunks) sm.emit_mask[tid] = 0u;
       }
       cp_async_wait<1>();  // this item's rows have landed (the next item's may still be in flight)
-      LG_PHASE_SYNC(0, __syncthreads())
+      __syncthreads();
       fast_land(sm, rows, it, P.site_flags + it.site_off);
-      LG_PHASE_SYNC(1, __syncthreads())
+      __syncthreads();
       // a site with more than kOthCap "other" reads does not fit the sparse lists: the generic kernel takes the unit
       const bool over = tid < S && sm.n_oth[tid] > (uint32_t)kOthCap;
       fast_site_lists(sm, S);
       fast_other_cells(sm, rows, S, het_pairs_only ? sm.het_mask : ~0ull);
       bool dense;
-      LG_PHASE_SYNC(2, dense = __syncthreads_or(over) != 0)  // (also: sm.info is read by every thread of the counts phase)
+      dense = __syncthreads_or(over) != 0;  // (also: sm.info is read by every thread of the counts phase)
       if (dense) {
         if (tid == 0) {
           P.item_dense[it.item] = 1;
@@ -584,21 +514,21 @@ __device__ __forceinline__ void pairs_fast_body(const FastParams& P) {
         else if (nw <= 4u) fast_counts<4>(P, sm, rows, ijt, n_pairs);
         else if (nw <= 7u) fast_counts<7>(P, sm, rows, ijt, n_pairs);
         else fast_counts<8>(P, sm, rows, ijt, n_pairs);
-        LG_PHASE_SYNC(3, __syncthreads())
+        __syncthreads();
         if (tid < 32u) fast_chunk_prefix(sm, n_chunks);
         if (P.mode & LGMI_MODE_EMIT_COUNTS) {
           __syncthreads();
           fast_emit_counts(P, sm, sm.val, base, n_chunks);
         }
         fast_mi(sm, sm.val);
-        LG_PHASE_SYNC(4, __syncthreads())
+        __syncthreads();
         if (tid == 0) P.unit_rec_off[it.unit] = base;
         // the serial per-site sums occupy the first one or two warps; the others write the records
         const uint32_t mean_warps = (S + 31u) >> 5;
         if ((tid >> 5) < mean_warps) fast_means(P, sm, sm.val, it);
         else fast_emit(P, sm, sm.val, it, ijt, base, n_chunks, mean_warps);
       }
-      LG_PHASE_SYNC(5, __syncthreads())  // everything of this item consumed before its buffers are reused
+      __syncthreads();  // everything of this item consumed before its buffers are reused
     }
     it = it_next;
     idx = idx_next;
@@ -607,140 +537,9 @@ __device__ __forceinline__ void pairs_fast_body(const FastParams& P) {
   cp_async_wait<0>();
 }
 
-#ifdef LGMI_HET_DEFERRED_MEANS
-// EXPERIMENT (off by default; DESIGN.md section 8, follow-up 1): the unit loop of k_pairs_fast_het with
-// the per-site means ONE UNIT BEHIND.  Warp 0 runs the previous unit's serial compensated sums while
-// warps 1-7 land the next unit, build its site lists and scatter its "other" cells on their own (named
-// barrier 1); everyone meets at the barrier before the counts phase, all eight warps write the records,
-// and there is no end-of-unit barrier.  The means read sm.val (not written again before that barrier:
-// its "no MI" pre-fill moves behind it) and a copy of the unit's site lists (sm.prev, made by warp 0
-// between the counts and the MI barrier, when the lists are stable).
-__device__ __forceinline__ void fast_group_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kFastThreads - 32) : "memory");
-}
-
-__device__ __forceinline__ void pairs_fast_het_deferred_body(const FastParams& P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
-  const uint32_t tid = threadIdx.x;
-  const bool lander = tid >= 32u;  // warps 1-7
-  const uint32_t gt = tid - 32u;   // thread index inside the landing group
-  constexpr uint32_t kGroup = kFastThreads - 32;
-
-  for (uint32_t k = tid; k <= (uint32_t)kFastMaxR; k += kFastThreads) {
-    const double2 v = (k < P.ln_cap) ? __ldg(reinterpret_cast<const double2*>(P.lntab) + k) : make_double2(0.0, 0.0);
-    sm.tab.ln[k].hi = v.x;
-    sm.tab.ln[k].lo = v.y;
-    sm.tab.inv[k] = k ? __drcp_rn((double)k) : 0.0;
-  }
-
-  uint32_t idx = blockIdx.x;
-  uint32_t buf = 0;
-  FastItem it;
-  if (idx < P.n_items) {
-    it = P.items[idx];
-    if (lander && !P.fast_empty[idx]) fast_prefetch(sm.rows[0], it, P.planes, gt, kGroup);
-  }
-  cp_async_commit();
-  bool mean_pending = false;  // the previous processed unit's means are still to be done (by warp 0)
-  uint32_t mean_S = 0u, mean_site_off = 0u;
-
-  while (idx < P.n_items) {
-    const uint32_t idx_next = idx + gridDim.x;
-    FastItem it_next;
-    if (idx_next < P.n_items) {
-      const bool empty_next = P.fast_empty[idx_next] != 0;
-      it_next = P.items[idx_next];
-      if (lander && !empty_next) fast_prefetch(sm.rows[buf ^ 1u], it_next, P.planes, gt, kGroup);
-    }
-    cp_async_commit();
-    const uint32_t S = it.S;
-    const unsigned long long base = P.item_off[it.item];
-    if (P.fast_empty[idx]) {  // touches no shared memory: no barrier
-      if (tid < S) {
-        P.site_mean[it.site_off + tid] = mi_nan();
-        P.site_cnt[it.site_off + tid] = 0u;
-      }
-      if (tid == 0) P.unit_rec_off[it.unit] = base;
-    } else {
-      const uint32_t n_pairs = S * (S - 1u) / 2u;
-      const uint32_t n_chunks = (n_pairs + 31u) >> 5;
-      uint32_t* rows = sm.rows[buf];
-      const uint16_t* __restrict__ ijt = P.ij_tab + lg_ij_tab_off(S);
-      bool over = false;
-      if (lander) {
-        if (gt < (uint32_t)kFastMaxS) sm.n_oth[gt] = 0u;
-        for (uint32_t q = gt; q < (n_pairs + 1u) >> 1; q += kGroup) sm.ocell[q] = 0u;
-        if (gt == 0) {
-          sm.n_list2 = 0u;
-          sm.n_list3 = 0u;
-          sm.n_oth_total = 0u;
-        }
-        cp_async_wait<1>();
-        fast_group_sync();
-        fast_land(sm, rows, it, P.site_flags + it.site_off, gt, kGroup);
-        fast_group_sync();
-        over = gt < S && sm.n_oth[gt] > (uint32_t)kOthCap;
-        fast_site_lists(sm, S, gt);
-        fast_other_cells(sm, rows, S, sm.het_mask, gt >> 5, kGroup / 32u);
-      } else if (mean_pending) {
-        fast_means_warp(P, sm.prev, sm.val, mean_S, mean_site_off);
-      }
-      const bool dense = __syncthreads_or(over) != 0;
-      mean_pending = !dense;
-      mean_S = S;
-      mean_site_off = it.site_off;
-      if (dense) {
-        if (tid == 0) {
-          P.item_dense[it.item] = 1;
-          atomicAdd(P.n_generic, 1u);
-        }
-      } else {
-        for (uint32_t q = tid; q < n_pairs; q += kFastThreads) sm.val[q] = kNoMi;
-        if (tid < n_chunks) sm.emit_mask[tid] = 0u;
-        __syncthreads();
-        const uint32_t nw = ((uint32_t)it.R + 31u) >> 5;
-        if (nw <= 4u) fast_counts_het<4>(P, sm, rows, S);
-        else fast_counts_het<8>(P, sm, rows, S);
-        __syncthreads();
-        if (tid < 32u) {
-          // the lists are stable between here and the next barrier; the landing group rewrites them after it
-          for (uint32_t q = tid; q < (uint32_t)kFastMaxS; q += 32u) {
-            sm.prev.het_list[q] = sm.het_list[q];
-            sm.prev.nonhet_list[q] = sm.nonhet_list[q];
-          }
-          if (tid == 0) sm.prev.het_mask = sm.het_mask;
-          fast_chunk_prefix(sm, n_chunks);
-        }
-        if (P.mode & LGMI_MODE_EMIT_COUNTS) {
-          __syncthreads();
-          fast_emit_counts(P, sm, sm.val, base, n_chunks);
-        }
-        fast_mi(sm, sm.val);
-        __syncthreads();
-        if (tid == 0) P.unit_rec_off[it.unit] = base;
-        fast_emit(P, sm, sm.val, it, ijt, base, n_chunks, 0u);
-        // no barrier: what the next iteration writes before its all-thread barrier (the other row buffer,
-        // the zeroed "other" bookkeeping, flags, info, the site lists) is not read by the emit or the means
-      }
-    }
-    it = it_next;
-    idx = idx_next;
-    buf ^= 1u;
-  }
-  if (!lander && mean_pending) fast_means_warp(P, sm.prev, sm.val, mean_S, mean_site_off);
-  cp_async_wait<0>();
-}
-#endif
 
 __global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast(const FastParams P) { pairs_fast_body<false>(P); }
 // launched instead of k_pairs_fast when the mode is HET_ONLY | SKIP_NONHET
-__global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast_het(const FastParams P) {
-#ifdef LGMI_HET_DEFERRED_MEANS
-  pairs_fast_het_deferred_body(P);
-#else
-  pairs_fast_body<true>(P);
-#endif
-}
+__global__ void __launch_bounds__(kFastThreads, 4) k_pairs_fast_het(const FastParams P) { pairs_fast_body<true>(P); }
 
 }  // namespace lgmi

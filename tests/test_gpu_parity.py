@@ -256,9 +256,10 @@ def test_many_sites_multi_item_unit(lg, gpu_ctx):
 
 
 def test_mid_units_popcount_and_tensor_paths_agree(lg, gpu_ctx):
-    """Mid-depth units (more than 64 sites or 256 reads): k_tile_gram + k_tile_finish (tcgen05, default) and
-    k_tile_mi (popcount) must give the same records, tables and means bit for bit, and both match the oracle.
-    Shapes straddle the 128-site row blocks, the 48-site column blocks and the 128-read k-blocks."""
+    """Mid-depth units (more than 64 sites or 256 reads): k_tile_gram + k_tile_finish (tcgen05, default), its
+    warp-specialised form k_tile_gram_ws (path 2) and k_tile_mi (popcount, path 0) must give the same records,
+    tables and means bit for bit, and all match the oracle.  Shapes straddle the 128-site row blocks, the 48-site
+    column blocks and the 128-read k-blocks."""
     rng = np.random.default_rng(20261031)
     shapes = [(65, 40), (48, 257), (49, 300), (129, 129), (97, 1000), (2, 700), (3, 4097), (257, 70), (200, 385),
               (145, 128), (64, 9000)]
@@ -267,17 +268,18 @@ def test_mid_units_popcount_and_tensor_paths_agree(lg, gpu_ctx):
     pb = lg.pack_units(eus)
     out = {}
     try:
-        for tensor in (True, False):
-            gpu_ctx.set_tile_path(tensor)
+        for path in (1, 2, 0):
+            gpu_ctx.set_tile_path(path)
             full = check_batch(lg, gpu_ctx, eus, 6, min_exact=0.9)
             het = lg.mi_step_batched(pb, 9, lg.MODE_HET_ONLY | lg.MODE_SKIP_NONHET | lg.MODE_EMIT_COUNTS, ctx=gpu_ctx)
-            out[tensor] = (full, het)
+            out[path] = (full, het)
     finally:
-        gpu_ctx.set_tile_path(True)
-    for a, b in zip(out[True], out[False]):
-        assert np.array_equal(a.records, b.records) and np.array_equal(a.counts, b.counts)
-        assert np.array_equal(a.site_mean, b.site_mean, equal_nan=True) and np.array_equal(a.site_cnt, b.site_cnt)
-        assert np.array_equal(a.unit_rec_off, b.unit_rec_off)
+        gpu_ctx.set_tile_path(1)
+    for path in (1, 2):
+        for a, b in zip(out[path], out[0]):
+            assert np.array_equal(a.records, b.records) and np.array_equal(a.counts, b.counts)
+            assert np.array_equal(a.site_mean, b.site_mean, equal_nan=True) and np.array_equal(a.site_cnt, b.site_cnt)
+            assert np.array_equal(a.unit_rec_off, b.unit_rec_off)
 
 
 # --------------------------------------------------------------------------- tensor-core path (K3)
@@ -546,23 +548,24 @@ def test_cfg4_full_size_properties_and_oracle_sample(lg, gpu_ctx):
     S, R = pb.units['n_sites'].astype(np.int64), pb.units['n_reads'].astype(np.int64)
     out = {}
     try:
-        for tensor in (True, False):
-            gpu_ctx.set_tile_path(tensor)
+        for path in (1, 2, 0):
+            gpu_ctx.set_tile_path(path)
             b = lg.Batch(gpu_ctx, pb)
             b.upload()
             b.run(6, lg.MODE_ALL_PAIRS)
-            out[tensor] = b.download()
-            if tensor:
+            out[path] = b.download()
+            if path:
                 b.run(6, lg.MODE_ALL_PAIRS)
                 again = b.download()
-                assert np.array_equal(again.records, out[True].records)                  # deterministic
+                assert np.array_equal(again.records, out[path].records)                  # deterministic
             b.close()
     finally:
-        gpu_ctx.set_tile_path(True)
-    res = out[True]
-    assert np.array_equal(res.records, out[False].records)
-    assert np.array_equal(res.site_mean, out[False].site_mean, equal_nan=True)
-    assert np.array_equal(res.site_cnt, out[False].site_cnt)
+        gpu_ctx.set_tile_path(1)
+    res = out[1]
+    for path in (2, 0):                      # many tiles per CTA here: the tile-to-tile hand-over of both tensor-core forms
+        assert np.array_equal(res.records, out[path].records)
+        assert np.array_equal(res.site_mean, out[path].site_mean, equal_nan=True)
+        assert np.array_equal(res.site_cnt, out[path].site_cnt)
     _order_and_mean_properties(pb, res)
     rng = np.random.default_rng(2)
     small = np.flatnonzero((S <= 64) & (R <= 256) & (S >= 2))
