@@ -172,6 +172,10 @@ typedef struct {
   const uint32_t* rec_ij;       /* ... and its i | j << 16; under              */
                                 /* LGMI_MODE_COMPACT_OUTPUT with no unit above */
                                 /* 256 sites an array of uint16: i | j << 8    */
+  uint32_t n_dense_four;        /* of n_dense_units: those whose "other" reads */
+                                /* were rare enough for the four-block form    */
+                                /* (lgmi_set_dense_path); dense_macs / gram_macs*/
+                                /* count the form each unit actually took      */
 } lgmi_result;
 
 typedef struct lgmi_ctx lgmi_t;
@@ -199,6 +203,16 @@ LGMI_API uint64_t lgmi_launch_count(const lgmi_t* ctx);
  * (mutual_information.py:15-40).  Default 48 sites x 8192 reads; applies to   *
  * batches created afterwards.  Tests lower it to force the path.              */
 LGMI_API int lgmi_set_dense_threshold(lgmi_t* ctx, uint32_t min_sites, uint32_t min_reads);
+/* How the tensor-core path builds the tables (mutual_information.py:24-40: labels *
+ * major 2 / minor 1 / other 0).  blocks = 4 (default): while no site of the unit   *
+ * has more than max(256, R/64) reads with label "other" -- decided on the device,  *
+ * per unit and run -- only the four Gram blocks among {major or minor, major} go   *
+ * through the tensor cores and the five cells with an "other" label are counted    *
+ * from the listed reads (k_dense_prep, k_other_fix); otherwise, and always with    *
+ * blocks = 9, all nine blocks of {covered, major or minor, major}.  Same integers  *
+ * either way; applies to batches created afterwards.  Environment                  *
+ * LGMI_DENSE_PATH=4/9 sets the default.                                            */
+LGMI_API int lgmi_set_dense_path(lgmi_t* ctx, int blocks);
 /* Small units (<= 60 sites, <= 256 reads) have their counts built by          *
  * AND+popcount (0, default) or as one small int8 Gram matrix per unit on the  *
  * tensor cores (tensor_cores != 0: k_small_gram + k_pairs_pre).  Same         *

@@ -41,7 +41,7 @@ DENSE_DEFAULT = (48, 8192)    # lgmi_set_dense_threshold defaults: (min_sites, m
 EXPORTS = (
     "lgmi_version", "lgmi_create", "lgmi_destroy", "lgmi_last_error", "lgmi_set_stream",
     "lgmi_pinned_alloc", "lgmi_pinned_free", "lgmi_launch_count", "lgmi_set_dense_threshold",
-    "lgmi_set_small_path", "lgmi_set_tile_path",
+    "lgmi_set_small_path", "lgmi_set_tile_path", "lgmi_set_dense_path",
     "lgmi_batch_create", "lgmi_batch_destroy", "lgmi_batch_upload", "lgmi_batch_run",
     "lgmi_batch_download", "lgmi_batch_sync", "lgmi_batch_device_ptrs",
     "lgmi_batch_algorithmic_bytes", "lgmi_pipeline_create", "lgmi_pipeline_step", "lgmi_pipeline_step_packed",
@@ -72,6 +72,7 @@ class Result(C.Structure):
         ("gram_macs", C.c_uint64),
         ("rec_mi", C.c_void_p),
         ("rec_ij", C.c_void_p),
+        ("n_dense_four", C.c_uint32),
     ]
 
 
@@ -108,6 +109,7 @@ def load():
         "lgmi_set_dense_threshold": (i32, [vp, u32, u32]),
         "lgmi_set_small_path": (i32, [vp, i32]),
         "lgmi_set_tile_path": (i32, [vp, i32]),
+        "lgmi_set_dense_path": (i32, [vp, i32]),
         "lgmi_batch_create": (i32, [vp, vp, u32, u64, u64, pvp]),
         "lgmi_batch_destroy": (None, [vp]),
         "lgmi_batch_upload": (i32, [vp, vp, vp]),

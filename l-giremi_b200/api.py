@@ -59,6 +59,11 @@ class Context:
         """Small units counted by popcount (False, default) or on the tensor cores (True)."""
         check(self._lib.lgmi_set_small_path(self.handle, 1 if tensor_cores else 0), self.handle)
 
+    def set_dense_path(self, blocks):
+        """Deep units: 4 = four Gram blocks + "other" cells from the listed reads while those are rare (decided on
+        the device per unit and run; default), 9 = always nine blocks (lgmi_set_dense_path)."""
+        check(self._lib.lgmi_set_dense_path(self.handle, int(blocks)), self.handle)
+
     def set_tile_path(self, tensor_cores):
         """Mid-depth units counted on the tensor cores (True / 1, default: k_tile_gram; 2: the warp-specialised
         k_tile_gram_ws) or by tiled popcount (False / 0)."""
@@ -138,6 +143,7 @@ class StepResult:
         self.pairs_kernel_ms = float(res.pairs_kernel_ms)
         self.dense_kernel_ms = float(res.dense_kernel_ms)
         self.n_dense_units = int(res.n_dense_units)
+        self.n_dense_four = int(res.n_dense_four)
         self.dense_macs = int(res.dense_macs)
         self.gram_kernel_ms = float(res.gram_kernel_ms)
         self.gram_macs = int(res.gram_macs)

@@ -124,6 +124,8 @@ struct lgmi_ctx {
   int num_sms = 0;
   int pairs_ctas_per_sm = 0;
   int pre_ctas_per_sm = 0;
+  int dense_path = 4;  // deep units: 4 = four Gram blocks + sparse "other" cells where the "other" reads are rare (decided on
+                       // the device per unit and run), 9 = always nine blocks
   int small_path = 0;  // 0: popcount (k_pairs_fast, default: faster); 1: counted on the tensor cores
   int tile_path = 1;   // mid-depth units: 0 popcount (k_tile_mi), 1 tensor cores (k_tile_gram, default),
                        // 2 tensor cores, warp-specialised (k_tile_gram_ws)
@@ -145,10 +147,17 @@ static cudaError_t pool_host_alloc(lgmi_ctx* ctx, T** out, size_t bytes) {
 }
 
 // one unit of the tensor-core path
-struct DensePlan {
-  uint32_t unit = 0, S = 0, W = 0, S_pad = 0, k_blocks = 0, n_tiles = 0;
+struct DenseTileList {
+  uint64_t off = 0, macs = 0;
+  uint32_t n = 0;
   uint32_t n_whole = 0;  // the first n_whole work items are whole tiles; the rest share tiles (last wave, split in K)
-  uint64_t plane_off = 0, gram_off = 0, tile_off = 0, macs = 0;
+};
+struct DensePlan {
+  uint32_t unit = 0, S = 0, W = 0, S_pad = 0, k_blocks = 0;
+  uint32_t oth_cap = 0;       // listed "other" reads per site (four-block form)
+  bool four = false;          // the four-block form may be chosen (else the run is told "nine" up front)
+  DenseTileList list4, list9; // P, M x P, M  /  C, P, M x C, P, M
+  uint64_t plane_off = 0, gram_off = 0;
   CUtensorMap tmap;
 };
 
@@ -189,6 +198,9 @@ struct lgmi_batch {
   std::vector<DensePlan> dense_plans;
   uint8_t* d_x = nullptr;       // indicator matrix of the unit being contracted (reused unit after unit)
   uint32_t* d_gram = nullptr;   // nine count matrices per dense unit
+  uint32_t* d_xt = nullptr;     // four-block form: transposed label planes of the unit being contracted
+  uint32_t* d_oth_cnt = nullptr, *d_oth_list = nullptr;  // ... and its listed "other" reads per site
+  uint32_t* d_unit_mode = nullptr;  // per unit: the form of this run (0 four blocks, else nine)
   DenseTile* d_tiles = nullptr;
   uint64_t dense_macs = 0;      // multiply-accumulates the tile lists amount to
   // small units counted on the tensor cores
@@ -203,7 +215,7 @@ struct lgmi_batch {
   int gram_kernel = 1;                 // 1 k_tile_gram, 2 k_tile_gram_ws (the context's tile path when the batch was made)
   uint2* d_tile_cnt = nullptr;         // its output: 24 bytes of counts per pair slot
   uint32_t* d_tile_next = nullptr;     // its work counter
-  uint32_t n_tiled_work_items = 0;     // work items (Item) of the k_tile_mi units: k_pairs_generic<true>'s
+  uint32_t n_tiled_work_items = 0;     // work items (Item) of the tiled and of the deep units: k_pairs_generic<1>'s and <2>'s
   uint32_t* d_tile_counts = nullptr;  // EMIT_COUNTS only, allocated on first use
   uint64_t n_tiled_slots = 0;
   // host (pinned) mirrors
@@ -353,6 +365,7 @@ extern "C" int lgmi_create(int device, lgmi_t** out) {
     return rc;
   }
   if (const char* e = getenv("LGMI_SMALL_PATH")) ctx->small_path = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("LGMI_DENSE_PATH")) ctx->dense_path = atoi(e) == 9 ? 9 : 4;
   if (const char* e = getenv("LGMI_TILE_PATH")) ctx->tile_path = std::min(2, std::max(0, atoi(e)));
   if (const char* e = getenv("LGMI_GRAPHS")) ctx->pipeline_graphs = atoi(e) ? 1 : 0;
   if (cudaFuncSetAttribute(k_tile_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTgSmemBytes) != cudaSuccess ||
@@ -440,6 +453,13 @@ extern "C" int lgmi_set_small_path(lgmi_t* ctx, int tensor_cores) {
   return LGMI_OK;
 }
 
+extern "C" int lgmi_set_dense_path(lgmi_t* ctx, int blocks) {
+  if (!ctx) return LGMI_ERR_ARG;
+  if (blocks != 4 && blocks != 9) return fail(ctx, LGMI_ERR_ARG, "lgmi_set_dense_path: blocks must be 4 or 9");
+  ctx->dense_path = blocks;
+  return LGMI_OK;
+}
+
 extern "C" int lgmi_set_tile_path(lgmi_t* ctx, int tensor_cores) {
   if (!ctx) return LGMI_ERR_ARG;
   ctx->tile_path = tensor_cores < 0 ? 0 : (tensor_cores > 2 ? 2 : tensor_cores);
@@ -487,6 +507,10 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   ctx->dev_pool.release(b->d_unit_rec_off);
   ctx->dev_pool.release(b->d_x);
   ctx->dev_pool.release(b->d_gram);
+  ctx->dev_pool.release(b->d_xt);
+  ctx->dev_pool.release(b->d_oth_cnt);
+  ctx->dev_pool.release(b->d_oth_list);
+  ctx->dev_pool.release(b->d_unit_mode);
   ctx->dev_pool.release(b->d_tiles);
   ctx->dev_pool.release(b->d_tile_items);
   ctx->dev_pool.release(b->d_gram_tiles);
@@ -526,7 +550,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   std::vector<TgTile> gram_tiles;
   std::vector<uint32_t> tile_words, gram_words_of;  // W of each tile's unit (launch order: longest first)
   bool any_gram_tiled = false;
-  uint64_t dense = 0, gram_words = 0, x_bytes = 0;
+  uint64_t dense = 0, gram_words = 0, x_bytes = 0, xt_words = 0, oth_words = 0;
+  uint32_t oth_sites = 0;
   for (uint32_t k = 0; k < n_units; ++k) {
     const lgmi_unit_desc& u = units[k];
     if (u.n_sites > 65535u) {
@@ -568,27 +593,29 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       pl.k_blocks = u.row_words * 32u / (uint32_t)kDenseBK;  // W is a multiple of 4: whole 128-read blocks
       pl.plane_off = u.plane_off;
       pl.gram_off = gram_words;
-      pl.tile_off = dense_tiles.size();
-      for (uint32_t a = 0; a < 3; ++a)
-        for (uint32_t bb = 0; bb < 3; ++bb)
-          for (uint32_t J = 0; J < pl.S_pad / (uint32_t)kDenseBN; ++J)
-            for (uint32_t I = 0; I < pl.S_pad / (uint32_t)kDenseBM; ++I) {
-              // some pair i < j inside the tile, both real sites
-              const uint32_t i_min = I * (uint32_t)kDenseBM;
-              const uint32_t j_max = std::min(J * (uint32_t)kDenseBN + (uint32_t)kDenseBN, pl.S) - 1u;
-              if (J * (uint32_t)kDenseBN >= pl.S || i_min >= j_max) continue;
-              dense_tiles.push_back(DenseTile{(uint8_t)a, (uint8_t)bb, (uint16_t)I, (uint16_t)J, 0, 0u, pl.k_blocks});
-            }
-      {
+      pl.four = ctx->dense_path == 4;
+      pl.oth_cap = std::max<uint32_t>(kDenseOthMin, u.n_reads / kDenseOthDiv);
+      auto build_list = [&](DenseTileList& L, uint32_t g0) {  // row groups g0 .. 2 of X against each other
+        L.off = dense_tiles.size();
+        for (uint32_t a = g0; a < 3; ++a)
+          for (uint32_t bb = g0; bb < 3; ++bb)
+            for (uint32_t J = 0; J < pl.S_pad / (uint32_t)kDenseBN; ++J)
+              for (uint32_t I = 0; I < pl.S_pad / (uint32_t)kDenseBM; ++I) {
+                // some pair i < j inside the tile, both real sites
+                const uint32_t i_min = I * (uint32_t)kDenseBM;
+                const uint32_t j_max = std::min(J * (uint32_t)kDenseBN + (uint32_t)kDenseBN, pl.S) - 1u;
+                if (J * (uint32_t)kDenseBN >= pl.S || i_min >= j_max) continue;
+                dense_tiles.push_back(DenseTile{(uint8_t)a, (uint8_t)bb, (uint16_t)I, (uint16_t)J, 0, 0u, pl.k_blocks});
+              }
         // one CTA per SM walks the list with stride #SMs: a last, partly filled wave leaves SMs idle for a whole
         // tile time, so its tiles are cut along K into as many parts as fill it (added atomically into zeroed tiles)
-        const uint32_t n = (uint32_t)(dense_tiles.size() - pl.tile_off), grid = (uint32_t)ctx->num_sms;
+        const uint32_t n = (uint32_t)(dense_tiles.size() - L.off), grid = (uint32_t)ctx->num_sms;
         const uint32_t rem = n % grid;
         uint32_t parts = rem ? std::min<uint32_t>(8u, grid / rem) : 1u;
         while (parts > 1u && pl.k_blocks < 8u * parts) --parts;  // at least 8 k-blocks (1 024 reads) per part
-        pl.n_whole = n;
+        L.n_whole = n;
         if (parts >= 2u) {
-          pl.n_whole = n - rem;
+          L.n_whole = n - rem;
           std::vector<DenseTile> tail(dense_tiles.end() - rem, dense_tiles.end());
           dense_tiles.resize(dense_tiles.size() - rem);
           for (uint32_t q = 0; q < parts; ++q)
@@ -599,13 +626,19 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
               dense_tiles.push_back(t);
             }
         }
+        L.n = (uint32_t)(dense_tiles.size() - L.off);
+        for (uint32_t t = 0; t < L.n; ++t) {
+          const DenseTile& dt = dense_tiles[L.off + t];
+          L.macs += (uint64_t)kDenseBM * kDenseBN * (dt.kb1 - dt.kb0) * kDenseBK;
+        }
+      };
+      if (pl.four) build_list(pl.list4, 1u);
+      build_list(pl.list9, 0u);
+      if (pl.four) {
+        xt_words = std::max<uint64_t>(xt_words, 3ull * pl.k_blocks * kDenseBK * (pl.S_pad / 32u));
+        oth_words = std::max<uint64_t>(oth_words, (uint64_t)pl.S * pl.oth_cap);
+        oth_sites = std::max<uint32_t>(oth_sites, pl.S);
       }
-      pl.n_tiles = (uint32_t)(dense_tiles.size() - pl.tile_off);
-      for (uint32_t t = 0; t < pl.n_tiles; ++t) {
-        const DenseTile& dt = dense_tiles[pl.tile_off + t];
-        pl.macs += (uint64_t)kDenseBM * kDenseBN * (dt.kb1 - dt.kb0) * kDenseBK;
-      }
-      b->dense_macs += pl.macs;
       gram_words += 9ull * pl.S_pad * pl.S_pad;
       x_bytes = std::max<uint64_t>(x_bytes, 3ull * pl.S_pad * pl.k_blocks * kDenseBK);
       d.gram_off = pl.gram_off;
@@ -653,8 +686,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       it.pair_begin = t * (uint32_t)kPairsMax;
       it.pair_cnt = (uint32_t)std::min<uint64_t>(kPairsMax, np - (uint64_t)t * kPairsMax);
       it.flags = (t == 0 ? ITEM_FIRST : 0u) | (nit == 1 ? ITEM_SINGLE : 0u) | (d.tiled ? ITEM_TILED : 0u) |
-                 (d.tiled == 2 ? ITEM_TILED_GRAM : 0u);
-      if (d.tiled) ++b->n_tiled_work_items;
+                 (d.tiled == 2 ? ITEM_TILED_GRAM : 0u) | (d.gram_off != kNoGram ? ITEM_GRAM : 0u);
+      if (d.tiled || d.gram_off != kNoGram) ++b->n_tiled_work_items;  // (not k_pairs_generic<0>'s)
       if (nit == 1 && np >= 1 && u.n_sites <= (uint32_t)kFastMaxS && u.n_reads <= (uint32_t)kFastMaxR) {
         it.flags |= ITEM_FAST;
         FastItem f;
@@ -753,6 +786,12 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
     BCU(pool_malloc(ctx, &b->d_x, x_bytes));
     BCU(cudaMemsetAsync(b->d_x, 0, x_bytes, bstream(b)));  // rows of the site padding stay zero
     BCU(pool_malloc(ctx, &b->d_gram, gram_words * sizeof(uint32_t)));
+    BCU(pool_malloc(ctx, &b->d_unit_mode, (size_t)n_units * sizeof(uint32_t)));
+    if (xt_words) {
+      BCU(pool_malloc(ctx, &b->d_xt, xt_words * sizeof(uint32_t)));
+      BCU(pool_malloc(ctx, &b->d_oth_list, oth_words * sizeof(uint32_t)));
+      BCU(pool_malloc(ctx, &b->d_oth_cnt, (size_t)oth_sites * sizeof(uint32_t)));
+    }
     BCU(pool_malloc(ctx, &b->d_tiles, dense_tiles.size() * sizeof(DenseTile)));
     BCU(cudaMemcpyAsync(b->d_tiles, dense_tiles.data(), dense_tiles.size() * sizeof(DenseTile), cudaMemcpyHostToDevice,
                         bstream(b)));
@@ -911,6 +950,7 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
   P.dense = b->d_dense;
   P.unit_rec_off = b->d_unit_rec_off;
   P.gram = b->d_gram;
+  P.unit_mode = b->d_unit_mode;
   P.unit_base = b->unit_base;
   P.tile_counts = b->d_tile_counts;
 
@@ -928,30 +968,48 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
     ++ctx->launches;
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[4], bstream(b)));
+  if (!b->dense_plans.empty())  // every dense unit starts a run in the four-block form
+    CU(ctx, cudaMemsetAsync(b->d_unit_mode, 0, (size_t)b->n_units * sizeof(uint32_t), bstream(b)));
   for (const DensePlan& pl : b->dense_plans) {
-    // K3: bit-planes -> 0/1 bytes -> nine count matrices on the tensor cores
-    const uint64_t groups = 3ull * pl.S * pl.k_blocks * (kDenseBK / 16);
-    const unsigned egrid = (unsigned)std::min<uint64_t>((groups + 255) / 256, (uint64_t)ctx->num_sms * 16u);
-    k_expand_planes<<<egrid, 256, 0, bstream(b)>>>(b->d_planes + pl.plane_off, pl.S, pl.W, pl.S_pad, b->d_x);
-    ++ctx->launches;
-    DenseParams D;
-    D.tiles = b->d_tiles + pl.tile_off;
-    D.n_tiles = pl.n_tiles;
-    D.k_blocks = pl.k_blocks;
-    D.S_pad = pl.S_pad;
-    D.gram = b->d_gram + pl.gram_off;
-    D.error = reinterpret_cast<uint32_t*>(&b->d_header->pad);
-    const unsigned ggrid = (unsigned)std::min<uint32_t>(pl.n_tiles, (uint32_t)ctx->num_sms);
-    if (pl.n_tiles > pl.n_whole) {
-      k_zero_partial_tiles<<<pl.n_tiles - pl.n_whole, 256, 0, bstream(b)>>>(D.tiles + pl.n_whole, pl.n_tiles - pl.n_whole,
-                                                                            pl.S_pad, D.gram);
-      ++ctx->launches;
-    }
+    // K3: bit-planes -> 0/1 bytes -> count matrices on the tensor cores (lgmi_dense.cuh)
+    uint32_t* mode = b->d_unit_mode + pl.unit;
+    const uint32_t* planes = b->d_planes + pl.plane_off;
+    const uint64_t K_pad = (uint64_t)pl.k_blocks * kDenseBK;
+    if (pl.four) CU(ctx, cudaMemsetAsync(b->d_oth_cnt, 0, (size_t)pl.S * sizeof(uint32_t), bstream(b)));
+    else CU(ctx, cudaMemsetAsync(mode, 1, sizeof(uint32_t), bstream(b)));  // (any non-zero value: nine blocks)
+    k_dense_prep<<<dim3((pl.W + 7u) / 8u, pl.S_pad / 256u), 256, 0, bstream(b)>>>(planes, pl.S, pl.W, pl.S_pad, b->d_x, b->d_xt,
+                                                                                 b->d_oth_cnt, b->d_oth_list, pl.oth_cap, mode);
+    const unsigned cgrid = (unsigned)std::min<uint64_t>(((uint64_t)pl.S * pl.W + 255) / 256, (uint64_t)ctx->num_sms * 16u);
+    k_dense_cover<<<cgrid, 256, 0, bstream(b)>>>(planes, pl.S, pl.W, b->d_x, mode);
+    ctx->launches += 2;
     const bool last = &pl == &b->dense_plans.back();
     if (last && timing) CU(ctx, cudaEventRecord(b->ev[6], bstream(b)));
-    k_gram_i8<<<ggrid, kDenseThreads, kDenseSmemBytes, bstream(b)>>>(pl.tmap, D);
+    for (int form = pl.four ? 0 : 1; form < 2; ++form) {  // the launch of the form the unit is not in returns at once
+      const DenseTileList& L = form ? pl.list9 : pl.list4;
+      DenseParams D;
+      D.tiles = b->d_tiles + L.off;
+      D.n_tiles = L.n;
+      D.k_blocks = pl.k_blocks;
+      D.S_pad = pl.S_pad;
+      D.gram = b->d_gram + pl.gram_off;
+      D.error = reinterpret_cast<uint32_t*>(&b->d_header->pad);
+      D.mode = mode;
+      D.nine = (uint32_t)form;
+      const unsigned ggrid = (unsigned)std::min<uint32_t>(L.n, (uint32_t)ctx->num_sms);
+      if (L.n > L.n_whole) {
+        k_zero_partial_tiles<<<L.n - L.n_whole, 256, 0, bstream(b)>>>(D.tiles + L.n_whole, L.n - L.n_whole, pl.S_pad, D.gram,
+                                                                     mode, (uint32_t)form);
+        ++ctx->launches;
+      }
+      k_gram_i8<<<ggrid, kDenseThreads, kDenseSmemBytes, bstream(b)>>>(pl.tmap, D);
+      ++ctx->launches;
+    }
     if (last && timing) CU(ctx, cudaEventRecord(b->ev[7], bstream(b)));
-    ++ctx->launches;
+    if (pl.four) {
+      k_other_fix<<<pl.S, 256, 0, bstream(b)>>>(b->d_xt, K_pad, pl.S, pl.S_pad, b->d_oth_cnt, b->d_oth_list, pl.oth_cap,
+                                               b->d_gram + pl.gram_off, mode);
+      ++ctx->launches;
+    }
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[5], bstream(b)));
   if (b->n_tile_items) {
@@ -1074,11 +1132,15 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
     // everything the small-unit kernel does not take; exits at once when there is nothing
     if (b->n_tile_items || b->n_gram_tiles) {  // ordering + emission of what k_tile_mi / k_tile_finish computed
       const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
-      k_pairs_generic<true><<<grid, kThreads, 0, bstream(b)>>>(P);
+      k_pairs_generic<1><<<grid, kThreads, 0, bstream(b)>>>(P);
       ++ctx->launches;
     }
     const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
-    k_pairs_generic<false><<<grid, kThreads, 0, bstream(b)>>>(P);
+    if (!b->dense_plans.empty()) {  // the deep units: tables from the count matrices
+      k_pairs_generic<2><<<(unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 3u), kThreads, 0, bstream(b)>>>(P);
+      ++ctx->launches;
+    }
+    k_pairs_generic<0><<<grid, kThreads, 0, bstream(b)>>>(P);
     ++ctx->launches;
   }
   if (b->n_mean_items) {
@@ -1113,11 +1175,23 @@ static int fill_scalars(lgmi_batch* b, lgmi_result* out) {
     CU(ctx, cudaEventElapsedTime(&ms, b->ev[4], b->ev[5]));
     out->dense_kernel_ms = ms;
   }
-  if (timing && !b->dense_plans.empty()) {
-    CU(ctx, cudaEventElapsedTime(&ms, b->ev[6], b->ev[7]));
-    out->gram_kernel_ms = ms;
-    const DensePlan& pl = b->dense_plans.back();
-    out->gram_macs = pl.macs;
+  if (!b->dense_plans.empty()) {
+    // which form each deep unit took is decided on the device: read back (the stream has been synchronised)
+    std::vector<uint32_t> modes(b->n_units);
+    CU(ctx, cudaMemcpy(modes.data(), b->d_unit_mode, (size_t)b->n_units * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    b->dense_macs = 0;
+    out->n_dense_four = 0;
+    for (const DensePlan& pl : b->dense_plans) {
+      const bool nine = modes[pl.unit] != 0u;
+      b->dense_macs += nine ? pl.list9.macs : pl.list4.macs;
+      out->n_dense_four += nine ? 0u : 1u;
+    }
+    if (timing) {
+      CU(ctx, cudaEventElapsedTime(&ms, b->ev[6], b->ev[7]));
+      out->gram_kernel_ms = ms;
+      const DensePlan& pl = b->dense_plans.back();
+      out->gram_macs = modes[pl.unit] ? pl.list9.macs : pl.list4.macs;
+    }
   }
   out->n_dense_units = (uint32_t)b->dense_plans.size();
   out->dense_macs = b->dense_macs;

@@ -1,14 +1,25 @@
 // lgmi_dense.cuh -- the deep-unit path: contingency counts as a dense int8
 // contraction on the 5th-generation tensor cores (tcgen05 / TMEM / TMA).
 //
-// For a unit with many reads the nine cells of every pair's 3x3 table are the
-// nine blocks of a Gram matrix
-//        G[a][b][i][j] = sum_r X[a][i][r] * X[b][j][r],   a, b in {other, minor, major}
-// of the 0/1 indicator matrix X (3*S_pad rows, K_pad = 32*W columns, one byte per
-// read, K-contiguous).  T[a*3+b] of pair (i, j) is G[a][b][i][j]; integer and
-// exact (s32 accumulators, counts <= R < 2^31).
+// For a unit with many reads the cells of every pair's 3x3 table are blocks of a Gram matrix
+//        G[a][b][i][j] = sum_r X[a][i][r] * X[b][j][r]
+// of 0/1 indicator rows X (one byte per read, K-contiguous, K_pad = 32*W columns); integer and
+// exact (s32 accumulators, counts <= R < 2^31).  The indicator sets are nested -- C covered,
+// P = covered with the site's major or minor allele, M = major -- and the table follows by
+// inclusion-exclusion (gram_table in lgmi_kernels.cuh).  Two forms, chosen on the device per unit and run:
 //
-//   k_expand_planes   bit-planes [M | m | C] -> X rows in label order [O | m | M]
+//   four blocks   reads labelled "other" (covered, neither major nor minor) are rare: only P.P, P.M, M.P, M.M
+//   (mode 0)      go through the tensor cores (2.25 x fewer multiply-accumulates); the five cells that
+//                 involve an "other" label come from the listed (site, read) entries: k_dense_prep lists them
+//                 and writes the label planes transposed (one bit row per read), k_other_fix
+//                 adds, for every listed read of a site, that read's bit rows into per-partner counters
+//   nine blocks   some site lists more than R/64 "other" reads: all of C, P, M against C, P, M
+//   (mode != 0)
+//
+//   k_dense_prep      bit-planes [M | m | C] -> X row groups P, M; per site the reads with label "other" (more
+//                     than the list holds -> mode 1) and the transposed label planes O, m, M
+//   k_dense_cover     nine blocks only: X row group C
+//   k_other_fix       the "other" cells of every pair from the lists and the transposed planes
 //   k_gram_i8         one 128 x 256 output tile per CTA iteration:
 //                       warp 0  TMA producer (cp.async.bulk.tensor, 128B swizzle)
 //                       warp 1  single-thread tcgen05.mma.kind::i8 issuer, M=128 N=256 K=32
@@ -38,7 +49,7 @@ constexpr uint32_t kDenseSmemBytes = kDenseStages * kDenseStageBytes + 1024 /*al
 constexpr uint32_t kDenseTmemCols = 256;
 
 struct DenseTile {
-  uint8_t a, b;       // planes (label order: 0 other, 1 minor, 2 major)
+  uint8_t a, b;       // row groups of X (0 covered, 1 major or minor, 2 major)
   uint16_t I, J;      // site blocks: rows [128 I, +128), columns [256 J, +256)
   uint16_t partial;   // 1: the tile's K range is shared by several items (last wave): results are added atomically
                       //    into a zeroed tile
@@ -53,33 +64,243 @@ struct DenseParams {
   uint32_t S_pad;     // multiple of 256
   uint32_t* gram;     // [9][S_pad][S_pad]
   uint32_t* error;    // set to 1 if a barrier wait ran out (never in a correct run)
+  const uint32_t* mode;  // the unit's form this run (0 four blocks, else nine): a launch whose list is of the
+  uint32_t nine;         // other form (nine != 0 vs *mode != 0) returns at once
 };
 
 // ------------------------------------------------------------------ expansion
 // 4 bits -> 4 bytes of 0/1
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
-// one thread per 16 output bytes of one (plane, site) row
-__global__ void __launch_bounds__(256) k_expand_planes(const uint32_t* __restrict__ planes, uint32_t S, uint32_t W,
-                                                       uint32_t S_pad, uint8_t* __restrict__ X) {
+constexpr uint32_t kDenseOthDiv = 64u;   // a site lists up to max(256, R / 64) reads with label "other"
+constexpr uint32_t kDenseOthMin = 256u;
+
+// 32 x 32 bit transpose across a warp: lane p ends up with bit q = bit p of lane q's word
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
+#pragma unroll
+  for (uint32_t j = 16u, m = 0x0000ffffu; j; j >>= 1, m ^= m << j) {
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+    x = (lane & j) ? ((x & ~m) | ((y & ~m) >> j)) : ((x & m) | ((y & m) << j));
+  }
+  return x;
+}
+
+__device__ __forceinline__ void store_bytes32(uint8_t* __restrict__ dst, uint32_t bits) {
+  uint4 lo, hi;
+  lo.x = spread4(bits & 15u);
+  lo.y = spread4((bits >> 4) & 15u);
+  lo.z = spread4((bits >> 8) & 15u);
+  lo.w = spread4((bits >> 12) & 15u);
+  hi.x = spread4((bits >> 16) & 15u);
+  hi.y = spread4((bits >> 20) & 15u);
+  hi.z = spread4((bits >> 24) & 15u);
+  hi.w = spread4(bits >> 28);
+  reinterpret_cast<uint4*>(dst)[0] = lo;
+  reinterpret_cast<uint4*>(dst)[1] = hi;
+}
+
+// One pass over the planes.  CTA = 256 sites (a warp per group of 32, a lane per site) x 256 reads (8 words):
+// every lane reads whole 32-byte sectors of its site's rows and writes its 256 bytes of the X row groups
+// 1 (major or minor) and 2 (major): X[g][s][r].  For the four-block form -- unless the run was told "nine
+// blocks" up front (*mode != 0 at the start) -- it also lists the site's reads with label "other" (any order;
+// a list that overflows sets *mode: nine blocks) and transposes the label words O, m, M in registers (5 shuffle
+// steps per 32 x 32 block); those leave through a shared-memory tile as whole sectors of
+// xt[label][read][site word].  Row group 0 (covered) is written by k_dense_cover, only for nine blocks.
+__global__ void __launch_bounds__(256) k_dense_prep(const uint32_t* __restrict__ planes, uint32_t S, uint32_t W,
+                                                    uint32_t S_pad, uint8_t* __restrict__ X, uint32_t* __restrict__ xt,
+                                                    uint32_t* __restrict__ cnt, uint32_t* __restrict__ list, uint32_t cap,
+                                                    uint32_t* __restrict__ mode) {
+  __shared__ __align__(16) uint32_t tile[3][256][8];  // [label][read of the block][site group of the block]
+  __shared__ uint32_t s_nine;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  // one read per CTA: another CTA of this launch may set the flag meanwhile (the four-block outputs are not used then)
+  if (tid == 0) s_nine = *reinterpret_cast<volatile uint32_t*>(mode);
+  __syncthreads();
+  const uint32_t nine = s_nine;
+  const uint32_t w0 = blockIdx.x * 8u, sg0 = blockIdx.y * 8u;
+  const uint32_t s = (sg0 + warp) * 32u + lane;
   const uint64_t K_pad = 32ull * W;
-  const uint64_t per_row = K_pad / 16u;  // 16-byte groups per row
-  const uint64_t total = 3ull * S * per_row;
+  const uint32_t Sw = S_pad >> 5;
+  const bool second = w0 + 4u < W;  // W is a multiple of 4: the block's second four words may lie past the row
+  uint32_t Mw[8], mw[8], Cw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) Mw[k] = mw[k] = Cw[k] = 0u;
+  if (s < S) {
+    const uint32_t* row = planes + (size_t)s * 3u * W + w0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !second) break;
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(row) + h);
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(row + W) + h);
+      const uint4 c = __ldg(reinterpret_cast<const uint4*>(row + 2u * W) + h);
+      Mw[4 * h] = a.x; Mw[4 * h + 1] = a.y; Mw[4 * h + 2] = a.z; Mw[4 * h + 3] = a.w;
+      mw[4 * h] = b.x; mw[4 * h + 1] = b.y; mw[4 * h + 2] = b.z; mw[4 * h + 3] = b.w;
+      Cw[4 * h] = c.x; Cw[4 * h + 1] = c.y; Cw[4 * h + 2] = c.z; Cw[4 * h + 3] = c.w;
+    }
+  }
+  if (!nine) {  // the site's "other" reads of these eight words, one reservation in its list
+    uint32_t n = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) n += (uint32_t)__popc(Cw[k] & ~Mw[k] & ~mw[k]);
+    if (n) {
+      uint32_t idx = atomicAdd(cnt + s, n);
+      if (idx + n > cap) {
+        *mode = 1u;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          uint32_t O = Cw[k] & ~Mw[k] & ~mw[k];
+          while (O) {
+            const uint32_t bit = (uint32_t)__ffs((int)O) - 1u;
+            O &= O - 1u;
+            list[(size_t)s * cap + idx++] = (w0 + (uint32_t)k) * 32u + bit;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t L2 = Mw[k] & Cw[k], L1 = mw[k] & Cw[k] & ~Mw[k], L0 = Cw[k] & ~Mw[k] & ~mw[k];
+    if (s < S && (k < 4 || second)) {
+      uint8_t* x = X + ((size_t)S_pad + s) * K_pad + (size_t)(w0 + k) * 32u;
+      store_bytes32(x, L1 | L2);
+      store_bytes32(x + (size_t)S_pad * K_pad, L2);
+    }
+    if (!nine) {  // (CTA-uniform)
+      tile[0][k * 32 + lane][warp] = transpose32(L0, lane);
+      tile[1][k * 32 + lane][warp] = transpose32(L1, lane);
+      tile[2][k * 32 + lane][warp] = transpose32(L2, lane);
+    }
+  }
+  if (nine) return;
+  __syncthreads();
+  const uint32_t n_reads = second ? 256u : 128u;
+  for (uint32_t e = tid; e < 3u * n_reads * 2u; e += 256u) {
+    const uint32_t half = e & 1u, r = (e >> 1) % n_reads, b = (e >> 1) / n_reads;
+    const uint4 v = *reinterpret_cast<const uint4*>(&tile[b][r][4u * half]);
+    *reinterpret_cast<uint4*>(xt + ((size_t)b * K_pad + (size_t)w0 * 32u + r) * Sw + sg0 + 4u * half) = v;
+  }
+}
+
+// nine blocks only: row group 0 of X (covered), one thread per 32 reads of a site
+__global__ void __launch_bounds__(256) k_dense_cover(const uint32_t* __restrict__ planes, uint32_t S, uint32_t W,
+                                                     uint8_t* __restrict__ X, const uint32_t* __restrict__ mode) {
+  if (!*mode) return;
+  const uint64_t total = (uint64_t)S * W, K_pad = 32ull * W;
   for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t row = e / per_row;
-    const uint32_t g = (uint32_t)(e - row * per_row);  // 16 reads: half of word g/2
-    const uint32_t s = (uint32_t)(row % S), label = (uint32_t)(row / S);
-    const uint32_t* src = planes + (size_t)s * 3u * W;
-    const uint32_t w = g >> 1;
-    const uint32_t M = src[w], m = src[W + w], C = src[2u * W + w];
-    uint32_t bits = (label == 2u) ? (M & C) : (label == 1u) ? (m & C & ~M) : (C & ~M & ~m);
-    bits = (bits >> ((g & 1u) * 16u)) & 0xffffu;
-    uint4 out;
-    out.x = spread4(bits & 15u);
-    out.y = spread4((bits >> 4) & 15u);
-    out.z = spread4((bits >> 8) & 15u);
-    out.w = spread4(bits >> 12);
-    *reinterpret_cast<uint4*>(X + ((size_t)label * S_pad + s) * K_pad + (size_t)g * 16u) = out;
+    const uint32_t s = (uint32_t)(e / W), w = (uint32_t)(e - (uint64_t)s * W);
+    store_bytes32(X + (size_t)s * K_pad + (size_t)w * 32u, planes[(size_t)s * 3u * W + 2u * W + w]);
+  }
+}
+
+// The table cells with an "other" label, four-block form.  One CTA per site s: for every listed read r of s and
+// every partner t, xt[b][r] says whether t carries label b at r; the bit rows are added up in packed 4-bit
+// counters (15 reads), those in packed bytes (255 reads), those in shared memory.  Written where gram_table
+// reads them: slot 0 / 1 / 2 of pair (s, t), t > s, = reads "other" at s and other / minor / major at t;
+// slot 3 / 6 of pair (t, s), t < s, = reads minor / major at t and "other" at s.
+__global__ void __launch_bounds__(256) k_other_fix(const uint32_t* __restrict__ xt, uint64_t K_pad, uint32_t S,
+                                                   uint32_t S_pad, const uint32_t* __restrict__ cnt,
+                                                   const uint32_t* __restrict__ list, uint32_t cap,
+                                                   uint32_t* __restrict__ gram, const uint32_t* __restrict__ mode) {
+  if (*mode) return;
+  __shared__ uint32_t acc[3][2048];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t half = warp & 1u, quarter = warp >> 1;  // word half of a 64-word pass; every fourth listed read
+  const uint32_t s = blockIdx.x, Sw = S_pad >> 5;
+  const uint32_t n = min(cnt[s], cap);
+  const uint32_t* __restrict__ mine = list + (size_t)s * cap;
+  const size_t plane = (size_t)S_pad * S_pad;
+  for (uint32_t w0 = 0; w0 < Sw; w0 += 64u) {
+    for (uint32_t e = tid; e < 3u * 2048u; e += 256u) (&acc[0][0])[e] = 0u;
+    __syncthreads();
+    const uint32_t word = w0 + half * 32u + lane;
+    const bool valid = word < Sw;
+    uint32_t nb[3][4], by[3][8];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) nb[b][q] = 0u;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) by[b][c] = 0u;
+    }
+    auto nib_to_bytes = [&]() {
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          by[b][q] += nb[b][q] & 0x0f0f0f0fu;             // byte k <- partner bit 8 k + q
+          by[b][4 + q] += (nb[b][q] >> 4) & 0x0f0f0f0fu;  // byte k <- partner bit 8 k + 4 + q
+          nb[b][q] = 0u;
+        }
+    };
+    auto bytes_to_smem = [&]() {
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t v = (by[b][c] >> (8 * k)) & 0xffu;
+            if (v) atomicAdd(&acc[b][(half * 32u + lane) * 32u + 8u * k + c], v);
+          }
+          by[b][c] = 0u;
+        }
+    };
+    uint32_t in_nib = 0, in_byte = 0;
+    // this warp's listed reads are k = quarter + 4 m: fetched 32 at a time (one per lane), and the bit rows of
+    // eight reads are requested before the first is added (the loads are L2 hits ~600 cycles away)
+    const uint32_t n_mine = n > quarter ? (n - quarter + 3u) / 4u : 0u;
+    for (uint32_t m0 = 0; m0 < n_mine; m0 += 32u) {
+      const uint32_t have = min(32u, n_mine - m0);
+      const uint32_t my = lane < have ? __ldg(mine + quarter + 4u * (m0 + lane)) : 0u;
+      for (uint32_t q0 = 0; q0 < have; q0 += 8u) {
+        uint32_t x[8][3];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t r = __shfl_sync(0xffffffffu, my, (q0 + (uint32_t)u) & 31u);
+          const bool ok = valid && q0 + (uint32_t)u < have;
+#pragma unroll
+          for (int b = 0; b < 3; ++b) x[u][b] = ok ? __ldg(xt + ((size_t)b * K_pad + r) * Sw + word) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            nb[b][0] += x[u][b] & 0x11111111u;
+            nb[b][1] += (x[u][b] >> 1) & 0x11111111u;
+            nb[b][2] += (x[u][b] >> 2) & 0x11111111u;
+            nb[b][3] += (x[u][b] >> 3) & 0x11111111u;
+          }
+          if (++in_nib == 15u) {
+            nib_to_bytes();
+            in_nib = 0;
+            if (++in_byte == 17u) {  // 17 * 15 = 255
+              bytes_to_smem();
+              in_byte = 0;
+            }
+          }
+        }
+      }
+    }
+    nib_to_bytes();
+    bytes_to_smem();
+    __syncthreads();
+    for (uint32_t tl = tid; tl < 2048u; tl += 256u) {
+      const uint32_t t = w0 * 32u + tl;
+      if (t >= S) break;
+      if (t > s) {
+        uint32_t* out = gram + (size_t)s * S_pad + t;
+        out[0] = acc[0][tl];
+        out[plane] = acc[1][tl];
+        out[2u * plane] = acc[2][tl];
+      } else if (t < s) {
+        uint32_t* out = gram + (size_t)t * S_pad + s;
+        out[3u * plane] = acc[1][tl];
+        out[6u * plane] = acc[2][tl];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -171,7 +392,9 @@ __device__ __forceinline__ void tmem_load_32x32(uint32_t taddr, uint32_t (&r)[32
 // zero the 128 x 256 output tiles that several work items add into (one CTA per listed item; an item whose
 // kb0 is 0 zeroes its tile, the others skip)
 __global__ void __launch_bounds__(256) k_zero_partial_tiles(const DenseTile* __restrict__ tiles, uint32_t n_tiles,
-                                                            uint32_t S_pad, uint32_t* __restrict__ gram) {
+                                                            uint32_t S_pad, uint32_t* __restrict__ gram,
+                                                            const uint32_t* __restrict__ mode, uint32_t nine) {
+  if ((*mode != 0u) != (nine != 0u)) return;  // the list of the unit's other form
   const DenseTile tile = tiles[blockIdx.x];
   if (blockIdx.x >= n_tiles || !tile.partial || tile.kb0 != 0) return;
   uint32_t* base = gram + ((size_t)(tile.a * 3u + tile.b) * S_pad + (size_t)tile.I * kDenseBM) * S_pad + (size_t)tile.J * kDenseBN;
@@ -184,6 +407,7 @@ __global__ void __launch_bounds__(256) k_zero_partial_tiles(const DenseTile* __r
 // ------------------------------------------------------------------ the GEMM
 __global__ void __launch_bounds__(kDenseThreads, 1) k_gram_i8(const __grid_constant__ CUtensorMap tmap,
                                                               const DenseParams P) {
+  if ((*P.mode != 0u) != (P.nine != 0u)) return;  // the list of the unit's other form (CTA-uniform, before any barrier)
   extern __shared__ uint8_t dense_smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dense_smem_raw) + 1023u) & ~uintptr_t(1023));

@@ -41,7 +41,8 @@ constexpr uint64_t kNoGram = ~0ull;
 enum : uint32_t {
   ITEM_FIRST = 1u, ITEM_SINGLE = 2u, ITEM_FAST = 4u, ITEM_PRE = 8u /* counted by k_small_gram */,
   ITEM_TILED = 16u /* MI precomputed by k_tile_mi or k_tile_gram + k_tile_finish */,
-  ITEM_TILED_GRAM = 32u /* ... by the latter, which also counts the item's emitted pairs */
+  ITEM_TILED_GRAM = 32u /* ... by the latter, which also counts the item's emitted pairs */,
+  ITEM_GRAM = 64u /* deep unit: tables from the count matrices of the tensor-core path (k_pairs_generic<2>) */
 };
 
 struct Item {
@@ -72,6 +73,7 @@ struct RunParams {
   uint8_t* item_dense;                 // k_count: fast-eligible item with > kOthCap "other" reads at a site
   uint32_t* n_generic;                 // items k_pairs_generic has to process (host count + dense ones)
   const uint32_t* gram;                // count matrices of the tensor-core path (DevUnit::gram_off)
+  const uint32_t* unit_mode;           // per unit, tensor-core path: 0 four Gram blocks + "other" cells, else nine blocks
   uint32_t* tile_counts;               // EMIT_COUNTS: 3x3 tables of the k_tile_mi units, 9 per dense slot
   uint32_t unit_base;                  // added to the unit field of every record
   Header* header;
@@ -147,17 +149,40 @@ __device__ __forceinline__ bool pair_table(const uint4* __restrict__ ri, const u
   return false;
 }
 
-// 3x3 table of pair (i, j) from the Gram matrices of the tensor-core path; returns N
+// 3x3 table of pair (i, j) from the count matrices of the tensor-core path (lgmi_dense.cuh); returns N.
+// Slot a * 3 + b of the scratch holds, for row group a of site i and b of site j (0 covered, 1 major or
+// minor, 2 major), |X_a,i & X_b,j|; the sets are nested, so the labels follow by inclusion-exclusion.
+// nine == 0 (four-block form): only slots 4, 5, 7, 8 are Gram blocks; slots 0, 1, 2, 3, 6 hold the cells
+// with an "other" label as k_other_fix counted them.
 __device__ __forceinline__ uint32_t gram_table(const uint32_t* __restrict__ g, uint32_t S_pad, uint32_t i, uint32_t j,
-                                               uint32_t T[9]) {
+                                               uint32_t nine, uint32_t T[9]) {
   const size_t plane = (size_t)S_pad * S_pad;
   const uint32_t* p = g + (size_t)i * S_pad + j;
+  uint32_t G[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) G[k] = __ldg(p + (size_t)k * plane);
+  const uint32_t PP = G[4], PM = G[5], MP = G[7], MM = G[8];
+  T[8] = MM;
+  T[7] = MP - MM;            // i major, j minor
+  T[5] = PM - MM;            // i minor, j major
+  T[4] = PP - MP - PM + MM;
+  if (nine) {
+    const uint32_t CC = G[0], CP = G[1], CM = G[2], PC = G[3], MC = G[6];
+    T[6] = MC - MP;                  // i major, j other
+    T[3] = (PC - MC) - (PP - MP);    // i minor, j other
+    T[2] = CM - PM;                  // i other, j major
+    T[1] = (CP - CM) - (PP - PM);    // i other, j minor
+    T[0] = CC - CP - PC + PP;
+  } else {
+    T[0] = G[0];
+    T[1] = G[1];
+    T[2] = G[2];
+    T[3] = G[3];
+    T[6] = G[6];
+  }
   uint32_t n = 0;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    T[k] = __ldg(p + (size_t)k * plane);
-    n += T[k];
-  }
+  for (int k = 0; k < 9; ++k) n += T[k];
   return n;
 }
 
@@ -168,22 +193,40 @@ __device__ __forceinline__ uint32_t gram_table(const uint32_t* __restrict__ g, u
 // sites or 256 reads, pair-less units, and small units with dense third alleles.
 // The output offset of every item is known before the kernel starts (k_count +
 // exclusive scan), so no CTA ever waits on another.
-// kTiled: only the items whose MI k_tile_mi has already computed (pure ordering and emission: few
-// registers, four CTAs per SM to hide the loads); !kTiled: everything else.
-template <bool kTiled>
-__global__ void __launch_bounds__(kThreads, kTiled ? 4 : 2) k_pairs_generic(const RunParams P) {
+// kKind 1: only the items whose MI k_tile_mi / k_tile_finish has already computed (pure ordering and
+// emission: few registers, four CTAs per SM to hide the loads); kKind 2: the items of the deep units,
+// tables from the count matrices of the tensor-core path -- classified first, then the branch-free
+// epilogues of lgmi_fast.cuh over full warps of each class; kKind 0: everything else.
+// 2x2 block of a deep unit's table alone (the pairs without an "other" label need nothing else)
+__device__ __forceinline__ void gram_table_2x2(const uint32_t* __restrict__ g, uint32_t S_pad, uint32_t i, uint32_t j,
+                                               uint32_t& mm, uint32_t& mM, uint32_t& Mm, uint32_t& MM) {
+  const size_t plane = (size_t)S_pad * S_pad;
+  const uint32_t* p = g + (size_t)i * S_pad + j;
+  const uint32_t PP = __ldg(p + 4u * plane), PM = __ldg(p + 5u * plane), MP = __ldg(p + 7u * plane);
+  MM = __ldg(p + 8u * plane);
+  Mm = MP - MM;
+  mM = PM - MM;
+  mm = PP - MP - PM + MM;
+}
+
+template <int kKind>
+__global__ void __launch_bounds__(kThreads, kKind == 1 ? 4 : (kKind == 2 ? 3 : 2)) k_pairs_generic(const RunParams P) {
+  constexpr bool kTiled = kKind == 1;
   __shared__ double s_mi[kPairsMax];    // MI of each pair of the item, NaN = no MI
   __shared__ uint32_t s_ij[kPairsMax];  // (i << 16) | j
   __shared__ uint32_t s_warp[kThreads / 32];
+  __shared__ uint16_t s_list[kKind == 2 ? kPairsMax : 1];  // kKind 2: pairs with a 2x2 table from the front, the others from the back
+  __shared__ uint32_t s_n2, s_n3;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const LnGlobal ln{P.lntab};
   const bool het_only = (P.mode & LGMI_MODE_HET_ONLY) != 0u;
   const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
-  if (!kTiled && *P.n_generic == 0u) return;  // every item was a small unit taken by k_pairs_fast
+  if (kKind == 0 && *P.n_generic == 0u) return;  // every item was a small unit taken by k_pairs_fast
 
   for (uint32_t item_idx = blockIdx.x; item_idx < P.n_items; item_idx += gridDim.x) {
     const Item it = P.items[item_idx];
-    if (kTiled != ((it.flags & ITEM_TILED) != 0u)) continue;          // the other instantiation's
+    if (kTiled != ((it.flags & ITEM_TILED) != 0u)) continue;          // another instantiation's
+    if ((kKind == 2) != ((it.flags & ITEM_GRAM) != 0u)) continue;
     if ((it.flags & ITEM_FAST) && !P.item_dense[item_idx]) continue;  // k_pairs_fast's
     const DevUnit u = P.units[it.unit];
     const uint32_t W4 = u.W >> 2;
@@ -203,6 +246,71 @@ __global__ void __launch_bounds__(kThreads, kTiled ? 4 : 2) k_pairs_generic(cons
         if (pl != tid) lg_pair_advance(i, j, u.S, kThreads);
         s_ij[pl] = (i << 16) | j;
       }
+    } else if constexpr (kKind == 2) {
+      const uint32_t nine = P.unit_mode[it.unit];
+      const uint32_t* __restrict__ g = P.gram + u.gram_off;
+      const uint32_t lt = (1u << lane) - 1u;
+      if (tid == 0) {
+        s_n2 = 0u;
+        s_n3 = 0u;
+      }
+      __syncthreads();
+      // pass 1: the tables -> min-common filter, class of every pair (NaN for those without MI)
+      const uint32_t n_slots = (it.pair_cnt + 31u) & ~31u;
+      for (uint32_t pl = tid; pl < n_slots; pl += kThreads) {
+        uint32_t cls = 0u;  // 0 no MI, 2 -> 2x2 list, 3 -> 3x3 list
+        if (pl < it.pair_cnt) {
+          if (pl != tid) lg_pair_advance(i, j, u.S, kThreads);
+          s_ij[pl] = (i << 16) | j;
+          bool evaluate = true;
+          if (skip_nonhet)
+            evaluate = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
+                       ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
+          if (evaluate) {
+            uint32_t T[9];
+            const uint32_t n_common = gram_table(g, u.S_pad, i, j, nine, T);
+            if ((int)n_common >= P.min_common)  // strict '<' drops (mutual_information.py:19)
+              cls = (T[0] | T[1] | T[2] | T[3] | T[6]) ? 3u : 2u;
+          }
+          if (!cls) s_mi[pl] = lg_nan();
+        }
+        const uint32_t m2 = __ballot_sync(0xffffffffu, cls == 2u);
+        const uint32_t m3 = __ballot_sync(0xffffffffu, cls == 3u);
+        uint32_t b2 = 0u, b3 = 0u;
+        if (lane == 0) {
+          if (m2) b2 = atomicAdd(&s_n2, (uint32_t)__popc(m2));
+          if (m3) b3 = atomicAdd(&s_n3, (uint32_t)__popc(m3));
+        }
+        b2 = __shfl_sync(0xffffffffu, b2, 0);
+        b3 = __shfl_sync(0xffffffffu, b3, 0);
+        if (cls == 2u) s_list[b2 + __popc(m2 & lt)] = (uint16_t)pl;
+        if (cls == 3u) s_list[kPairsMax - 1u - (b3 + __popc(m3 & lt))] = (uint16_t)pl;
+      }
+      __syncthreads();
+      // pass 2: MI over warp-sized chunks of each class (the tables again: L2 hits)
+      const uint32_t n2 = s_n2, n3 = s_n3;
+      const uint32_t nc2 = (n2 + 31u) >> 5, nc3 = (n3 + 31u) >> 5;
+      const GlobalTab tab{P.lntab};
+      const bool small_counts = u.R <= 65535u;  // the reorganised epilogues are checked for counts below 2^16
+      for (uint32_t c = warp; c < nc2 + nc3; c += kThreads / 32) {
+        if (c < nc2) {
+          const uint32_t q = c * 32u + lane;
+          if (q < n2) {
+            const uint32_t pl = s_list[q], ij = s_ij[pl];
+            uint32_t mm, mM, Mm, MM;
+            gram_table_2x2(g, u.S_pad, ij >> 16, ij & 0xffffu, mm, mM, Mm, MM);
+            s_mi[pl] = small_counts ? mi_2x2(tab, mm, mM, Mm, MM) : lg_mi_from_2x2(mm, mM, Mm, MM, ln);
+          }
+        } else {
+          const uint32_t q = (c - nc2) * 32u + lane;
+          if (q < n3) {
+            const uint32_t pl = s_list[kPairsMax - 1u - q], ij = s_ij[pl];
+            uint32_t T[9];
+            gram_table(g, u.S_pad, ij >> 16, ij & 0xffffu, nine, T);
+            s_mi[pl] = small_counts ? mi_3x3(tab, T) : lg_mi_from_table(T, ln);
+          }
+        }
+      }
     } else {
       for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
         if (pl != tid) lg_pair_advance(i, j, u.S, kThreads);
@@ -212,14 +320,7 @@ __global__ void __launch_bounds__(kThreads, kTiled ? 4 : 2) k_pairs_generic(cons
         if (skip_nonhet)
           evaluate = ((flags[i] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP) ||
                      ((flags[j] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP);
-        if (evaluate && u.gram_off != kNoGram) {
-          uint32_t T[9];
-          const uint32_t n_common = gram_table(P.gram + u.gram_off, u.S_pad, i, j, T);
-          if ((int)n_common >= P.min_common) {
-            if ((T[0] | T[1] | T[2] | T[3] | T[6]) == 0u) mi = lg_mi_from_2x2(T[4], T[5], T[7], T[8], ln);
-            else mi = lg_mi_from_table(T, ln);
-          }
-        } else if (evaluate) {
+        if (evaluate) {
           const uint4* ri = base + (size_t)i * 3u * W4;
           const uint4* rj = base + (size_t)j * 3u * W4;
           const uint32_t n_common = pair_common(ri, rj, W4);
@@ -281,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, kTiled ? 4 : 2) k_pairs_generic(cons
 #pragma unroll
             for (int k = 0; k < 9; ++k) T[k] = src[k];
           } else if (u.gram_off != kNoGram) {
-            gram_table(P.gram + u.gram_off, u.S_pad, ij >> 16, ij & 0xffffu, T);
+            gram_table(P.gram + u.gram_off, u.S_pad, ij >> 16, ij & 0xffffu, P.unit_mode[it.unit], T);
           } else {
             const uint4* ri = base + (size_t)(ij >> 16) * 3u * W4;
             const uint4* rj = base + (size_t)(ij & 0xffffu) * 3u * W4;
@@ -637,7 +738,7 @@ __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
         uint32_t n;
         if (u.gram_off != kNoGram) {
           uint32_t T[9];
-          n = gram_table(P.gram + u.gram_off, u.S_pad, i, j, T);
+          n = gram_table(P.gram + u.gram_off, u.S_pad, i, j, P.unit_mode[it.unit], T);
         } else {
           n = pair_common(base + (size_t)i * 3u * W4, base + (size_t)j * 3u * W4, W4);
         }
@@ -717,39 +818,52 @@ __global__ void __launch_bounds__(kMeanThreads) k_site_mean_dense(const DevUnit*
     cp_async_commit();  // (an empty group keeps the count of groups per tile at one)
   };
 
-  const uint32_t s = s0 + lane;
+  const uint32_t s = s0 + lane;  // (256 = 8 x 32 threads: a thread's entries of a tile all belong to site s0 + lane)
   const bool s_ok = s < S;
   const bool s_het = s_ok && (flags[s_ok ? s : 0u] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
   // all MI values are >= +0.0: CPython's compensated sum (mutual_information.py:56-58) without branches;
-  // an absent value adds +0.0, which leaves sum and compensation as they are
+  // an absent value adds +0.0, which leaves sum and compensation as they are.  Per tile: every thread first
+  // replaces the entries that do not count (no MI, the site itself, neither site a het_snp) by +0.0 and counts
+  // the others; warp 0 then runs the 32 serial sums over plain values -- two dependent fp64 additions per step
+  // (sum, compensation) with everything else off the critical path.
   double acc_s = 0.0, acc_c = 0.0;
-  uint32_t acc_n = 0;
+  uint32_t my_n = 0;
+  __shared__ uint32_t s_n[32];
+  if (tid < 32u) s_n[tid] = 0u;
 #pragma unroll
   for (uint32_t tb = 0; tb + 1u < (uint32_t)kMeanBufs; ++tb) request_tile(tb);
   for (uint32_t tb = 0; tb < n_blocks; ++tb) {
     request_tile(tb + kMeanBufs - 1u);   // into the buffer everybody left at the end of the previous iteration
     cp_async_wait<kMeanBufs - 1>();      // tile tb has landed (this thread's part; the barrier covers the rest)
     __syncthreads();
-    if (warp == 0 && s_ok) {             // one site per lane, partners ascending
-      const uint32_t b = tb % kMeanBufs, t0 = tb << 5;
-      const uint32_t partners = s_het ? 0xffffffffu : s_phet[b];  // a non-het site sums over its het partners only
-#pragma unroll 4
+    const uint32_t b = tb % kMeanBufs, t0 = tb << 5;
+    const uint32_t partners = s_het ? 0xffffffffu : s_phet[b];  // a non-het site sums over its het partners only
+#pragma unroll
+    for (uint32_t q = 0; q < 4u; ++q) {
+      const uint32_t tl = warp + 8u * q, t = t0 + tl;
+      const double v = s_tile[b][tl][lane];
+      const bool have = s_ok && t < S && t != s && ((partners >> tl) & 1u) && __double2hiint(v) < 0x7ff00000;  // NaN: no MI
+      s_tile[b][tl][lane] = have ? v : 0.0;
+      my_n += have ? 1u : 0u;
+    }
+    __syncthreads();
+    if (warp == 0) {                     // one site per lane, partners ascending
+#pragma unroll 8
       for (uint32_t tl = 0; tl < 32u; ++tl) {
-        const uint32_t t = t0 + tl;
-        const double v = s_tile[b][tl][lane];
-        const bool have = t < S && t != s && ((partners >> tl) & 1u) && __double2hiint(v) < 0x7ff00000;  // NaN: no MI
-        const double x = have ? v : 0.0;
+        const double x = s_tile[b][tl][lane];
         const double tt = __dadd_rn(acc_s, x);
-        const double big = (acc_s >= x) ? acc_s : x, small = (acc_s >= x) ? x : acc_s;
+        const double big = fmax(acc_s, x), small = fmin(acc_s, x);
         acc_c = __dadd_rn(acc_c, __dadd_rn(__dsub_rn(big, tt), small));
         acc_s = tt;
-        acc_n += have ? 1u : 0u;
       }
     }
     __syncthreads();  // tile tb consumed: its buffer is the target of the next request
   }
   cp_async_wait<0>();
+  if (my_n) atomicAdd(&s_n[lane], my_n);
+  __syncthreads();
   if (warp == 0 && s_ok) {
+    const uint32_t acc_n = s_n[lane];
     double mean = lg_nan();
     if (acc_n) {
       double tot = acc_s;

@@ -317,6 +317,46 @@ def test_dense_path_small_shapes(lg, dense_everything):
     assert np.array_equal(dense.site_mean, popc.site_mean, equal_nan=True)
 
 
+def _other_heavy_unit(rng, S, R, cov, third):
+    """Like _synth_unit with a chosen rate of third alleles (label "other")."""
+    a, k = synth.draw_alleles(rng, 1, S, R, cov)
+    al = a[0]
+    extra = (rng.random(al.shape) < third) & (al != synth.NOCOV)
+    al[extra] = synth.THIRD
+    return enc.EncodedUnit([1000 + 37 * s for s in range(S)],
+                           [("mismatch", "snp", "het_snp")[int(x)] for x in k[0]], synth.labels_from_alleles(al))
+
+
+@pytest.mark.parametrize("blocks", [4, 9])
+def test_dense_forms_agree_and_fall_back(lg, dense_everything, blocks):
+    """lgmi_set_dense_path: four Gram blocks + the "other" cells from the listed reads, or nine blocks.  Units with
+    few "other" reads take the four-block form, a unit with a site above max(256, R/64) of them falls back to nine
+    blocks on the device; counts, MI and means against the oracle, and the same records as the popcount path."""
+    ctx = dense_everything
+    ctx.set_dense_path(blocks)
+    try:
+        rng = np.random.default_rng(131)
+        sparse = [_synth_unit(rng, S, R, 0.6) for S, R in ((40, 700), (130, 1500), (300, 520), (65, 20000))]
+        some = _other_heavy_unit(rng, 90, 30000, 0.6, 0.004)      # ~100 "other" reads per site: listed (cap 468)
+        many = _other_heavy_unit(rng, 70, 3000, 0.7, 0.4)          # het sites: ~600 per site, over the cap of 256 -> nine blocks
+        lab = rng.integers(0, 3, size=(50, 900)).astype(np.uint8)
+        lab[lab == 0] = 255                                          # no "other" label at all: not covered instead
+        none = enc.EncodedUnit(list(range(50)), ["het_snp" if s % 7 == 0 else "mismatch" for s in range(50)], lab)
+        eus = sparse + [some, many, none]
+        for mc in (3, 6):
+            full = check_batch(lg, ctx, eus, mc, min_exact=0.9)
+            assert full.n_dense_units == len(eus)
+            assert full.n_dense_four == (len(eus) - 1 if blocks == 4 else 0)
+        dense = lg.mi_step_batched(lg.pack_units(eus), 6, lg.MODE_ALL_PAIRS | lg.MODE_EMIT_COUNTS, ctx=ctx)
+        ctx.set_dense_threshold(1 << 20, 1 << 30)
+        popc = lg.mi_step_batched(lg.pack_units(eus), 6, lg.MODE_ALL_PAIRS | lg.MODE_EMIT_COUNTS, ctx=ctx)
+        assert popc.n_dense_units == 0
+        assert np.array_equal(dense.records, popc.records) and np.array_equal(dense.counts, popc.counts)
+        assert np.array_equal(dense.site_mean, popc.site_mean, equal_nan=True)
+    finally:
+        ctx.set_dense_path(4)
+
+
 def test_dense_path_deep_unit(lg, gpu_ctx):
     """A unit over the default threshold (520 sites x 12 000 reads) mixed with small
     units in one batch: the deep one takes the tensor cores, the others do not."""
