@@ -201,6 +201,8 @@ struct lgmi_batch {
   uint32_t* d_xt = nullptr;     // four-block form: transposed label planes of the unit being contracted
   uint32_t* d_oth_cnt = nullptr, *d_oth_list = nullptr;  // ... and its listed "other" reads per site
   uint32_t* d_unit_mode = nullptr;  // per unit: the form of this run (0 four blocks, else nine)
+  cudaStream_t fix_stream = nullptr;             // k_other_fix runs beside k_gram_i8 (forked after k_dense_prep,
+  cudaEvent_t fix_fork = nullptr, fix_join = nullptr;  // joined before the tables are read)
   DenseTile* d_tiles = nullptr;
   uint64_t dense_macs = 0;      // multiply-accumulates the tile lists amount to
   // small units counted on the tensor cores
@@ -511,6 +513,9 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   ctx->dev_pool.release(b->d_oth_cnt);
   ctx->dev_pool.release(b->d_oth_list);
   ctx->dev_pool.release(b->d_unit_mode);
+  if (b->fix_stream) cudaStreamDestroy(b->fix_stream);
+  if (b->fix_fork) cudaEventDestroy(b->fix_fork);
+  if (b->fix_join) cudaEventDestroy(b->fix_join);
   ctx->dev_pool.release(b->d_tiles);
   ctx->dev_pool.release(b->d_tile_items);
   ctx->dev_pool.release(b->d_gram_tiles);
@@ -791,6 +796,9 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       BCU(pool_malloc(ctx, &b->d_xt, xt_words * sizeof(uint32_t)));
       BCU(pool_malloc(ctx, &b->d_oth_list, oth_words * sizeof(uint32_t)));
       BCU(pool_malloc(ctx, &b->d_oth_cnt, (size_t)oth_sites * sizeof(uint32_t)));
+      BCU(cudaStreamCreateWithFlags(&b->fix_stream, cudaStreamNonBlocking));
+      BCU(cudaEventCreateWithFlags(&b->fix_fork, cudaEventDisableTiming));
+      BCU(cudaEventCreateWithFlags(&b->fix_join, cudaEventDisableTiming));
     }
     BCU(pool_malloc(ctx, &b->d_tiles, dense_tiles.size() * sizeof(DenseTile)));
     BCU(cudaMemcpyAsync(b->d_tiles, dense_tiles.data(), dense_tiles.size() * sizeof(DenseTile), cudaMemcpyHostToDevice,
@@ -982,6 +990,12 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
     const unsigned cgrid = (unsigned)std::min<uint64_t>(((uint64_t)pl.S * pl.W + 255) / 256, (uint64_t)ctx->num_sms * 16u);
     k_dense_cover<<<cgrid, 256, 0, bstream(b)>>>(planes, pl.S, pl.W, b->d_x, mode);
     ctx->launches += 2;
+    if (pl.four) {
+      // the "other" cells need the lists and the transposed planes only: counted on a second stream while the
+      // tensor cores run (a 25 KB, 384-thread CTA fits on an SM next to k_gram_i8's); joined below, before the
+      // next unit's k_dense_prep reuses the lists and before anything reads the tables
+      CU(ctx, cudaEventRecord(b->fix_fork, bstream(b)));
+    }
     const bool last = &pl == &b->dense_plans.back();
     if (last && timing) CU(ctx, cudaEventRecord(b->ev[6], bstream(b)));
     for (int form = pl.four ? 0 : 1; form < 2; ++form) {  // the launch of the form the unit is not in returns at once
@@ -1005,10 +1019,13 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
       ++ctx->launches;
     }
     if (last && timing) CU(ctx, cudaEventRecord(b->ev[7], bstream(b)));
-    if (pl.four) {
-      k_other_fix<<<pl.S, 256, 0, bstream(b)>>>(b->d_xt, K_pad, pl.S, pl.S_pad, b->d_oth_cnt, b->d_oth_list, pl.oth_cap,
-                                               b->d_gram + pl.gram_off, mode);
+    if (pl.four) {  // (issued after k_gram_i8: its one CTA per SM goes first, the fix-up's CTAs fill in beside them)
+      CU(ctx, cudaStreamWaitEvent(b->fix_stream, b->fix_fork, 0));
+      k_other_fix<<<pl.S, kFixThreads, 0, b->fix_stream>>>(b->d_xt, K_pad, pl.S, pl.S_pad, b->d_oth_cnt, b->d_oth_list, pl.oth_cap,
+                                                        b->d_gram + pl.gram_off, mode);
       ++ctx->launches;
+      CU(ctx, cudaEventRecord(b->fix_join, b->fix_stream));
+      CU(ctx, cudaStreamWaitEvent(bstream(b), b->fix_join, 0));
     }
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[5], bstream(b)));

@@ -100,8 +100,8 @@ __device__ __forceinline__ void store_bytes32(uint8_t* __restrict__ dst, uint32_
 }
 
 // One pass over the planes.  CTA = 256 sites (a warp per group of 32, a lane per site) x 256 reads (8 words):
-// every lane reads whole 32-byte sectors of its site's rows and writes its 256 bytes of the X row groups
-// 1 (major or minor) and 2 (major): X[g][s][r].  For the four-block form -- unless the run was told "nine
+// every lane reads whole 32-byte sectors of its site's rows; the words of the X row groups 1 (major or minor)
+// and 2 (major) pass through shared memory so that a warp stores 256 contiguous bytes of X[g][s][r] at a time.  For the four-block form -- unless the run was told "nine
 // blocks" up front (*mode != 0 at the start) -- it also lists the site's reads with label "other" (any order;
 // a list that overflows sets *mode: nine blocks) and transposes the label words O, m, M in registers (5 shuffle
 // steps per 32 x 32 block); those leave through a shared-memory tile as whole sectors of
@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(256) k_dense_prep(const uint32_t* __restrict__
                                                     uint32_t* __restrict__ cnt, uint32_t* __restrict__ list, uint32_t cap,
                                                     uint32_t* __restrict__ mode) {
   __shared__ __align__(16) uint32_t tile[3][256][8];  // [label][read of the block][site group of the block]
+  __shared__ uint32_t raw[2][256][9];                 // [row group P, M][site of the block][word] (+1: no bank conflicts)
   __shared__ uint32_t s_nine;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   // one read per CTA: another CTA of this launch may set the flag meanwhile (the four-block outputs are not used then)
@@ -162,19 +163,29 @@ __global__ void __launch_bounds__(256) k_dense_prep(const uint32_t* __restrict__
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const uint32_t L2 = Mw[k] & Cw[k], L1 = mw[k] & Cw[k] & ~Mw[k], L0 = Cw[k] & ~Mw[k] & ~mw[k];
-    if (s < S && (k < 4 || second)) {
-      uint8_t* x = X + ((size_t)S_pad + s) * K_pad + (size_t)(w0 + k) * 32u;
-      store_bytes32(x, L1 | L2);
-      store_bytes32(x + (size_t)S_pad * K_pad, L2);
-    }
+    raw[0][warp * 32u + lane][k] = L1 | L2;
+    raw[1][warp * 32u + lane][k] = L2;
     if (!nine) {  // (CTA-uniform)
       tile[0][k * 32 + lane][warp] = transpose32(L0, lane);
       tile[1][k * 32 + lane][warp] = transpose32(L1, lane);
       tile[2][k * 32 + lane][warp] = transpose32(L2, lane);
     }
   }
-  if (nine) return;
   __syncthreads();
+  // X: a warp writes the 256 contiguous bytes of one (row group, site) at a time -- lane = 8 reads
+  {
+    const uint32_t k = lane >> 2, q4 = lane & 3u;
+    if (k < 4u || second) {
+      for (uint32_t e = warp; e < 512u; e += 8u) {
+        const uint32_t sl = e >> 1, g = e & 1u, site = sg0 * 32u + sl;
+        if (site >= S) break;
+        const uint32_t bits = (raw[g][sl][k] >> (8u * q4)) & 0xffu;
+        *reinterpret_cast<uint2*>(X + ((size_t)(g + 1u) * S_pad + site) * K_pad + (size_t)(w0 + k) * 32u + q4 * 8u) =
+            make_uint2(spread4(bits & 15u), spread4(bits >> 4));
+      }
+    }
+  }
+  if (nine) return;
   const uint32_t n_reads = second ? 256u : 128u;
   for (uint32_t e = tid; e < 3u * n_reads * 2u; e += 256u) {
     const uint32_t half = e & 1u, r = (e >> 1) % n_reads, b = (e >> 1) / n_reads;
@@ -195,109 +206,98 @@ __global__ void __launch_bounds__(256) k_dense_cover(const uint32_t* __restrict_
 }
 
 // The table cells with an "other" label, four-block form.  One CTA per site s: for every listed read r of s and
-// every partner t, xt[b][r] says whether t carries label b at r; the bit rows are added up in packed 4-bit
-// counters (15 reads), those in packed bytes (255 reads), those in shared memory.  Written where gram_table
-// reads them: slot 0 / 1 / 2 of pair (s, t), t > s, = reads "other" at s and other / minor / major at t;
-// slot 3 / 6 of pair (t, s), t < s, = reads minor / major at t and "other" at s.
-__global__ void __launch_bounds__(256) k_other_fix(const uint32_t* __restrict__ xt, uint64_t K_pad, uint32_t S,
-                                                   uint32_t S_pad, const uint32_t* __restrict__ cnt,
-                                                   const uint32_t* __restrict__ list, uint32_t cap,
-                                                   uint32_t* __restrict__ gram, const uint32_t* __restrict__ mode) {
+// every partner t, xt[b][r] says whether t carries label b at r.  A warp owns one label, one half of a pass of
+// 64 site words and every other listed read; the bit rows of seven reads are requested together (L2 hits), folded
+// by a carry-save tree into three words (ones, twos, fours), added into packed 4-bit counters (two such groups),
+// those into packed bytes (252 reads), those into shared memory.  Written where gram_table reads them: slot
+// 0 / 1 / 2 of pair (s, t), t > s, = reads "other" at s and other / minor / major at t; slot 3 / 6 of pair
+// (t, s), t < s, = reads minor / major at t and "other" at s.
+constexpr int kFixThreads = 384;  // 12 warps = 3 labels x 2 word halves x 2 read halves
+constexpr uint32_t kFixStride = 65u;  // words of shared memory per partner bit: (bit, word) and (word, bit) walks both hit 32 banks
+
+__device__ __forceinline__ uint32_t fix_spread(uint32_t x, uint32_t q) { return (x >> q) & 0x11111111u; }
+
+__global__ void __launch_bounds__(kFixThreads, 3) k_other_fix(const uint32_t* __restrict__ xt, uint64_t K_pad, uint32_t S,
+                                                           uint32_t S_pad, const uint32_t* __restrict__ cnt,
+                                                           const uint32_t* __restrict__ list, uint32_t cap,
+                                                           uint32_t* __restrict__ gram, const uint32_t* __restrict__ mode) {
   if (*mode) return;
-  __shared__ uint32_t acc[3][2048];
+  __shared__ uint32_t acc[3][32u * kFixStride];  // [label][partner bit * 65 + site word of the pass]
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t half = warp & 1u, quarter = warp >> 1;  // word half of a 64-word pass; every fourth listed read
+  const uint32_t label = warp % 3u, half = (warp / 3u) & 1u, parity = warp / 6u;
   const uint32_t s = blockIdx.x, Sw = S_pad >> 5;
   const uint32_t n = min(cnt[s], cap);
   const uint32_t* __restrict__ mine = list + (size_t)s * cap;
   const size_t plane = (size_t)S_pad * S_pad;
+  const uint32_t n_mine = n > parity ? (n - parity + 1u) / 2u : 0u;  // this warp's listed reads: k = parity + 2 m
   for (uint32_t w0 = 0; w0 < Sw; w0 += 64u) {
-    for (uint32_t e = tid; e < 3u * 2048u; e += 256u) (&acc[0][0])[e] = 0u;
+    for (uint32_t e = tid; e < 3u * 32u * kFixStride; e += kFixThreads) (&acc[0][0])[e] = 0u;
     __syncthreads();
-    const uint32_t word = w0 + half * 32u + lane;
+    const uint32_t wl = half * 32u + lane, word = w0 + wl;
     const bool valid = word < Sw;
-    uint32_t nb[3][4], by[3][8];
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) nb[b][q] = 0u;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) by[b][c] = 0u;
-    }
-    auto nib_to_bytes = [&]() {
-#pragma unroll
-      for (int b = 0; b < 3; ++b)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          by[b][q] += nb[b][q] & 0x0f0f0f0fu;             // byte k <- partner bit 8 k + q
-          by[b][4 + q] += (nb[b][q] >> 4) & 0x0f0f0f0fu;  // byte k <- partner bit 8 k + 4 + q
-          nb[b][q] = 0u;
-        }
-    };
+    const uint32_t* __restrict__ col = xt + (size_t)label * K_pad * Sw + (valid ? word : 0u);
+    uint32_t nb[4] = {0u, 0u, 0u, 0u}, by[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     auto bytes_to_smem = [&]() {
 #pragma unroll
-      for (int b = 0; b < 3; ++b)
+      for (int c = 0; c < 8; ++c) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t v = (by[b][c] >> (8 * k)) & 0xffu;
-            if (v) atomicAdd(&acc[b][(half * 32u + lane) * 32u + 8u * k + c], v);
-          }
-          by[b][c] = 0u;
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t v = (by[c] >> (8 * k)) & 0xffu;
+          if (v) atomicAdd(&acc[label][(8u * k + c) * kFixStride + wl], v);
         }
+        by[c] = 0u;
+      }
     };
-    uint32_t in_nib = 0, in_byte = 0;
-    // this warp's listed reads are k = quarter + 4 m: fetched 32 at a time (one per lane), and the bit rows of
-    // eight reads are requested before the first is added (the loads are L2 hits ~600 cycles away)
-    const uint32_t n_mine = n > quarter ? (n - quarter + 3u) / 4u : 0u;
-    for (uint32_t m0 = 0; m0 < n_mine; m0 += 32u) {
-      const uint32_t have = min(32u, n_mine - m0);
-      const uint32_t my = lane < have ? __ldg(mine + quarter + 4u * (m0 + lane)) : 0u;
-      for (uint32_t q0 = 0; q0 < have; q0 += 8u) {
-        uint32_t x[8][3];
+    uint32_t groups = 0;
+    for (uint32_t m0 = 0; m0 < n_mine; m0 += 28u) {
+      const uint32_t have = min(28u, n_mine - m0);
+      const uint32_t my = lane < have ? __ldg(mine + parity + 2u * (m0 + lane)) : 0u;  // the next 28 reads, one per lane
+      for (uint32_t q0 = 0; q0 < have; q0 += 14u) {
+        uint32_t x[14];  // two groups of seven: fourteen bit rows requested before the first is used
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 14; ++u) {
           const uint32_t r = __shfl_sync(0xffffffffu, my, (q0 + (uint32_t)u) & 31u);
-          const bool ok = valid && q0 + (uint32_t)u < have;
-#pragma unroll
-          for (int b = 0; b < 3; ++b) x[u][b] = ok ? __ldg(xt + ((size_t)b * K_pad + r) * Sw + word) : 0u;
+          x[u] = (valid && q0 + (uint32_t)u < have) ? __ldg(col + (size_t)r * Sw) : 0u;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t* y = x + 7 * h;
+          // seven one-bit rows -> ones + 2 twos + 4 fours
+          const uint32_t a1 = y[0] ^ y[1] ^ y[2], c1 = (y[0] & y[1]) | (y[2] & (y[0] ^ y[1]));
+          const uint32_t a2 = y[3] ^ y[4] ^ y[5], c2 = (y[3] & y[4]) | (y[5] & (y[3] ^ y[4]));
+          const uint32_t ones = a1 ^ a2 ^ y[6], c3 = (a1 & a2) | (y[6] & (a1 ^ a2));
+          const uint32_t twos = c1 ^ c2 ^ c3, fours = (c1 & c2) | (c3 & (c1 ^ c2));
 #pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            nb[b][0] += x[u][b] & 0x11111111u;
-            nb[b][1] += (x[u][b] >> 1) & 0x11111111u;
-            nb[b][2] += (x[u][b] >> 2) & 0x11111111u;
-            nb[b][3] += (x[u][b] >> 3) & 0x11111111u;
-          }
-          if (++in_nib == 15u) {
-            nib_to_bytes();
-            in_nib = 0;
-            if (++in_byte == 17u) {  // 17 * 15 = 255
-              bytes_to_smem();
-              in_byte = 0;
-            }
-          }
+          for (uint32_t q = 0; q < 4u; ++q)
+            nb[q] += fix_spread(ones, q) + 2u * fix_spread(twos, q) + 4u * fix_spread(fours, q);  // <= 7 per group
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {           // two groups: a nibble holds at most 14
+          by[q] += nb[q] & 0x0f0f0f0fu;         // byte k <- partner bit 8 k + q
+          by[4 + q] += (nb[q] >> 4) & 0x0f0f0f0fu;  // byte k <- partner bit 8 k + 4 + q
+          nb[q] = 0u;
+        }
+        if (++groups == 18u) {  // 18 x 14 = 252 per byte
+          bytes_to_smem();
+          groups = 0;
         }
       }
     }
-    nib_to_bytes();
     bytes_to_smem();
     __syncthreads();
-    for (uint32_t tl = tid; tl < 2048u; tl += 256u) {
+    for (uint32_t tl = tid; tl < 2048u; tl += kFixThreads) {
       const uint32_t t = w0 * 32u + tl;
       if (t >= S) break;
+      const uint32_t at = (tl & 31u) * kFixStride + (tl >> 5);
       if (t > s) {
         uint32_t* out = gram + (size_t)s * S_pad + t;
-        out[0] = acc[0][tl];
-        out[plane] = acc[1][tl];
-        out[2u * plane] = acc[2][tl];
+        out[0] = acc[0][at];
+        out[plane] = acc[1][at];
+        out[2u * plane] = acc[2][at];
       } else if (t < s) {
         uint32_t* out = gram + (size_t)t * S_pad + s;
-        out[3u * plane] = acc[1][tl];
-        out[6u * plane] = acc[2][tl];
+        out[3u * plane] = acc[1][at];
+        out[6u * plane] = acc[2][at];
       }
     }
     __syncthreads();

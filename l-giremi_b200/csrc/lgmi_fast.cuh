@@ -41,6 +41,9 @@ constexpr int kFastMaxPairs = 2048;  // >= 64*63/2 = 2016, whole 32-pair chunks
 constexpr int kFastChunks = kFastMaxPairs / 32;
 constexpr int kRowStride = 28;       // words per landed site row: M[8] | P[8] | C[8] | pad[4]
 constexpr int kOthCap = 7;           // "other" reads kept per site (3-bit cells); more -> generic kernel
+constexpr uint32_t kFastMathMaxCount = (1u << 21) - 1u;  // the reorganised epilogues below are host-tested bit for bit
+                                     // against lgmi_math.cuh for table counts up to here (tests/test_fast_host.py);
+                                     // units with more reads keep the straightforward arithmetic
 
 // ln k as hi + lo (hi = RN(ln k)); entry 0 is {0, 0}
 struct __align__(16) FastLn {

@@ -366,6 +366,15 @@ __device__ __forceinline__ void fast_emit_counts(const FastParams& P, SM& sm, co
 // |s| >= |x| is s >= x).  Het sites sum over every partner, the others over the
 // het sites only.  Threads [0, n_het) take the het sites (the long chains share
 // warps), the next S - n_het threads the other sites.
+// The rounding error of t = RN(s + x), exactly (Knuth's two-sum: six additions, no comparison).  CPython's
+// compensated sum adds (s - t) + x when |s| >= |x| and (x - t) + s otherwise (Dekker's fast two-sum with the
+// operands ordered): either way that IS the exact error of the addition, which is a double, so the three forms
+// give the same bits -- and this one needs no select on the serial path.
+__device__ __forceinline__ double two_sum_err(double s, double x, double t) {
+  const double bp = __dsub_rn(t, s);
+  return __dadd_rn(__dsub_rn(s, __dsub_rn(t, bp)), __dsub_rn(x, bp));
+}
+
 struct MeanAcc {
   double s, c;
   uint32_t n;
@@ -376,8 +385,7 @@ struct MeanAcc {
     const bool have = __double2hiint(v) < 0x7ff00000;
     const double x = have ? v : 0.0;
     const double t = __dadd_rn(s, x);
-    const double big = (s >= x) ? s : x, small = (s >= x) ? x : s;
-    c = __dadd_rn(c, __dadd_rn(__dsub_rn(big, t), small));
+    c = __dadd_rn(c, two_sum_err(s, x, t));
     s = t;
     n += have ? 1u : 0u;
   }

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, kKind == 1 ? 4 : (kKind == 2 ? 3 : 2
       const uint32_t n2 = s_n2, n3 = s_n3;
       const uint32_t nc2 = (n2 + 31u) >> 5, nc3 = (n3 + 31u) >> 5;
       const GlobalTab tab{P.lntab};
-      const bool small_counts = u.R <= 65535u;  // the reorganised epilogues are checked for counts below 2^16
+      const bool small_counts = u.R <= kFastMathMaxCount;  // (else the straightforward arithmetic of lgmi_math.cuh)
       for (uint32_t c = warp; c < nc2 + nc3; c += kThreads / 32) {
         if (c < nc2) {
           const uint32_t q = c * 32u + lane;
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(kThreads) k_count(const RunParams P) {
 // serial; the 32 sites of a block are not.
 constexpr int kMeanSites = 32;    // sites per CTA (= lanes of the consuming warp)
 constexpr int kMeanThreads = 256;
-constexpr int kMeanBufs = 4;      // tiles in flight
+constexpr int kMeanBufs = 5;      // tile buffers: one being summed, one being masked, three in flight
 struct MeanItem {
   uint32_t unit;
   uint32_t site_begin;
@@ -797,9 +797,9 @@ __global__ void __launch_bounds__(kMeanThreads) k_site_mean_dense(const DevUnit*
 
   // a tile by cp.async (nobody waits on its own loads): partners t0 .. t0 + 31 against sites s0 .. s0 + 31
   auto request_tile = [&](uint32_t tb) {
-    if (tb < n_blocks) {
+    if (tb < n_blocks && warp != 0u) {
       const uint32_t t0 = tb << 5, b = tb % kMeanBufs;
-      for (uint32_t e = tid; e < 1024u; e += kMeanThreads) {
+      for (uint32_t e = tid - 32u; e < 1024u; e += kMeanThreads - 32u) {  // (warps 1-7: warp 0 only sums)
         // below the diagonal block the fast index runs over the sites (row of the partner), above it over
         // the partners (row of the site); inside it either way
         const uint32_t hi = e >> 5, lo = e & 31u;
@@ -818,46 +818,54 @@ __global__ void __launch_bounds__(kMeanThreads) k_site_mean_dense(const DevUnit*
     cp_async_commit();  // (an empty group keeps the count of groups per tile at one)
   };
 
-  const uint32_t s = s0 + lane;  // (256 = 8 x 32 threads: a thread's entries of a tile all belong to site s0 + lane)
+  const uint32_t s = s0 + lane;  // (a thread's entries of a tile all belong to site s0 + lane)
   const bool s_ok = s < S;
   const bool s_het = s_ok && (flags[s_ok ? s : 0u] & LGMI_SITE_TYPE_MASK) == LGMI_SITE_HET_SNP;
   // all MI values are >= +0.0: CPython's compensated sum (mutual_information.py:56-58) without branches;
   // an absent value adds +0.0, which leaves sum and compensation as they are.  Per tile: every thread first
   // replaces the entries that do not count (no MI, the site itself, neither site a het_snp) by +0.0 and counts
   // the others; warp 0 then runs the 32 serial sums over plain values -- two dependent fp64 additions per step
-  // (sum, compensation) with everything else off the critical path.
+  // (sum, compensation); the rounding error of each addition comes from the branch-free two_sum_err.
   double acc_s = 0.0, acc_c = 0.0;
   uint32_t my_n = 0;
   __shared__ uint32_t s_n[32];
   if (tid < 32u) s_n[tid] = 0u;
-#pragma unroll
-  for (uint32_t tb = 0; tb + 1u < (uint32_t)kMeanBufs; ++tb) request_tile(tb);
-  for (uint32_t tb = 0; tb < n_blocks; ++tb) {
-    request_tile(tb + kMeanBufs - 1u);   // into the buffer everybody left at the end of the previous iteration
-    cp_async_wait<kMeanBufs - 1>();      // tile tb has landed (this thread's part; the barrier covers the rest)
-    __syncthreads();
+  auto mask_tile = [&](uint32_t tb) {  // warps 1-7: entries (partner warp - 1 + 7 q, site s0 + lane) of tile tb
+    if (tb >= n_blocks || warp == 0u) return;
     const uint32_t b = tb % kMeanBufs, t0 = tb << 5;
     const uint32_t partners = s_het ? 0xffffffffu : s_phet[b];  // a non-het site sums over its het partners only
 #pragma unroll
-    for (uint32_t q = 0; q < 4u; ++q) {
-      const uint32_t tl = warp + 8u * q, t = t0 + tl;
+    for (uint32_t q = 0; q < 5u; ++q) {
+      const uint32_t tl = warp - 1u + 7u * q, t = t0 + tl;
+      if (tl >= 32u) break;
       const double v = s_tile[b][tl][lane];
       const bool have = s_ok && t < S && t != s && ((partners >> tl) & 1u) && __double2hiint(v) < 0x7ff00000;  // NaN: no MI
       s_tile[b][tl][lane] = have ? v : 0.0;
       my_n += have ? 1u : 0u;
     }
-    __syncthreads();
-    if (warp == 0) {                     // one site per lane, partners ascending
+  };
+  // one barrier per tile: while warp 0 sums tile tb, warps 1-7 mask tile tb + 1 and request
+  // tile tb + kMeanBufs - 1 into the buffer of tile tb - 1
+#pragma unroll
+  for (uint32_t tb = 0; tb + 1u < (uint32_t)kMeanBufs; ++tb) request_tile(tb);
+  cp_async_wait<kMeanBufs - 2>();  // tile 0 has landed (this thread's part; the barrier covers the rest)
+  __syncthreads();
+  mask_tile(0u);
+  for (uint32_t tb = 0; tb < n_blocks; ++tb) {
+    cp_async_wait<kMeanBufs - 3>();  // tile tb + 1
+    __syncthreads();                 // ... everybody's part of it; tile tb is masked; tile tb - 1 is summed
+    request_tile(tb + kMeanBufs - 1u);
+    mask_tile(tb + 1u);
+    if (warp == 0) {                 // one site per lane, partners ascending
+      const uint32_t b = tb % kMeanBufs;
 #pragma unroll 8
       for (uint32_t tl = 0; tl < 32u; ++tl) {
         const double x = s_tile[b][tl][lane];
         const double tt = __dadd_rn(acc_s, x);
-        const double big = fmax(acc_s, x), small = fmin(acc_s, x);
-        acc_c = __dadd_rn(acc_c, __dadd_rn(__dsub_rn(big, tt), small));
+        acc_c = __dadd_rn(acc_c, two_sum_err(acc_s, x, tt));
         acc_s = tt;
       }
     }
-    __syncthreads();  // tile tb consumed: its buffer is the target of the next request
   }
   cp_async_wait<0>();
   if (my_n) atomicAdd(&s_n[lane], my_n);

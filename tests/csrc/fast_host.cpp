@@ -63,6 +63,23 @@ void g_mi_3x3_many(const uint32_t* T, int64_t m, const double* lntab, double* ou
   const GlobalTab t{reinterpret_cast<const lg_dd*>(lntab)};
   for (int64_t k = 0; k < m; ++k) out[k] = mi_3x3(t, T + 9 * k);
 }
+// the same for `samples` random (n, N), N < 2^31 (deep units: counts far beyond the exhaustive range)
+int64_t f_markstein_large_mismatches(int64_t samples, uint64_t seed) {
+  int64_t bad = 0;
+  uint64_t x = seed * 0x9e3779b97f4a7c15ull + 1;
+  for (int64_t k = 0; k < samples; ++k) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    const uint32_t N = (uint32_t)(x >> 33) | 1u;
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    const uint32_t n = (uint32_t)((x >> 11) % ((uint64_t)N + 1));
+    const double dN = (double)N, y = 1.0 / dN, dn = (double)n;
+    const double q0 = dn * y;
+    const double r = std::fma(-q0, dN, dn);
+    const double q = std::fma(r, y, q0);
+    bad += (q != dn / dN);
+  }
+  return bad;
+}
 // number of (n, N) with 0 <= n <= N <= n_max where the Markstein quotient differs from n / N
 int64_t f_markstein_mismatches(uint32_t n_max) {
   int64_t bad = 0;

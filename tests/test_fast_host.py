@@ -154,3 +154,67 @@ def test_global_table_epilogues_same_bits_for_large_counts(fast_host, math_host,
         assert one[0] == unhex(case["mi"]), case
         n += 1
     assert n > 2000
+
+
+def test_global_table_epilogues_same_bits_up_to_two_million_reads(fast_host, math_host):
+    """The deep-unit pair kernel (k_pairs_generic<2>) runs the reorganised epilogues for units of up to
+    kFastMathMaxCount = 2^21 - 1 reads (cfg3: 100 000): same bits as the straightforward arithmetic on tables with
+    counts of that size -- the Markstein quotient is the rounded quotient for any integers below 2^32, the logs
+    come from the same double-double table."""
+    n = 1 << 21
+    big = np.empty(2 * n, dtype=np.float64)
+    math_host.t_build_lntab(big.ctypes.data, 0, n)
+    rng = np.random.default_rng(10)
+    tabs = []
+    for _ in range(20000):
+        scale = int(rng.choice([20000, 100000, 230000]))
+        t = rng.integers(0, scale, 9)
+        if rng.random() < 0.7:                                       # "other" cells stay small
+            t[[0, 1, 2, 3, 6]] = rng.integers(0, int(rng.choice([2, 30, 800])), 5)
+        t[rng.random(9) < rng.choice([0.0, 0.3, 0.6])] = 0
+        if 0 < t.sum() < n:
+            tabs.append(t)
+    tabs.append(np.array([0, 0, 0, 0, n - 1, 0, 0, 0, 0]))
+    tabs.append(np.array([1, 0, 3, 0, 700000, 2, 5, 1, 1300000]))
+    tabs = u32(np.array(tabs))
+    out = np.empty(len(tabs))
+    fast_host.g_mi_3x3_many(tabs.ctypes.data, len(tabs), big.ctypes.data, out.ctypes.data)
+    for t, got in zip(tabs, out.tolist()):
+        assert got == math_host.t_mi_from_table(t.ctypes.data, big.ctypes.data), t
+    two = tabs[~tabs[:, [0, 1, 2, 3, 6]].any(axis=1)]
+    cells = u32(two[:, [4, 5, 7, 8]])
+    out2 = np.empty(len(cells))
+    fast_host.g_mi_2x2_many(cells.ctypes.data, len(cells), big.ctypes.data, out2.ctypes.data)
+    for c, got in zip(cells.tolist(), out2.tolist()):
+        assert got == math_host.t_mi_from_2x2(c[0], c[1], c[2], c[3], big.ctypes.data), c
+    assert len(cells) > 100 and len(tabs) > 15000
+    assert fast_host.f_markstein_large_mismatches(200000, 11) == 0
+
+
+def test_two_sum_error_equals_cpython_compensation_term():
+    """csrc/lgmi_fast_kernel.cuh two_sum_err: the branch-free six-addition error of RN(s + x) is, bit for bit, the term
+    CPython's compensated float sum adds -- (s - t) + x when |s| >= |x|, (x - t) + s otherwise (Python/bltinmodule.c
+    cs_add, what mutual_information.py:56-58 runs) -- over magnitudes from denormal-ish MI noise to large sums."""
+    rng = np.random.default_rng(12)
+    n = 400000
+    s = np.abs(rng.standard_normal(n)) * 10.0 ** rng.integers(-18, 6, n)
+    x = np.abs(rng.standard_normal(n)) * 10.0 ** rng.integers(-18, 6, n)
+    s[::7] = 0.0
+    x[::11] = 0.0
+    x[::13] = s[::13]
+    t = s + x
+    big, small = np.where(s >= x, s, x), np.where(s >= x, x, s)
+    want = (big - t) + small
+    bp = t - s
+    got = (s - (t - bp)) + (x - bp)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    # and a whole sum: same (s, c) sequence as math.fsum-free CPython sum() of non-negative values
+    vals = (np.abs(rng.standard_normal(3000)) * 10.0 ** rng.integers(-12, 1, 3000)).tolist()
+    acc_s = acc_c = 0.0
+    for v in vals:
+        tt = acc_s + v
+        b = tt - acc_s
+        acc_c += (acc_s - (tt - b)) + (v - b)
+        acc_s = tt
+    total = acc_s + acc_c if acc_c != 0.0 else acc_s
+    assert total == sum(vals)
