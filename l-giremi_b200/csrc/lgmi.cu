@@ -598,7 +598,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       pl.k_blocks = u.row_words * 32u / (uint32_t)kDenseBK;  // W is a multiple of 4: whole 128-read blocks
       pl.plane_off = u.plane_off;
       pl.gram_off = gram_words;
-      pl.four = ctx->dense_path == 4;
+      // (k_other_fix addresses a label's transposed plane with 32-bit word offsets)
+      pl.four = ctx->dense_path == 4 && (uint64_t)pl.k_blocks * kDenseBK * (pl.S_pad / 32u) < (1ull << 32);
       pl.oth_cap = std::max<uint32_t>(kDenseOthMin, u.n_reads / kDenseOthDiv);
       auto build_list = [&](DenseTileList& L, uint32_t g0) {  // row groups g0 .. 2 of X against each other
         L.off = dense_tiles.size();

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kFixThreads, 3) k_other_fix(const uint32_t* __
     __syncthreads();
     const uint32_t wl = half * 32u + lane, word = w0 + wl;
     const bool valid = word < Sw;
-    const uint32_t* __restrict__ col = xt + (size_t)label * K_pad * Sw + (valid ? word : 0u);
+    const uint32_t* __restrict__ col = xt + (size_t)label * K_pad * Sw + (valid ? word : 0u);  // (an invalid lane's sums go nowhere)
     uint32_t nb[4] = {0u, 0u, 0u, 0u}, by[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     auto bytes_to_smem = [&]() {
 #pragma unroll
@@ -251,13 +251,19 @@ __global__ void __launch_bounds__(kFixThreads, 3) k_other_fix(const uint32_t* __
     uint32_t groups = 0;
     for (uint32_t m0 = 0; m0 < n_mine; m0 += 28u) {
       const uint32_t have = min(28u, n_mine - m0);
-      const uint32_t my = lane < have ? __ldg(mine + parity + 2u * (m0 + lane)) : 0u;  // the next 28 reads, one per lane
+      // the next 28 reads, one per lane, as word offsets of their bit rows (K_pad * Sw < 2^32: checked by the host)
+      const uint32_t my = lane < have ? __ldg(mine + parity + 2u * (m0 + lane)) * Sw : 0u;
       for (uint32_t q0 = 0; q0 < have; q0 += 14u) {
         uint32_t x[14];  // two groups of seven: fourteen bit rows requested before the first is used
 #pragma unroll
-        for (int u = 0; u < 14; ++u) {
-          const uint32_t r = __shfl_sync(0xffffffffu, my, (q0 + (uint32_t)u) & 31u);
-          x[u] = (valid && q0 + (uint32_t)u < have) ? __ldg(col + (size_t)r * Sw) : 0u;
+        for (int u = 0; u < 14; ++u) {  // (rows past the warp's last listed read: row 0, masked out below)
+          const uint32_t off = __shfl_sync(0xffffffffu, my, (q0 + (uint32_t)u) & 31u);
+          x[u] = __ldg(col + off);
+        }
+        if (q0 + 14u > have) {  // (warp-uniform) the last, partial round
+#pragma unroll
+          for (int u = 0; u < 14; ++u)
+            if (q0 + (uint32_t)u >= have) x[u] = 0u;
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {

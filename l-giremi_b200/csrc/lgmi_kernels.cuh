@@ -797,17 +797,33 @@ __global__ void __launch_bounds__(kMeanThreads) k_site_mean_dense(const DevUnit*
 
   // a tile by cp.async (nobody waits on its own loads): partners t0 .. t0 + 31 against sites s0 .. s0 + 31
   auto request_tile = [&](uint32_t tb) {
-    if (tb < n_blocks && warp != 0u) {
+    if (tb < n_blocks && warp != 0u) {  // (warps 1-7: warp 0 only sums)
       const uint32_t t0 = tb << 5, b = tb % kMeanBufs;
-      for (uint32_t e = tid - 32u; e < 1024u; e += kMeanThreads - 32u) {  // (warps 1-7: warp 0 only sums)
-        // below the diagonal block the fast index runs over the sites (row of the partner), above it over
-        // the partners (row of the site); inside it either way
-        const uint32_t hi = e >> 5, lo = e & 31u;
-        const uint32_t tl = (t0 < s0) ? hi : lo, sl = (t0 < s0) ? lo : hi;
-        const uint32_t t = t0 + tl, s = s0 + sl;
-        const bool ok = t < S && s < S && t != s;
-        const uint64_t idx = ok ? ((t < s) ? lg_row_off(t, S) + (s - t - 1u) : lg_row_off(s, S) + (t - s - 1u)) : 0ull;
-        cp_async8(&s_tile[b][tl][sl], d + idx, ok);
+      if (t0 + 32u <= s0) {
+        // partners below the site block: a warp copies 32 consecutive entries of one partner's row per step
+        const uint32_t s_ = s0 + lane;
+        for (uint32_t tl = warp - 1u; tl < 32u; tl += 7u) {
+          const uint32_t t = t0 + tl;  // (t < s0 <= s_: a pair, t a real site)
+          const bool ok = s_ < S;
+          cp_async8(&s_tile[b][tl][lane], d + (ok ? lg_row_off(t, S) + (s_ - t - 1u) : 0ull), ok);
+        }
+      } else if (t0 >= s0 + 32u) {
+        // partners above it: 32 consecutive entries of one site's row per step
+        const uint32_t t = t0 + lane;
+        for (uint32_t sl = warp - 1u; sl < 32u; sl += 7u) {
+          const uint32_t s_ = s0 + sl;  // (s_ < t)
+          const bool ok = t < S && s_ < S;
+          cp_async8(&s_tile[b][lane][sl], d + (ok ? lg_row_off(s_, S) + (t - s_ - 1u) : 0ull), ok);
+        }
+      } else {
+        // the diagonal block: either side of each site
+        for (uint32_t e = tid - 32u; e < 1024u; e += kMeanThreads - 32u) {
+          const uint32_t tl = e >> 5, sl = e & 31u;
+          const uint32_t t = t0 + tl, s_ = s0 + sl;
+          const bool ok = t < S && s_ < S && t != s_;
+          const uint64_t idx = ok ? ((t < s_) ? lg_row_off(t, S) + (s_ - t - 1u) : lg_row_off(s_, S) + (t - s_ - 1u)) : 0ull;
+          cp_async8(&s_tile[b][tl][sl], d + idx, ok);
+        }
       }
       if (warp == 1u) {
         const uint32_t t = t0 + lane;
