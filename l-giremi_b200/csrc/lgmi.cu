@@ -201,6 +201,10 @@ struct lgmi_batch {
   uint32_t* d_xt = nullptr;     // four-block form: transposed label planes of the unit being contracted
   uint32_t* d_oth_cnt = nullptr, *d_oth_list = nullptr;  // ... and its listed "other" reads per site
   uint32_t* d_unit_mode = nullptr;  // per unit: the form of this run (0 four blocks, else nine)
+  // graph replays / pipeline groups: the small units' kernels (k_count_fast before the scan, k_pairs_fast after it) run on
+  // a second stream beside the kernels of the larger units (forked and joined by events inside the captured chain)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t side_ev[4] = {};
   cudaStream_t fix_stream = nullptr;             // k_other_fix runs beside k_gram_i8 (forked after k_dense_prep,
   cudaEvent_t fix_fork = nullptr, fix_join = nullptr;  // joined before the tables are read)
   DenseTile* d_tiles = nullptr;
@@ -513,6 +517,9 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   ctx->dev_pool.release(b->d_oth_cnt);
   ctx->dev_pool.release(b->d_oth_list);
   ctx->dev_pool.release(b->d_unit_mode);
+  if (b->side_stream) cudaStreamDestroy(b->side_stream);
+  for (cudaEvent_t e : b->side_ev)
+    if (e) cudaEventDestroy(e);
   if (b->fix_stream) cudaStreamDestroy(b->fix_stream);
   if (b->fix_fork) cudaEventDestroy(b->fix_fork);
   if (b->fix_join) cudaEventDestroy(b->fix_join);
@@ -694,8 +701,8 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       it.flags = (t == 0 ? ITEM_FIRST : 0u) | (nit == 1 ? ITEM_SINGLE : 0u) | (d.tiled ? ITEM_TILED : 0u) |
                  (d.tiled == 2 ? ITEM_TILED_GRAM : 0u) | (d.gram_off != kNoGram ? ITEM_GRAM : 0u);
       if (d.tiled || d.gram_off != kNoGram) ++b->n_tiled_work_items;  // (not k_pairs_generic<0>'s)
-      if (nit == 1 && np >= 1 && u.n_sites <= (uint32_t)kFastMaxS && u.n_reads <= (uint32_t)kFastMaxR) {
-        it.flags |= ITEM_FAST;
+      if (nit == 1 && np >= 1 && d.gram_off == kNoGram && u.n_sites <= (uint32_t)kFastMaxS && u.n_reads <= (uint32_t)kFastMaxR) {
+        it.flags |= ITEM_FAST;  // (a unit sent to the tensor-core path by a lowered threshold is not also k_pairs_fast's)
         FastItem f;
         f.plane_off = u.plane_off;
         f.site_off = u.site_off;
@@ -750,6 +757,10 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   } while (0)
 
   for (cudaEvent_t& e : b->ev) BCU(cudaEventCreate(&e));
+  if ((b->n_fast || b->n_pre) && (!b->dense_plans.empty() || b->n_tile_items || b->n_gram_tiles)) {
+    BCU(cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : b->side_ev) BCU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   BCU(pool_malloc(ctx, &b->d_units, std::max<size_t>(1, n_units) * sizeof(DevUnit)));
   BCU(pool_malloc(ctx, &b->d_items, std::max<size_t>(1, b->n_items) * sizeof(Item)));
   BCU(pool_malloc(ctx, &b->d_fast_items, std::max<size_t>(1, fast_items.size()) * sizeof(FastItem)));
@@ -977,6 +988,14 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
     ++ctx->launches;
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[4], bstream(b)));
+  // untimed runs (graph captures, pipeline groups) of mixed batches: the small units' kernels on the side stream
+  static const bool fork_ok = !(getenv("LGMI_FORK") && atoi(getenv("LGMI_FORK")) == 0);  // LGMI_FORK=0: one stream
+  const bool forked = !timing && b->side_stream != nullptr && fork_ok;
+  cudaStream_t small = forked ? b->side_stream : bstream(b);
+  if (forked) {
+    CU(ctx, cudaEventRecord(b->side_ev[0], bstream(b)));
+    CU(ctx, cudaStreamWaitEvent(small, b->side_ev[0], 0));
+  }
   if (!b->dense_plans.empty())  // every dense unit starts a run in the four-block form
     CU(ctx, cudaMemsetAsync(b->d_unit_mode, 0, (size_t)b->n_units * sizeof(uint32_t), bstream(b)));
   for (const DensePlan& pl : b->dense_plans) {
@@ -1070,7 +1089,7 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
     G.n_generic = b->d_n_generic;
     G.error = reinterpret_cast<uint32_t*>(&b->d_header->pad);
     const unsigned grid = (unsigned)std::min<uint64_t>(b->n_pre, (uint64_t)ctx->num_sms * 2u);
-    k_small_gram<<<grid, kSgThreads, sizeof(SgSmem) + 1024, bstream(b)>>>(G);
+    k_small_gram<<<grid, kSgThreads, sizeof(SgSmem) + 1024, small>>>(G);
     ++ctx->launches;
   }
   if (b->n_fast) {
@@ -1086,8 +1105,12 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
     C.item_cnt = b->d_item_cnt;
     C.fast_empty = b->d_fast_empty;
     const unsigned grid = (unsigned)std::min<uint64_t>(b->n_fast, (uint64_t)ctx->num_sms * 8u);
-    k_count_fast<<<grid, kThreads, 0, bstream(b)>>>(C);
+    k_count_fast<<<grid, kThreads, 0, small>>>(C);
     ++ctx->launches;
+  }
+  if (forked) {  // the scan needs every item's count
+    CU(ctx, cudaEventRecord(b->side_ev[1], small));
+    CU(ctx, cudaStreamWaitEvent(bstream(b), b->side_ev[1], 0));
   }
   if (b->n_items) {
     // K0 of everything else + scan: every item's place in the ordered output
@@ -1104,6 +1127,10 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
     ++ctx->launches;
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[2], bstream(b)));
+  if (forked) {
+    CU(ctx, cudaEventRecord(b->side_ev[2], bstream(b)));
+    CU(ctx, cudaStreamWaitEvent(small, b->side_ev[2], 0));
+  }
   if (b->n_fast || b->n_pre) {
     FastParams F;
     F.items = b->d_fast_items;
@@ -1132,38 +1159,44 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
       Q.F.n_items = b->n_pre;
       Q.val = b->d_val;
       const unsigned grid = (unsigned)std::min<uint64_t>(b->n_pre, (uint64_t)ctx->num_sms * ctx->pre_ctas_per_sm);
-      k_pairs_pre<<<grid, kFastThreads, sizeof(PreSmem), bstream(b)>>>(Q);
+      k_pairs_pre<<<grid, kFastThreads, sizeof(PreSmem), small>>>(Q);
       ++ctx->launches;
     }
     if (b->n_fast) {
       // persistent CTAs: a whole number of CTAs per SM, never more than there are items
       const unsigned grid = (unsigned)std::min<uint64_t>(b->n_fast, (uint64_t)ctx->num_sms * ctx->pairs_ctas_per_sm);
       if ((mode & (LGMI_MODE_HET_ONLY | LGMI_MODE_SKIP_NONHET)) == (LGMI_MODE_HET_ONLY | LGMI_MODE_SKIP_NONHET))
-        k_pairs_fast_het<<<grid, kFastThreads, sizeof(FastSmem), bstream(b)>>>(F);
+        k_pairs_fast_het<<<grid, kFastThreads, sizeof(FastSmem), small>>>(F);
       else
-        k_pairs_fast<<<grid, kFastThreads, sizeof(FastSmem), bstream(b)>>>(F);
+        k_pairs_fast<<<grid, kFastThreads, sizeof(FastSmem), small>>>(F);
       ++ctx->launches;
     }
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[3], bstream(b)));
+  if (forked) CU(ctx, cudaEventRecord(b->side_ev[3], small));
   if (b->n_items) {
-    // everything the small-unit kernel does not take; exits at once when there is nothing
+    // everything the small-unit kernel does not take
     if (b->n_tile_items || b->n_gram_tiles) {  // ordering + emission of what k_tile_mi / k_tile_finish computed
       const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
       k_pairs_generic<1><<<grid, kThreads, 0, bstream(b)>>>(P);
       ++ctx->launches;
     }
-    const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
     if (!b->dense_plans.empty()) {  // the deep units: tables from the count matrices
       k_pairs_generic<2><<<(unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 3u), kThreads, 0, bstream(b)>>>(P);
       ++ctx->launches;
     }
-    k_pairs_generic<0><<<grid, kThreads, 0, bstream(b)>>>(P);
-    ++ctx->launches;
   }
-  if (b->n_mean_items) {
+  if (b->n_mean_items) {  // (units of several items: none of them is k_pairs_fast's or k_pairs_generic<0>'s)
     k_site_mean_dense<<<b->n_mean_items, kMeanThreads, 0, bstream(b)>>>(b->d_units, b->d_mean_items, b->d_flags, b->d_dense,
                                                                        b->d_site_mean, b->d_site_cnt);
+    ++ctx->launches;
+  }
+  if (forked) CU(ctx, cudaStreamWaitEvent(bstream(b), b->side_ev[3], 0));
+  if (b->n_items) {
+    // small units k_pairs_fast handed on (a site with too many "other" reads) and pair-less units; exits at once
+    // when there is nothing
+    const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
+    k_pairs_generic<0><<<grid, kThreads, 0, bstream(b)>>>(P);
     ++ctx->launches;
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[1], bstream(b)));
