@@ -51,7 +51,7 @@ def test_abi_struct_layouts(lg):
     L = importlib_lib()
     assert L.UNIT_DESC.itemsize == 24 and L.UNIT_DESC.fields["site_off"][1] == 20
     assert L.PAIR_REC.itemsize == 16 and L.PAIR_REC.fields["mi"][1] == 8
-    assert ctypes.sizeof(L.Result) == 128
+    assert ctypes.sizeof(L.Result) == 136
     # ... and the C compiler agrees with the ctypes mirror, field by field
     fields = [f[0] for f in L.Result._fields_]
     prog = '#include <stdio.h>\n#include <stddef.h>\n#include "lgmi.h"\nint main(void){printf("%zu", sizeof(lgmi_result));' + \
