@@ -127,8 +127,8 @@ struct lgmi_ctx {
   int dense_path = 4;  // deep units: 4 = four Gram blocks + sparse "other" cells where the "other" reads are rare (decided on
                        // the device per unit and run), 9 = always nine blocks
   int small_path = 0;  // 0: popcount (k_pairs_fast, default: faster); 1: counted on the tensor cores
-  int tile_path = 1;   // mid-depth units: 0 popcount (k_tile_mi), 1 tensor cores (k_tile_gram, default),
-                       // 2 tensor cores, warp-specialised (k_tile_gram_ws)
+  int tile_path = 2;   // mid-depth units: 0 popcount (k_tile_mi), 1 tensor cores (k_tile_gram),
+                       // 2 tensor cores, warp-specialised (k_tile_gram_ws, default)
   // tensor-core path: units at least this large build their tables with k_gram_i8
   uint32_t dense_min_sites = 48, dense_min_reads = 8192;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)

@@ -150,7 +150,6 @@ __device__ __forceinline__ void fast_counts(const FastParams& P, FastSmem& sm, c
   const bool het_only = (P.mode & LGMI_MODE_HET_ONLY) != 0u;
   const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
   const uint32_t n_slots = (n_pairs + 31u) & ~31u;
-  const uint32_t lt = (1u << lane) - 1u;
   for (uint32_t p = tid; p < n_slots; p += kFastThreads) {
     uint32_t cls = 0u;  // 0 no MI, 2 -> 2x2 list, 3 -> 3x3 list
     bool emit = false;
@@ -173,20 +172,51 @@ __device__ __forceinline__ void fast_counts(const FastParams& P, FastSmem& sm, c
       }
       sm.val[p] = v;
     }
-    // warp-aggregated bookkeeping: this warp's 32 pairs are one lexicographic chunk
+    // this warp's 32 pairs are one lexicographic chunk: three ballots are all the bookkeeping here; the lists
+    // are built from the masks afterwards (fast_build_lists), without atomics
     const uint32_t me = __ballot_sync(0xffffffffu, emit);
     const uint32_t m2 = __ballot_sync(0xffffffffu, cls == 2u);
     const uint32_t m3 = __ballot_sync(0xffffffffu, cls == 3u);
-    uint32_t b2 = 0u, b3 = 0u;
     if (lane == 0) {
       sm.emit_mask[p >> 5] = me;
-      if (m2) b2 = atomicAdd(&sm.n_list2, (uint32_t)__popc(m2));
-      if (m3) b3 = atomicAdd(&sm.n_list3, (uint32_t)__popc(m3));
+      sm.m2_mask[p >> 5] = m2;
+      sm.m3_mask[p >> 5] = m3;
     }
-    b2 = __shfl_sync(0xffffffffu, b2, 0);
-    b3 = __shfl_sync(0xffffffffu, b3, 0);
-    if (cls == 2u) sm.list[b2 + __popc(m2 & lt)] = (uint16_t)p;
-    if (cls == 3u) sm.list[kFastMaxPairs - 1u - (b3 + __popc(m3 & lt))] = (uint16_t)p;
+  }
+}
+
+// The two lists of fast_mi from the chunks' class masks: every warp scans the (at most 64) chunk counts itself --
+// 2x2 and 3x3 counts packed in one word -- and lists the pairs of its own chunks; no atomics, no barrier between
+// scan and fill.  2x2 pairs from the front of sm.list, 3x3 pairs from the back; the lists are in pair order.
+__device__ __forceinline__ void fast_build_lists(FastSmem& sm, uint32_t n_chunks) {
+  static_assert(kFastChunks == 64, "two chunks per lane");
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t lo = 0u, hi = 0u;  // chunks `lane` and `lane + 32`: 2x2 count | 3x3 count << 16
+  if (lane < n_chunks) lo = (uint32_t)__popc(sm.m2_mask[lane]) | ((uint32_t)__popc(sm.m3_mask[lane]) << 16);
+  if (lane + 32u < n_chunks) hi = (uint32_t)__popc(sm.m2_mask[lane + 32u]) | ((uint32_t)__popc(sm.m3_mask[lane + 32u]) << 16);
+  uint32_t ilo = lo, ihi = hi;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t a = __shfl_up_sync(0xffffffffu, ilo, o), b = __shfl_up_sync(0xffffffffu, ihi, o);
+    if ((int)lane >= o) {
+      ilo += a;
+      ihi += b;
+    }
+  }
+  const uint32_t tot_lo = __shfl_sync(0xffffffffu, ilo, 31);
+  ihi += tot_lo;
+  const uint32_t elo = ilo - lo, ehi = ihi - hi;  // exclusive prefixes
+  if (threadIdx.x == 31u) {  // (lane 31 of warp 0 holds the totals)
+    sm.n_list2 = ihi & 0xffffu;
+    sm.n_list3 = ihi >> 16;
+  }
+  for (uint32_t c = warp; c < n_chunks; c += kFastWarps) {
+    const uint32_t off = c < 32u ? __shfl_sync(0xffffffffu, elo, c) : __shfl_sync(0xffffffffu, ehi, c - 32u);
+    const uint32_t m2 = sm.m2_mask[c], m3 = sm.m3_mask[c];
+    const uint32_t p = c * 32u + lane;
+    if ((m2 >> lane) & 1u) sm.list[(off & 0xffffu) + __popc(m2 & lt)] = (uint16_t)p;
+    if ((m3 >> lane) & 1u) sm.list[kFastMaxPairs - 1u - ((off >> 16) + __popc(m3 & lt))] = (uint16_t)p;
   }
 }
 
@@ -523,10 +553,12 @@ __device__ __forceinline__ void pairs_fast_body(const FastParams& P) {
         else if (nw <= 7u) fast_counts<7>(P, sm, rows, ijt, n_pairs);
         else fast_counts<8>(P, sm, rows, ijt, n_pairs);
         __syncthreads();
+        if (!het_pairs_only) fast_build_lists(sm, n_chunks);  // (fast_counts_het appends to the lists itself)
         if (tid < 32u) fast_chunk_prefix(sm, n_chunks);
+        if (!het_pairs_only || (P.mode & LGMI_MODE_EMIT_COUNTS)) __syncthreads();
         if (P.mode & LGMI_MODE_EMIT_COUNTS) {
-          __syncthreads();
           fast_emit_counts(P, sm, sm.val, base, n_chunks);
+          __syncthreads();  // the packed counts have been written out: fast_mi may replace them by MI values
         }
         fast_mi(sm, sm.val);
         __syncthreads();

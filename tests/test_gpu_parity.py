@@ -256,8 +256,8 @@ def test_many_sites_multi_item_unit(lg, gpu_ctx):
 
 
 def test_mid_units_popcount_and_tensor_paths_agree(lg, gpu_ctx):
-    """Mid-depth units (more than 64 sites or 256 reads): k_tile_gram + k_tile_finish (tcgen05, default), its
-    warp-specialised form k_tile_gram_ws (path 2) and k_tile_mi (popcount, path 0) must give the same records,
+    """Mid-depth units (more than 64 sites or 256 reads): k_tile_gram + k_tile_finish (tcgen05, path 1), its
+    warp-specialised form k_tile_gram_ws (path 2, the default) and k_tile_mi (popcount, path 0) must give the same records,
     tables and means bit for bit, and all match the oracle.  Shapes straddle the 128-site row blocks, the 48-site
     column blocks and the 128-read k-blocks."""
     rng = np.random.default_rng(20261031)
@@ -274,7 +274,7 @@ def test_mid_units_popcount_and_tensor_paths_agree(lg, gpu_ctx):
             het = lg.mi_step_batched(pb, 9, lg.MODE_HET_ONLY | lg.MODE_SKIP_NONHET | lg.MODE_EMIT_COUNTS, ctx=gpu_ctx)
             out[path] = (full, het)
     finally:
-        gpu_ctx.set_tile_path(1)
+        gpu_ctx.set_tile_path(2)                                # (the default)
     for path in (1, 2):
         for a, b in zip(out[path], out[0]):
             assert np.array_equal(a.records, b.records) and np.array_equal(a.counts, b.counts)
@@ -600,7 +600,7 @@ def test_cfg4_full_size_properties_and_oracle_sample(lg, gpu_ctx):
                 assert np.array_equal(again.records, out[path].records)                  # deterministic
             b.close()
     finally:
-        gpu_ctx.set_tile_path(1)
+        gpu_ctx.set_tile_path(2)                                # (the default)
     res = out[1]
     for path in (2, 0):                      # many tiles per CTA here: the tile-to-tile hand-over of both tensor-core forms
         assert np.array_equal(res.records, out[path].records)
