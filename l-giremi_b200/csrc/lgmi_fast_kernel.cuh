@@ -113,6 +113,7 @@ __device__ __forceinline__ void fast_site_lists(SM& sm, uint32_t S, uint32_t s =
 // the first site only).  One warp per entry, lanes over the partners.  `need` = the sites some
 // partner of which is needed whatever the entry's site is: all ones normally, the het sites when
 // only pairs next to a het SNP are evaluated (SKIP_NONHET).
+template <bool kEveryPair>  // kEveryPair: `need` is all ones (the all-pairs kernel): no test
 __device__ __forceinline__ void fast_other_cells(FastSmem& sm, const uint32_t* __restrict__ rows, uint32_t S,
                                                  unsigned long long need, uint32_t warp = threadIdx.x >> 5,
                                                  uint32_t n_warps = kFastWarps) {
@@ -121,10 +122,10 @@ __device__ __forceinline__ void fast_other_cells(FastSmem& sm, const uint32_t* _
   for (uint32_t e = warp; e < E; e += n_warps) {
     const uint32_t v = sm.oth_flat[e];
     const uint32_t s = v >> 8, w = (v & 255u) >> 5, bit = v & 31u;
-    const bool s_needed = ((need >> s) & 1ull) != 0ull;
+    const bool s_needed = kEveryPair || ((need >> s) & 1ull) != 0ull;
     for (uint32_t t = lane; t < S; t += 32u) {
       if (t == s) continue;
-      if (!s_needed && !((need >> t) & 1ull)) continue;  // this pair is not evaluated
+      if (!kEveryPair && !s_needed && !((need >> t) & 1ull)) continue;  // this pair is not evaluated
       const uint32_t* rt = rows + t * kRowStride;
       if (!((rt[16u + w] >> bit) & 1u)) continue;  // t does not cover the read
       const uint32_t Pt = (rt[8u + w] >> bit) & 1u, Mt = (rt[w] >> bit) & 1u;
@@ -535,7 +536,7 @@ __device__ __forceinline__ void pairs_fast_body(const FastParams& P) {
       // a site with more than kOthCap "other" reads does not fit the sparse lists: the generic kernel takes the unit
       const bool over = tid < S && sm.n_oth[tid] > (uint32_t)kOthCap;
       fast_site_lists(sm, S);
-      fast_other_cells(sm, rows, S, het_pairs_only ? sm.het_mask : ~0ull);
+      fast_other_cells<!het_pairs_only>(sm, rows, S, het_pairs_only ? sm.het_mask : ~0ull);
       bool dense;
       dense = __syncthreads_or(over) != 0;  // (also: sm.info is read by every thread of the counts phase)
       if (dense) {
