@@ -24,6 +24,8 @@ def main():
             "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
             "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
             "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+            "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active",
+            "lts__t_sectors_srcunit_tex_op_read.sum",
             "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
             "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum"]

@@ -357,6 +357,41 @@ def test_dense_forms_agree_and_fall_back(lg, dense_everything, blocks):
         ctx.set_dense_path(4)
 
 
+def test_dense_four_blocks_more_than_2048_sites(lg, dense_everything):
+    """k_other_fix walks the partners 2 048 at a time and k_dense_prep the sites 256 at a time: a unit of 2 100 sites
+    (S_pad 2 304: two passes, a ragged last block) in both dense forms against the popcount path, bit for bit, and a
+    sample of its sites against the oracle."""
+    ctx = dense_everything
+    rng = np.random.default_rng(132)
+    eu = _other_heavy_unit(rng, 2100, 700, 0.4, 0.01)
+    pb = lg.pack_units([eu])
+    mode = lg.MODE_ALL_PAIRS | lg.MODE_EMIT_COUNTS
+    out = {}
+    try:
+        for blocks in (4, 9):
+            ctx.set_dense_path(blocks)
+            out[blocks] = lg.mi_step_batched(pb, 6, mode, ctx=ctx)
+            assert out[blocks].n_dense_units == 1 and out[blocks].n_dense_four == (1 if blocks == 4 else 0)
+    finally:
+        ctx.set_dense_path(4)
+    ctx.set_dense_threshold(1 << 20, 1 << 30)
+    popc = lg.mi_step_batched(pb, 6, mode, ctx=ctx)
+    assert popc.n_dense_units == 0 and popc.n_records > 100000
+    for blocks in (4, 9):
+        d = out[blocks]
+        assert np.array_equal(d.records, popc.records) and np.array_equal(d.counts, popc.counts)
+        assert np.array_equal(d.site_mean, popc.site_mean, equal_nan=True) and np.array_equal(d.site_cnt, popc.site_cnt)
+    idx = np.sort(rng.choice(2100, 24, replace=False))
+    i, j, mi, tab = c_oracle.unit_pairs_from_labels(signed(eu.labels[idx]), None, 6)
+    rec = out[4].records
+    key = rec['i'].astype(np.int64) * 65536 + rec['j']
+    want = idx[i].astype(np.int64) * 65536 + idx[j]
+    at = np.searchsorted(key, want)
+    assert np.array_equal(key[at], want)
+    assert np.array_equal(out[4].counts[at].astype(np.int64), tab)
+    assert_mi_close(rec['mi'][at], mi, 0.9)
+
+
 def test_dense_path_deep_unit(lg, gpu_ctx):
     """A unit over the default threshold (520 sites x 12 000 reads) mixed with small
     units in one batch: the deep one takes the tensor cores, the others do not."""
