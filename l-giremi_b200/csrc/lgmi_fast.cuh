@@ -90,7 +90,7 @@ struct FastSmem {
   uint32_t chunk_off[kFastChunks];
   uint32_t m2_mask[kFastChunks], m3_mask[kFastChunks];   // ... of its pairs with a 2x2 / a 3x3 table (all-pairs kernel)
   uint32_t ocell[kFastMaxPairs / 2];                     // 4 KB: per pair, 15 bits: the five 3-bit "other" cells
-  uint16_t oth_flat[kFastMaxS * kOthCap];                // every (site << 8 | read) with label "other", any order
+  uint16_t oth_flat[kFastMaxS * kOthCap];                // every (site << 8 | word) holding reads with label "other", any order
   uint32_t n_oth[kFastMaxS];
   uint32_t n_oth_total;
   uint8_t flags[kFastMaxS];

@@ -72,12 +72,10 @@ __device__ __forceinline__ void fast_land(FastSmem& sm, uint32_t* __restrict__ r
     const uint32_t Pw = (M | row[8 + k]) & C;
     row[k] = M;
     row[8 + k] = Pw;
-    uint32_t O = C & ~Pw;
-    while (O) {
-      const uint32_t b = __ffs((int)O) - 1u;
-      O &= O - 1u;
-      const uint32_t idx = atomicAdd(&sm.n_oth[s], 1u);
-      if (idx < (uint32_t)kOthCap) sm.oth_flat[atomicAdd(&sm.n_oth_total, 1u)] = (uint16_t)((s << 8) | (k * 32u + b));
+    const uint32_t O = C & ~Pw;
+    if (O) {  // a word with reads labelled "other": listed as (site, word); at most kOthCap such words per site count
+      const uint32_t idx = atomicAdd(&sm.n_oth[s], (uint32_t)__popc(O));
+      if (idx < (uint32_t)kOthCap) sm.oth_flat[atomicAdd(&sm.n_oth_total, 1u)] = (uint16_t)((s << 8) | k);
     }
   }
   // het mask (sites ascending) by the first two warps
@@ -106,13 +104,14 @@ __device__ __forceinline__ void fast_site_lists(SM& sm, uint32_t S, uint32_t s =
   }
 }
 
-// The table cells that involve an "other" label, scattered from the reads that carry one:
-// for every listed (site s, read r) and every partner site t that covers r, one 3-bit cell of
-// the pair gets +1 -- T[0][0], T[0][1], T[0][2] when s is the pair's first site (by t's label
-// at r), T[1][0], T[2][0] when it is the second (a read "other" at both sites is counted from
-// the first site only).  One warp per entry, lanes over the partners.  `need` = the sites some
-// partner of which is needed whatever the entry's site is: all ones normally, the het sites when
-// only pairs next to a het SNP are evaluated (SKIP_NONHET).
+// The table cells that involve an "other" label, scattered from the words that hold such reads: for every
+// listed (site s, word k) and every partner site t, the reads of the word that are "other" at s and covered at t
+// are counted by t's label -- T[0][0], T[0][1], T[0][2] when s is the pair's first site, T[1][0], T[2][0] when it
+// is the second (a read "other" at both sites is counted from the first site only) -- and the packed 3-bit
+// increments go into the pair's field with ONE shared-memory atomic.  One warp per entry, lanes over the
+// partners.  A site holds at most kOthCap such reads (else the unit is k_pairs_generic's), so no field overflows.
+// `need` = the sites some partner of which is needed whatever the entry's site is: the het sites when only pairs
+// next to a het SNP are evaluated (SKIP_NONHET).
 template <bool kEveryPair>  // kEveryPair: `need` is all ones (the all-pairs kernel): no test
 __device__ __forceinline__ void fast_other_cells(FastSmem& sm, const uint32_t* __restrict__ rows, uint32_t S,
                                                  unsigned long long need, uint32_t warp = threadIdx.x >> 5,
@@ -121,24 +120,28 @@ __device__ __forceinline__ void fast_other_cells(FastSmem& sm, const uint32_t* _
   const uint32_t E = sm.n_oth_total;
   for (uint32_t e = warp; e < E; e += n_warps) {
     const uint32_t v = sm.oth_flat[e];
-    const uint32_t s = v >> 8, w = (v & 255u) >> 5, bit = v & 31u;
+    const uint32_t s = v >> 8, k = v & 255u;
+    const uint32_t* rs = rows + s * kRowStride;
+    const uint32_t Os = rs[16u + k] & ~rs[8u + k];  // reads of the word labelled "other" at s
     const bool s_needed = kEveryPair || ((need >> s) & 1ull) != 0ull;
     for (uint32_t t = lane; t < S; t += 32u) {
       if (t == s) continue;
       if (!kEveryPair && !s_needed && !((need >> t) & 1ull)) continue;  // this pair is not evaluated
       const uint32_t* rt = rows + t * kRowStride;
-      if (!((rt[16u + w] >> bit) & 1u)) continue;  // t does not cover the read
-      const uint32_t Pt = (rt[8u + w] >> bit) & 1u, Mt = (rt[w] >> bit) & 1u;
-      uint32_t cell, p;
+      const uint32_t x = Os & rt[16u + k];  // ... and covered at t
+      if (!x) continue;
+      const uint32_t Pt = rt[8u + k], Mt = rt[k];
+      const uint32_t n_minor = (uint32_t)__popc(x & Pt & ~Mt), n_major = (uint32_t)__popc(x & Mt);
+      uint32_t inc, p;
       if (s < t) {
-        cell = Pt ? 1u + Mt : 0u;
+        inc = (uint32_t)__popc(x & ~Pt) | (n_minor << 3) | (n_major << 6);
         p = ((s * (2u * S - s - 1u)) >> 1) + (t - s - 1u);
       } else {
-        if (!Pt) continue;
-        cell = 3u + Mt;
+        inc = (n_minor << 9) | (n_major << 12);
+        if (!inc) continue;
         p = ((t * (2u * S - t - 1u)) >> 1) + (s - t - 1u);
       }
-      atomicAdd(&sm.ocell[p >> 1], 1u << (3u * cell + 16u * (p & 1u)));
+      atomicAdd(&sm.ocell[p >> 1], inc << (16u * (p & 1u)));
     }
   }
 }
