@@ -238,7 +238,7 @@ def int8_library_tops(torch):
 
 def dense_leg(lg, synth, ctx, torch, stream, steps, warmup, flush):
     """BASELINE.json configs[2]: one unit of 2 000 sites x 100 000 reads through
-    k_dense_prep + k_gram_i8 (int8 tcgen05) + k_other_fix + the MI epilogue kernels."""
+    k_dense_prep + k_dense_x + k_gram_i8 (int8 tcgen05) + k_other_fix + the MI epilogue kernels."""
     S, R, mc = CFG3["sites"], CFG3["reads"], CFG3["min_common"]
     pb, _ = synth.make_deep_unit(CFG3["seed"], S, R, CFG3["cov"])
     batch = lg.Batch(ctx, pb)

@@ -205,7 +205,7 @@ struct lgmi_batch {
   // a second stream beside the kernels of the larger units (forked and joined by events inside the captured chain)
   cudaStream_t side_stream = nullptr;
   cudaEvent_t side_ev[4] = {};
-  cudaStream_t fix_stream = nullptr;             // k_other_fix runs beside k_gram_i8 (forked after k_dense_prep,
+  cudaStream_t fix_stream = nullptr;             // k_other_fix runs beside k_dense_x (forked after k_dense_prep,
   cudaEvent_t fix_fork = nullptr, fix_join = nullptr;  // joined before the tables are read)
   DenseTile* d_tiles = nullptr;
   uint64_t dense_macs = 0;      // multiply-accumulates the tile lists amount to
@@ -735,6 +735,11 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   };
   deepest_first(tile_items, tile_words);
   deepest_first(gram_tiles, gram_words_of);
+  // per-site sums: a CTA's time grows with its unit's number of sites (one serial chain of S steps per site), so the
+  // CTAs of the largest units go first and the short ones fill the tail
+  std::stable_sort(mean_items.begin(), mean_items.end(), [&](const MeanItem& x, const MeanItem& y) {
+    return units[x.unit].n_sites > units[y.unit].n_sites;
+  });
   b->n_tile_items = (uint32_t)tile_items.size();
   b->n_gram_tiles = (uint32_t)gram_tiles.size();
   b->gram_kernel = ctx->tile_path == 2 ? 2 : 1;
@@ -1003,18 +1008,31 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
     uint32_t* mode = b->d_unit_mode + pl.unit;
     const uint32_t* planes = b->d_planes + pl.plane_off;
     const uint64_t K_pad = (uint64_t)pl.k_blocks * kDenseBK;
-    if (pl.four) CU(ctx, cudaMemsetAsync(b->d_oth_cnt, 0, (size_t)pl.S * sizeof(uint32_t), bstream(b)));
-    else CU(ctx, cudaMemsetAsync(mode, 1, sizeof(uint32_t), bstream(b)));  // (any non-zero value: nine blocks)
-    k_dense_prep<<<dim3((pl.W + 7u) / 8u, pl.S_pad / 256u), 256, 0, bstream(b)>>>(planes, pl.S, pl.W, pl.S_pad, b->d_x, b->d_xt,
-                                                                                 b->d_oth_cnt, b->d_oth_list, pl.oth_cap, mode);
-    const unsigned cgrid = (unsigned)std::min<uint64_t>(((uint64_t)pl.S * pl.W + 255) / 256, (uint64_t)ctx->num_sms * 16u);
-    k_dense_cover<<<cgrid, 256, 0, bstream(b)>>>(planes, pl.S, pl.W, b->d_x, mode);
-    ctx->launches += 2;
     if (pl.four) {
-      // the "other" cells need the lists and the transposed planes only: counted on a second stream while the
-      // tensor cores run (a 25 KB, 384-thread CTA fits on an SM next to k_gram_i8's); joined below, before the
-      // next unit's k_dense_prep reuses the lists and before anything reads the tables
+      CU(ctx, cudaMemsetAsync(b->d_oth_cnt, 0, (size_t)pl.S * sizeof(uint32_t), bstream(b)));
+      k_dense_prep<<<dim3((pl.W + 7u) / 8u, pl.S_pad / 256u), 256, 0, bstream(b)>>>(planes, pl.S, pl.W, pl.S_pad, b->d_xt,
+                                                                                   b->d_oth_cnt, b->d_oth_list, pl.oth_cap, mode);
+      ++ctx->launches;
+      // the "other" cells need the lists and the transposed planes only: counted on a second stream, beside the
+      // X rows and the first tiles of the GEMM; joined below, before the next unit's k_dense_prep reuses the lists and
+      // before anything reads the tables.  (Measured: its three CTAs per SM hold the whole register file, so
+      // k_dense_x mostly runs after it and the step costs what one fused pass cost; capping it at two CTAs per SM,
+      // or k_dense_x first on a smaller grid, was slower -- tools/experiments/README.md.  The nine-block form no
+      // longer pays for lists and transposes it does not use: 2.01 -> 1.65 ms.)
       CU(ctx, cudaEventRecord(b->fix_fork, bstream(b)));
+      CU(ctx, cudaStreamWaitEvent(b->fix_stream, b->fix_fork, 0));
+      k_other_fix<<<pl.S, kFixThreads, 0, b->fix_stream>>>(b->d_xt, K_pad, pl.S, pl.S_pad, b->d_oth_cnt, b->d_oth_list, pl.oth_cap,
+                                                        b->d_gram + pl.gram_off, mode);
+      ++ctx->launches;
+      CU(ctx, cudaEventRecord(b->fix_join, b->fix_stream));
+    } else {
+      CU(ctx, cudaMemsetAsync(mode, 1, sizeof(uint32_t), bstream(b)));  // (any non-zero value: nine blocks)
+    }
+    {
+      const uint64_t warps = (uint64_t)pl.S * ((pl.W + 7u) / 8u);
+      const unsigned xgrid = (unsigned)std::min<uint64_t>((warps + 7) / 8, (uint64_t)ctx->num_sms * 16u);
+      k_dense_x<<<xgrid, 256, 0, bstream(b)>>>(planes, pl.S, pl.W, pl.S_pad, b->d_x, mode);
+      ++ctx->launches;
     }
     const bool last = &pl == &b->dense_plans.back();
     if (last && timing) CU(ctx, cudaEventRecord(b->ev[6], bstream(b)));
@@ -1039,14 +1057,7 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
       ++ctx->launches;
     }
     if (last && timing) CU(ctx, cudaEventRecord(b->ev[7], bstream(b)));
-    if (pl.four) {  // (issued after k_gram_i8: its one CTA per SM goes first, the fix-up's CTAs fill in beside them)
-      CU(ctx, cudaStreamWaitEvent(b->fix_stream, b->fix_fork, 0));
-      k_other_fix<<<pl.S, kFixThreads, 0, b->fix_stream>>>(b->d_xt, K_pad, pl.S, pl.S_pad, b->d_oth_cnt, b->d_oth_list, pl.oth_cap,
-                                                        b->d_gram + pl.gram_off, mode);
-      ++ctx->launches;
-      CU(ctx, cudaEventRecord(b->fix_join, b->fix_stream));
-      CU(ctx, cudaStreamWaitEvent(bstream(b), b->fix_join, 0));
-    }
+    if (pl.four) CU(ctx, cudaStreamWaitEvent(bstream(b), b->fix_join, 0));
   }
   if (timing) CU(ctx, cudaEventRecord(b->ev[5], bstream(b)));
   if (b->n_tile_items) {

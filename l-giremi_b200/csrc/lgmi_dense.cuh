@@ -16,9 +16,9 @@
 //   nine blocks   some site lists more than R/64 "other" reads: all of C, P, M against C, P, M
 //   (mode != 0)
 //
-//   k_dense_prep      bit-planes [M | m | C] -> X row groups P, M; per site the reads with label "other" (more
-//                     than the list holds -> mode 1) and the transposed label planes O, m, M
-//   k_dense_cover     nine blocks only: X row group C
+//   k_dense_prep      four blocks: per site the reads with label "other" (more than the list holds -> mode 1)
+//                     and the transposed label planes O, m, M
+//   k_dense_x         bit-planes [M | m | C] -> X row groups P, M (and C for nine blocks)
 //   k_other_fix       the "other" cells of every pair from the lists and the transposed planes
 //   k_gram_i8         one 128 x 256 output tile per CTA iteration:
 //                       warp 0  TMA producer (cp.async.bulk.tensor, 128B swizzle)
@@ -85,39 +85,21 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
   return x;
 }
 
-__device__ __forceinline__ void store_bytes32(uint8_t* __restrict__ dst, uint32_t bits) {
-  uint4 lo, hi;
-  lo.x = spread4(bits & 15u);
-  lo.y = spread4((bits >> 4) & 15u);
-  lo.z = spread4((bits >> 8) & 15u);
-  lo.w = spread4((bits >> 12) & 15u);
-  hi.x = spread4((bits >> 16) & 15u);
-  hi.y = spread4((bits >> 20) & 15u);
-  hi.z = spread4((bits >> 24) & 15u);
-  hi.w = spread4(bits >> 28);
-  reinterpret_cast<uint4*>(dst)[0] = lo;
-  reinterpret_cast<uint4*>(dst)[1] = hi;
-}
-
-// One pass over the planes.  CTA = 256 sites (a warp per group of 32, a lane per site) x 256 reads (8 words):
-// every lane reads whole 32-byte sectors of its site's rows; the words of the X row groups 1 (major or minor)
-// and 2 (major) pass through shared memory so that a warp stores 256 contiguous bytes of X[g][s][r] at a time.  For the four-block form -- unless the run was told "nine
-// blocks" up front (*mode != 0 at the start) -- it also lists the site's reads with label "other" (any order;
-// a list that overflows sets *mode: nine blocks) and transposes the label words O, m, M in registers (5 shuffle
-// steps per 32 x 32 block); those leave through a shared-memory tile as whole sectors of
-// xt[label][read][site word].  Row group 0 (covered) is written by k_dense_cover, only for nine blocks.
+// Four-block form, first pass over the planes.  CTA = 256 sites (a warp per group of 32, a lane per site) x 256
+// reads (8 words): every lane reads whole 32-byte sectors of its site's rows, lists the site's reads with label
+// "other" (any order; a list that overflows sets *mode: nine blocks) and transposes the label words O, m, M in
+// registers (5 shuffle steps per 32 x 32 block); those leave through a shared-memory tile as whole sectors of
+// xt[label][read][site word].  Returns at once when the run was told "nine blocks" up front (*mode != 0).
 __global__ void __launch_bounds__(256) k_dense_prep(const uint32_t* __restrict__ planes, uint32_t S, uint32_t W,
-                                                    uint32_t S_pad, uint8_t* __restrict__ X, uint32_t* __restrict__ xt,
-                                                    uint32_t* __restrict__ cnt, uint32_t* __restrict__ list, uint32_t cap,
-                                                    uint32_t* __restrict__ mode) {
+                                                    uint32_t S_pad, uint32_t* __restrict__ xt, uint32_t* __restrict__ cnt,
+                                                    uint32_t* __restrict__ list, uint32_t cap, uint32_t* __restrict__ mode) {
   __shared__ __align__(16) uint32_t tile[3][256][8];  // [label][read of the block][site group of the block]
-  __shared__ uint32_t raw[2][256][9];                 // [row group P, M][site of the block][word] (+1: no bank conflicts)
   __shared__ uint32_t s_nine;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   // one read per CTA: another CTA of this launch may set the flag meanwhile (the four-block outputs are not used then)
   if (tid == 0) s_nine = *reinterpret_cast<volatile uint32_t*>(mode);
   __syncthreads();
-  const uint32_t nine = s_nine;
+  if (s_nine) return;
   const uint32_t w0 = blockIdx.x * 8u, sg0 = blockIdx.y * 8u;
   const uint32_t s = (sg0 + warp) * 32u + lane;
   const uint64_t K_pad = 32ull * W;
@@ -139,7 +121,7 @@ __global__ void __launch_bounds__(256) k_dense_prep(const uint32_t* __restrict__
       Cw[4 * h] = c.x; Cw[4 * h + 1] = c.y; Cw[4 * h + 2] = c.z; Cw[4 * h + 3] = c.w;
     }
   }
-  if (!nine) {  // the site's "other" reads of these eight words, one reservation in its list
+  {  // the site's "other" reads of these eight words, one reservation in its list
     uint32_t n = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) n += (uint32_t)__popc(Cw[k] & ~Mw[k] & ~mw[k]);
@@ -163,29 +145,11 @@ __global__ void __launch_bounds__(256) k_dense_prep(const uint32_t* __restrict__
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const uint32_t L2 = Mw[k] & Cw[k], L1 = mw[k] & Cw[k] & ~Mw[k], L0 = Cw[k] & ~Mw[k] & ~mw[k];
-    raw[0][warp * 32u + lane][k] = L1 | L2;
-    raw[1][warp * 32u + lane][k] = L2;
-    if (!nine) {  // (CTA-uniform)
-      tile[0][k * 32 + lane][warp] = transpose32(L0, lane);
-      tile[1][k * 32 + lane][warp] = transpose32(L1, lane);
-      tile[2][k * 32 + lane][warp] = transpose32(L2, lane);
-    }
+    tile[0][k * 32 + lane][warp] = transpose32(L0, lane);
+    tile[1][k * 32 + lane][warp] = transpose32(L1, lane);
+    tile[2][k * 32 + lane][warp] = transpose32(L2, lane);
   }
   __syncthreads();
-  // X: a warp writes the 256 contiguous bytes of one (row group, site) at a time -- lane = 8 reads
-  {
-    const uint32_t k = lane >> 2, q4 = lane & 3u;
-    if (k < 4u || second) {
-      for (uint32_t e = warp; e < 512u; e += 8u) {
-        const uint32_t sl = e >> 1, g = e & 1u, site = sg0 * 32u + sl;
-        if (site >= S) break;
-        const uint32_t bits = (raw[g][sl][k] >> (8u * q4)) & 0xffu;
-        *reinterpret_cast<uint2*>(X + ((size_t)(g + 1u) * S_pad + site) * K_pad + (size_t)(w0 + k) * 32u + q4 * 8u) =
-            make_uint2(spread4(bits & 15u), spread4(bits >> 4));
-      }
-    }
-  }
-  if (nine) return;
   const uint32_t n_reads = second ? 256u : 128u;
   for (uint32_t e = tid; e < 3u * n_reads * 2u; e += 256u) {
     const uint32_t half = e & 1u, r = (e >> 1) % n_reads, b = (e >> 1) / n_reads;
@@ -194,14 +158,39 @@ __global__ void __launch_bounds__(256) k_dense_prep(const uint32_t* __restrict__
   }
 }
 
-// nine blocks only: row group 0 of X (covered), one thread per 32 reads of a site
-__global__ void __launch_bounds__(256) k_dense_cover(const uint32_t* __restrict__ planes, uint32_t S, uint32_t W,
-                                                     uint8_t* __restrict__ X, const uint32_t* __restrict__ mode) {
-  if (!*mode) return;
-  const uint64_t total = (uint64_t)S * W, K_pad = 32ull * W;
-  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t s = (uint32_t)(e / W), w = (uint32_t)(e - (uint64_t)s * W);
-    store_bytes32(X + (size_t)s * K_pad + (size_t)w * 32u, planes[(size_t)s * 3u * W + 2u * W + w]);
+// Second pass: the X row groups the unit's form needs -- 1 (major or minor) and 2 (major), plus 0 (covered) for
+// nine blocks -- X[g][s][r], one byte per read.  A warp takes 256 reads (8 words) of one site at a time: a lane
+// reads the word its 8 reads live in (one sector per plane and warp) and stores 8 bytes per group, so that every
+// warp-wide store is 256 contiguous bytes.  Independent of the lists and the transposed planes: in the
+// four-block form k_other_fix runs beside it on a second stream.
+__global__ void __launch_bounds__(256) k_dense_x(const uint32_t* __restrict__ planes, uint32_t S, uint32_t W, uint32_t S_pad,
+                                                 uint8_t* __restrict__ X, const uint32_t* __restrict__ mode) {
+  const uint32_t nine = *mode;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t k = lane >> 2, q4 = lane & 3u;
+  const uint64_t K_pad = 32ull * W;
+  const uint32_t octets = (W + 7u) >> 3;
+  const uint64_t total = (uint64_t)S * octets;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t e = warp0; e < total; e += n_warps) {
+    const uint32_t s = (uint32_t)(e / octets), w = (uint32_t)(e - (uint64_t)s * octets) * 8u + k;
+    if (w >= W) continue;
+    const uint32_t* row = planes + (size_t)s * 3u * W + w;
+    const uint32_t Cw = __ldg(row + 2u * W), Mw = __ldg(row) & Cw, Pw = (Mw | __ldg(row + W)) & Cw;
+    uint8_t* x = X + (size_t)s * K_pad + (size_t)w * 32u + q4 * 8u;
+    const uint32_t sh = 8u * q4;
+    if (nine) {
+      const uint32_t bits = (Cw >> sh) & 0xffu;
+      *reinterpret_cast<uint2*>(x) = make_uint2(spread4(bits & 15u), spread4(bits >> 4));
+    }
+    {
+      const uint32_t bits = (Pw >> sh) & 0xffu;
+      *reinterpret_cast<uint2*>(x + (size_t)S_pad * K_pad) = make_uint2(spread4(bits & 15u), spread4(bits >> 4));
+    }
+    {
+      const uint32_t bits = (Mw >> sh) & 0xffu;
+      *reinterpret_cast<uint2*>(x + 2ull * S_pad * K_pad) = make_uint2(spread4(bits & 15u), spread4(bits >> 4));
+    }
   }
 }
 
