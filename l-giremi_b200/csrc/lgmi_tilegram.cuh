@@ -593,11 +593,27 @@ __global__ void __launch_bounds__(kThreads, LGMI_FINISH_CTAS) k_tile_finish(cons
     __syncthreads();
     uint32_t mine = 0;
     const uint32_t n_slots = (it.pair_cnt + 31u) & ~31u;
+    // the 24 bytes of the next pair of this thread are requested before the current pair is classified
+    uint2 nx0 = make_uint2(0u, 0u), nx1 = nx0, nx2 = nx0;
+    if (tid < it.pair_cnt) {
+      nx0 = __ldg(cnt + (slot0 + tid) * 3ull);
+      nx1 = __ldg(cnt + (slot0 + tid) * 3ull + 1);
+      nx2 = __ldg(cnt + (slot0 + tid) * 3ull + 2);
+    }
     for (uint32_t pl = tid; pl < n_slots; pl += kThreads) {
       uint32_t cls = 0u;  // 0 no MI, 2 -> 2x2 list, 3 -> 3x3 list
+      const uint2 w0 = nx0, w1 = nx1, w2 = nx2;
+      if (pl + kThreads < it.pair_cnt) {
+        nx0 = __ldg(cnt + (slot0 + pl + kThreads) * 3ull);
+        nx1 = __ldg(cnt + (slot0 + pl + kThreads) * 3ull + 1);
+        nx2 = __ldg(cnt + (slot0 + pl + kThreads) * 3ull + 2);
+      }
       if (pl < it.pair_cnt) {
         uint32_t T[9];
-        const uint32_t fl = tile_cnt_load(cnt, slot0 + pl, T);
+        T[0] = w0.x & 0xffffu; T[1] = w0.x >> 16; T[2] = w0.y & 0xffffu; T[3] = w0.y >> 16;
+        T[4] = w1.x & 0xffffu; T[5] = w1.x >> 16; T[6] = w1.y & 0xffffu; T[7] = w1.y >> 16;
+        T[8] = w2.x & 0xffffu;
+        const uint32_t fl = w2.x >> 16;
         uint32_t N = 0;
 #pragma unroll
         for (int k = 0; k < 9; ++k) N += T[k];
