@@ -15,10 +15,12 @@ time), so scaling is "weak".
 
 Prints ONE JSON line (rank 0):
   value         inputs resident in HBM, CUDA events around K steps, max over ranks
-  e2e           lgmi_pipeline_step_packed through the C ABI: pinned HOST planes in (packed
-                two-plane form), pinned HOST rows (MI + (i, j) arrays) + per-site means
-                out, H2D / kernels / D2H of four groups of units overlapped inside the
-                call (the plain three-plane upload-run-download time is reported next to it)
+  e2e           the pipelined step through the C ABI: pinned HOST planes in (packed two-plane
+                form), pinned HOST rows (MI + (i, j) arrays) + per-site means out, H2D / kernels /
+                D2H of four groups of units overlapped; measured as a stream of batches
+                (lgmi_pipeline_begin_packed of step k + 1 before lgmi_pipeline_finish of step k,
+                two pipelines) with the one-call-at-a-time figure (lgmi_pipeline_step_packed) and
+                the plain three-plane upload-run-download time reported next to it
   roofline      the dominant kernel (k_pairs_fast) against the measured HBM bandwidth,
                 timed live with CUDA events on the launching stream
   cpu_baseline  the unmodified reference (baseline/_ref; the oracle's port if that is
@@ -799,6 +801,22 @@ def run_gpu(args):
     pin_packed.array[...] = packed
     def e2e_step():
         return pipe.step(mc, mode_e2e | lg.MODE_COMPACT_OUTPUT, pin_packed.array, pin_flags.array, copy=False, tight=True)
+    # the same step as a stream of batches: a second pipeline, and step k + 1 begun (lgmi_pipeline_begin_packed)
+    # before step k is collected (lgmi_pipeline_finish) -- every step still uploads its input and reads its rows
+    depth = max(2, args.e2e_depth)                           # steps in flight = pipelines
+    more = [] if args.no_e2e else [lg.Pipeline(ctx, pb, args.e2e_chunks) for _ in range(depth - 1)]
+    def e2e_stream(n):
+        pipes = [pipe] + more
+        res = None
+        for k in range(n):                                   # begin(k); collect(k - depth + 2); finish(k - depth + 1)
+            pipes[k % depth].begin(mc, mode_e2e | lg.MODE_COMPACT_OUTPUT, pin_packed.array, pin_flags.array, tight=True)
+            if args.e2e_collect and depth > 2 and k >= depth - 2:
+                pipes[(k - depth + 2) % depth].collect()
+            if k >= depth - 1:
+                res = pipes[(k - depth + 1) % depth].finish(copy=False)
+        for k in range(max(0, n - depth + 1), n):
+            res = pipes[k % depth].finish(copy=False)
+        return res
     e2e_steps = 0 if args.no_e2e else args.steps
     for _ in range(args.warmup if e2e_steps else 1):
         out = e2e_step()
@@ -817,8 +835,29 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     barrier()
-    e2e_value = pairs_per_step * world * e2e_steps / float(t.item()) if e2e_steps else None
+    e2e_sync_ms = 1e3 * float(t.item()) / e2e_steps if e2e_steps else None
+    e2e_sync_value = pairs_per_step * world * e2e_steps / float(t.item()) if e2e_steps else None
     e2e_records = int(out.n_records)
+    e2e_value, e2e_ms = e2e_sync_value, e2e_sync_ms
+    if e2e_steps:
+        outs = e2e_stream(max(depth, args.warmup))
+        assert outs.n_records == e2e_records
+        launches_e2e0 = ctx.launch_count
+        barrier()
+        t0 = time.perf_counter()
+        outs = e2e_stream(e2e_steps)                          # starts idle, ends drained: fill and drain are inside
+        torch.cuda.synchronize()
+        stream_s = time.perf_counter() - t0
+        launches_e2e = ctx.launch_count - launches_e2e0
+        t = torch.tensor([stream_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        assert outs.n_records == e2e_records
+        e2e_ms = 1e3 * float(t.item()) / e2e_steps
+        e2e_value = pairs_per_step * world * e2e_steps / float(t.item())
+        for q in more:
+            q.close()
     link = link_probe(torch, dist, rank, world, int(h2d), int(d2h)) if e2e_steps else None
     # the plain sequence (upload, run, download one after the other), for comparison
     def serial_step():
@@ -890,9 +929,15 @@ def run_gpu(args):
                              "this peak, and AND/popcount + bookkeeping share the issue slots with it (DESIGN.md section 5)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "mode": "HET_ONLY: all candidates evaluated, het-kept rows (%d) + per-site mean MI returned"
-                        % e2e_records, "ms_per_step": 1e3 * float(t.item()) / e2e_steps if e2e_steps else None,
-                "api": "lgmi_pipeline_step_packed (tight two-plane input, MI + 2-byte (i, j) rows, no per-site count), "
-                       "%d groups of units on their own streams, each group's kernels one CUDA graph" % args.e2e_chunks,
+                        % e2e_records, "ms_per_step": e2e_ms,
+                "api": "lgmi_pipeline_begin_packed / _collect / _finish on %d pipelines, step k + %d begun before step k "
+                       "is finished (a stream of batches; every step uploads its input from pinned host memory and reads "
+                       "its rows back; the timed region starts idle and ends drained); tight two-plane input, MI + 2-byte "
+                       "(i, j) rows, no per-site count, %d groups of units on their own streams, each group's kernels one "
+                       "CUDA graph" % (depth, depth - 1, args.e2e_chunks),
+                "steps_in_flight": depth,
+                "one_step_at_a_time": {"ms_per_step": e2e_sync_ms, "value": e2e_sync_value, "unit": UNIT,
+                                       "api": "lgmi_pipeline_step_packed, each call returning before the next starts"},
                 "serial_upload_run_download_ms": serial_ms, "link_probe": link, "gpu_launches": launches_e2e * world,
                 "host_affinity": numa_note},
         "gpu_launches": launches * world,
@@ -928,6 +973,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="groups of units of the pipelined end-to-end step")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="steps in flight of the streamed end-to-end measurement")
+    ap.add_argument("--e2e-collect", type=int, default=1, help="0: no lgmi_pipeline_collect ahead of the finish")
     ap.add_argument("--no-dense", action="store_true", help="skip the cfg3 deep-unit (tensor-core) leg")
     ap.add_argument("--dense-only", action="store_true", help="profiling runs: only the cfg3 deep-unit leg")
     ap.add_argument("--no-strong", action="store_true", help="skip the cfg4 strong-scaling leg")

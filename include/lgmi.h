@@ -275,6 +275,27 @@ LGMI_API int lgmi_pipeline_step(lgmi_pipeline_t* p, const uint32_t* planes, cons
 LGMI_API int lgmi_pipeline_step_packed(lgmi_pipeline_t* p, const uint32_t* planes2,
                               const uint8_t* site_flags, int min_common, uint32_t mode,
                               lgmi_result* out);
+/* The step in two halves, for callers that stream batch after batch (the       *
+ * reference's loop over regions, mismatch.py:387-404, taken a batch of regions *
+ * at a time): begin queues the uploads and the kernels of every group and      *
+ * returns; finish waits for the groups in order, copies the rows back and      *
+ * fills *out exactly as lgmi_pipeline_step* does.  With two pipelines on one   *
+ * context, begin(B) before finish(A) lets B's uploads share the link with A's  *
+ * downloads (the link is full duplex) and keeps kernels queued while the host  *
+ * collects A.  collect is the first part of finish on its own: it waits for    *
+ * the groups' kernels and queues their downloads without waiting for them, so  *
+ * that "begin(k + 2); collect(k + 1); finish(k)" over three pipelines keeps    *
+ * both directions of the link queued while the host is inside finish; finish   *
+ * collects if nobody has.  The input buffers must stay untouched until finish  *
+ * returns; the output arrays of a pipeline are rewritten from its next collect *
+ * on.  One step in flight per pipeline: a second begin is LGMI_ERR_STATE, and  *
+ * so is a collect or finish without a begin.                                   */
+LGMI_API int lgmi_pipeline_begin(lgmi_pipeline_t* p, const uint32_t* planes, const uint8_t* site_flags,
+                        int min_common, uint32_t mode);
+LGMI_API int lgmi_pipeline_begin_packed(lgmi_pipeline_t* p, const uint32_t* planes2,
+                               const uint8_t* site_flags, int min_common, uint32_t mode);
+LGMI_API int lgmi_pipeline_collect(lgmi_pipeline_t* p);
+LGMI_API int lgmi_pipeline_finish(lgmi_pipeline_t* p, lgmi_result* out);
 LGMI_API void lgmi_pipeline_destroy(lgmi_pipeline_t* p);
 
 /* one-shot convenience: create + upload + run + download (+ destroy on wait)  */

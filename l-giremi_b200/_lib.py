@@ -45,6 +45,7 @@ EXPORTS = (
     "lgmi_batch_create", "lgmi_batch_destroy", "lgmi_batch_upload", "lgmi_batch_run",
     "lgmi_batch_download", "lgmi_batch_sync", "lgmi_batch_device_ptrs",
     "lgmi_batch_algorithmic_bytes", "lgmi_pipeline_create", "lgmi_pipeline_step", "lgmi_pipeline_step_packed",
+    "lgmi_pipeline_begin", "lgmi_pipeline_begin_packed", "lgmi_pipeline_collect", "lgmi_pipeline_finish",
     "lgmi_pipeline_destroy",
     "lgmi_submit", "lgmi_wait", "lgmi_site_mean_csr",
     "lgmi_ecdf", "lgmi_ecdf_eval", "lgmi_ecdf_table", "lgmi_device_count", "lgmi_cs_scan", "lgmi_encode_unit", "lgmi_unit_cost", "lgmi_partition_lpt",
@@ -121,6 +122,10 @@ def load():
         "lgmi_pipeline_create": (i32, [vp, vp, u32, u64, u64, u32, pvp]),
         "lgmi_pipeline_step": (i32, [vp, vp, vp, i32, u32, C.POINTER(Result)]),
         "lgmi_pipeline_step_packed": (i32, [vp, vp, vp, i32, u32, C.POINTER(Result)]),
+        "lgmi_pipeline_begin": (i32, [vp, vp, vp, i32, u32]),
+        "lgmi_pipeline_begin_packed": (i32, [vp, vp, vp, i32, u32]),
+        "lgmi_pipeline_collect": (i32, [vp]),
+        "lgmi_pipeline_finish": (i32, [vp, C.POINTER(Result)]),
         "lgmi_pipeline_destroy": (None, [vp]),
         "lgmi_submit": (i32, [vp, vp, u32, vp, u64, vp, u64, i32, u32]),
         "lgmi_wait": (i32, [vp, C.POINTER(Result)]),

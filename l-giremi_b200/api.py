@@ -278,13 +278,7 @@ class Pipeline:
                                              int(n_chunks), C.byref(h)), ctx.handle)
         self.handle = h
 
-    def step(self, min_common, mode=MODE_HET_ONLY, planes=None, site_flags=None, copy=True, packed=False,
-             tight=False) -> StepResult:
-        """One pipelined step.  packed=True: `planes` is the two-plane form (PlaneBatch.packed2(),
-        two thirds of the bytes); tight=True: its rows without the 128-read padding
-        (PlaneBatch.packed2(tight=True), MODE_TIGHT_INPUT); mode | MODE_SPLIT_RECORDS: rows come back as
-        rec_mi / rec_ij; mode | MODE_COMPACT_OUTPUT: the same with 2-byte (i, j) entries where no unit has
-        more than 256 sites, and no per-site count over the wire."""
+    def _inputs(self, mode, planes, site_flags, packed, tight):
         packed = packed or tight
         if planes is None:
             planes = self.pb.packed2(tight=tight) if packed else self.pb.planes
@@ -296,9 +290,36 @@ class Pipeline:
             want = self.pb.planes.size // 3 * 2 if packed else self.pb.planes.size
         assert planes.dtype == np.uint32 and planes.size == want
         assert site_flags.dtype == np.uint8 and site_flags.size == self.pb.n_sites
+        return planes, site_flags, mode, packed
+
+    def step(self, min_common, mode=MODE_HET_ONLY, planes=None, site_flags=None, copy=True, packed=False,
+             tight=False) -> StepResult:
+        """One pipelined step.  packed=True: `planes` is the two-plane form (PlaneBatch.packed2(),
+        two thirds of the bytes); tight=True: its rows without the 128-read padding
+        (PlaneBatch.packed2(tight=True), MODE_TIGHT_INPUT); mode | MODE_SPLIT_RECORDS: rows come back as
+        rec_mi / rec_ij; mode | MODE_COMPACT_OUTPUT: the same with 2-byte (i, j) entries where no unit has
+        more than 256 sites, and no per-site count over the wire."""
+        self.begin(min_common, mode, planes, site_flags, packed, tight)
+        return self.finish(copy=copy)
+
+    def begin(self, min_common, mode=MODE_HET_ONLY, planes=None, site_flags=None, packed=False, tight=False):
+        """First half of step(): queues the uploads and kernels of every group and returns
+        (lgmi_pipeline_begin*).  The input arrays must stay alive and untouched until finish()."""
+        planes, site_flags, mode, packed = self._inputs(mode, planes, site_flags, packed, tight)
+        fn = self._lib.lgmi_pipeline_begin_packed if packed else self._lib.lgmi_pipeline_begin
+        check(fn(self.handle, ptr(planes), ptr(site_flags), int(min_common), int(mode)), self.ctx.handle)
+        self._pending = (planes, site_flags)
+
+    def collect(self):
+        """First part of finish() on its own: waits for the groups' kernels and queues their downloads
+        (lgmi_pipeline_collect); the previous result's arrays are rewritten from here on."""
+        check(self._lib.lgmi_pipeline_collect(self.handle), self.ctx.handle)
+
+    def finish(self, copy=True) -> StepResult:
+        """Second half of step(): waits for the groups, copies the rows back (lgmi_pipeline_finish)."""
         res = Result()
-        fn = self._lib.lgmi_pipeline_step_packed if packed else self._lib.lgmi_pipeline_step
-        check(fn(self.handle, ptr(planes), ptr(site_flags), int(min_common), int(mode), C.byref(res)), self.ctx.handle)
+        check(self._lib.lgmi_pipeline_finish(self.handle, C.byref(res)), self.ctx.handle)
+        self._pending = None
         out = StepResult(res, self.pb.n_units, copy=copy)
         out._site_off = self.pb.units['site_off'].astype(np.int64)
         return out

@@ -1381,6 +1381,11 @@ struct lgmi_pipeline {
   double* h_site_mean = nullptr;
   uint32_t* h_site_cnt = nullptr;
   unsigned long long* h_unit_rec_off = nullptr;
+  // a step between lgmi_pipeline_begin* and lgmi_pipeline_finish
+  bool in_flight = false;   // begun, not finished
+  bool collected = false;   // ... and its downloads queued (lgmi_pipeline_collect)
+  uint32_t pend_mode = 0;
+  uint64_t pend_rows = 0;
 };
 
 extern "C" void lgmi_pipeline_destroy(lgmi_pipeline_t* p) {
@@ -1533,27 +1538,23 @@ static int grow_pinned(lgmi_pipeline* p, T*& buf, uint64_t& cap, uint64_t need, 
   return LGMI_OK;
 }
 
-static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, const uint8_t* site_flags, int min_common,
-                         uint32_t mode, lgmi_result* out) {
-  if (!p || !out) return LGMI_ERR_ARG;
+// First half of a step: everything that does not depend on a count -- the uploads, the kernels and the row split of
+// every group -- is queued, group after group, and the call returns.
+static int pipeline_begin(lgmi_pipeline* p, const uint32_t* planes, bool packed, const uint8_t* site_flags, int min_common,
+                          uint32_t mode) {
+  if (!p) return LGMI_ERR_ARG;
   lgmi_ctx* ctx = p->ctx;
+  if (p->in_flight) return fail(ctx, LGMI_ERR_STATE, "lgmi_pipeline_begin: the previous step has not been finished");
   if ((!planes && p->plane_words) || (!site_flags && p->n_sites))
     return fail(ctx, LGMI_ERR_ARG, "lgmi_pipeline_step: NULL input");
   CU(ctx, cudaSetDevice(ctx->device));
-  const bool want_counts = (mode & LGMI_MODE_EMIT_COUNTS) != 0u;
   const bool compact = (mode & LGMI_MODE_COMPACT_OUTPUT) != 0u;  // split rows with 2-byte (i, j) where possible, no site_cnt
   const bool split = (mode & LGMI_MODE_SPLIT_RECORDS) != 0u || compact;
   const bool ij16 = compact && p->max_sites <= 256u;
   const bool tight = (mode & LGMI_MODE_TIGHT_INPUT) != 0u;
   if (tight && !packed) return fail(ctx, LGMI_ERR_ARG, "LGMI_MODE_TIGHT_INPUT is a form of the two-plane input (lgmi_pipeline_step_packed)");
+  p->pend_mode = mode;
   mode &= ~(LGMI_MODE_SPLIT_RECORDS | LGMI_MODE_COMPACT_OUTPUT | LGMI_MODE_TIGHT_INPUT);  // a matter of the copies, not of the kernels
-  const size_t ij_bytes = ij16 ? sizeof(uint16_t) : sizeof(uint32_t);
-  static const bool debug = getenv("LGMI_PIPE_DEBUG") != nullptr;
-  const auto t_begin = std::chrono::steady_clock::now();
-  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
-  double t_enqueued = 0.0;
-  std::vector<double> t_done, t_copy, t_issue;
-  // everything that does not depend on a count is queued up front, group after group
   for (lgmi_pipeline::Chunk& c : p->chunks) {
     lgmi_batch* b = c.b;
     cudaStream_t st = b->own_stream;
@@ -1596,8 +1597,28 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
     }
     CU(ctx, cudaEventRecord(c.done, st));  // the group's record count is in its (host-resident) header by then
   }
-  t_enqueued = since();
-  // records: each group's place in the merged array is known once the groups before it have been counted
+  p->in_flight = true;
+  return LGMI_OK;
+}
+
+// Second half: waits for the groups in order and copies their rows to the host; a group's place in the merged
+// arrays is known once the groups before it have been counted.
+static int pipeline_collect(lgmi_pipeline* p) {
+  if (!p) return LGMI_ERR_ARG;
+  lgmi_ctx* ctx = p->ctx;
+  if (!p->in_flight) return fail(ctx, LGMI_ERR_STATE, "lgmi_pipeline_collect / finish: no step has been begun");
+  if (p->collected) return LGMI_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const uint32_t mode = p->pend_mode;
+  const bool want_counts = (mode & LGMI_MODE_EMIT_COUNTS) != 0u;
+  const bool compact = (mode & LGMI_MODE_COMPACT_OUTPUT) != 0u;
+  const bool split = (mode & LGMI_MODE_SPLIT_RECORDS) != 0u || compact;
+  const bool ij16 = compact && p->max_sites <= 256u;
+  const size_t ij_bytes = ij16 ? sizeof(uint16_t) : sizeof(uint32_t);
+  static const bool debug = getenv("LGMI_PIPE_DEBUG") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  std::vector<double> t_done, t_issue;
   uint64_t base = 0;
   for (lgmi_pipeline::Chunk& c : p->chunks) {
     lgmi_batch* b = c.b;
@@ -1637,21 +1658,39 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
     base += nrec;
     if (debug) t_issue.push_back(since());
   }
+  p->pend_rows = base;
+  p->collected = true;
+  if (debug) {
+    fprintf(stderr, "[lgmi pipeline] (ms since lgmi_pipeline_collect) groups counted at");
+    for (double t : t_done) fprintf(stderr, " %.3f", t);
+    fprintf(stderr, "; D2H issued by");
+    for (double t : t_issue) fprintf(stderr, " %.3f", t);
+    fprintf(stderr, " ms\n");
+  }
+  return LGMI_OK;
+}
+
+// Third part: the copies have landed; per-unit row offsets of the merged arrays, scalars.
+static int pipeline_finish(lgmi_pipeline* p, lgmi_result* out) {
+  if (!p || !out) return LGMI_ERR_ARG;
+  lgmi_ctx* ctx = p->ctx;
+  int rc_collect = pipeline_collect(p);
+  if (rc_collect) {
+    p->in_flight = p->collected = false;
+    return rc_collect;
+  }
+  p->in_flight = p->collected = false;
+  const uint32_t mode = p->pend_mode;
+  const bool want_counts = (mode & LGMI_MODE_EMIT_COUNTS) != 0u;
+  const bool compact = (mode & LGMI_MODE_COMPACT_OUTPUT) != 0u;
+  const bool split = (mode & LGMI_MODE_SPLIT_RECORDS) != 0u || compact;
+  const size_t ij_bytes = (compact && p->max_sites <= 256u) ? sizeof(uint16_t) : sizeof(uint32_t);
+  const uint64_t base = p->pend_rows;
   CU(ctx, cudaStreamSynchronize(p->d2h));
-  if (debug) t_copy.push_back(since());
   for (lgmi_pipeline::Chunk& c : p->chunks) {
     for (uint32_t u = 0; u < c.n_units; ++u) p->h_unit_rec_off[c.unit0 + u] = c.base + c.b->h_unit_rec_off[u];
   }
   p->h_unit_rec_off[p->n_units] = base;
-  if (debug) {
-    fprintf(stderr, "[lgmi pipeline] enqueued %.3f ms; groups counted at", t_enqueued);
-    for (double t : t_done) fprintf(stderr, " %.3f", t);
-    fprintf(stderr, "; D2H issued by");
-    for (double t : t_issue) fprintf(stderr, " %.3f", t);
-    fprintf(stderr, "; copied back at");
-    for (double t : t_copy) fprintf(stderr, " %.3f", t);
-    fprintf(stderr, " ms\n");
-  }
   memset(out, 0, sizeof *out);
   out->n_candidates = p->n_candidates;
   out->n_evaluated = 0;
@@ -1681,13 +1720,31 @@ static int pipeline_step(lgmi_pipeline* p, const uint32_t* planes, bool packed, 
 
 extern "C" int lgmi_pipeline_step(lgmi_pipeline_t* p, const uint32_t* planes, const uint8_t* site_flags, int min_common,
                                   uint32_t mode, lgmi_result* out) {
-  return pipeline_step(p, planes, false, site_flags, min_common, mode, out);
+  if (!p || !out) return LGMI_ERR_ARG;
+  int rc = pipeline_begin(p, planes, false, site_flags, min_common, mode);
+  return rc ? rc : pipeline_finish(p, out);
 }
 
 extern "C" int lgmi_pipeline_step_packed(lgmi_pipeline_t* p, const uint32_t* planes2, const uint8_t* site_flags,
                                          int min_common, uint32_t mode, lgmi_result* out) {
-  return pipeline_step(p, planes2, true, site_flags, min_common, mode, out);
+  if (!p || !out) return LGMI_ERR_ARG;
+  int rc = pipeline_begin(p, planes2, true, site_flags, min_common, mode);
+  return rc ? rc : pipeline_finish(p, out);
 }
+
+extern "C" int lgmi_pipeline_begin(lgmi_pipeline_t* p, const uint32_t* planes, const uint8_t* site_flags, int min_common,
+                                   uint32_t mode) {
+  return pipeline_begin(p, planes, false, site_flags, min_common, mode);
+}
+
+extern "C" int lgmi_pipeline_begin_packed(lgmi_pipeline_t* p, const uint32_t* planes2, const uint8_t* site_flags,
+                                          int min_common, uint32_t mode) {
+  return pipeline_begin(p, planes2, true, site_flags, min_common, mode);
+}
+
+extern "C" int lgmi_pipeline_collect(lgmi_pipeline_t* p) { return pipeline_collect(p); }
+
+extern "C" int lgmi_pipeline_finish(lgmi_pipeline_t* p, lgmi_result* out) { return pipeline_finish(p, out); }
 
 // --------------------------------------------------------------------------- one-shot
 extern "C" int lgmi_submit(lgmi_t* ctx, const lgmi_unit_desc* units, uint32_t n_units, const uint32_t* planes,

@@ -541,6 +541,62 @@ def test_compact_rows_use_two_byte_site_indices(lg, gpu_ctx):
     pipe.close()
 
 
+def test_two_pipelines_with_steps_in_flight(lg, gpu_ctx):
+    """lgmi_pipeline_begin* / lgmi_pipeline_finish: two pipelines over DIFFERENT batches on one context, the
+    next step begun before the previous one is collected, round after round -- every result equals the
+    synchronous step of its own batch, bit for bit; a second begin or a finish without a begin is an
+    error and leaves the pipeline usable."""
+    pbs = [synth.make_heavy_tail(20261101 + k, 70, s_max=150, r_max=2500)[0] for k in range(2)]
+    pipes = [lg.Pipeline(gpu_ctx, pb, 3) for pb in pbs]
+    mode = lg.MODE_HET_ONLY | lg.MODE_COMPACT_OUTPUT
+    want = [p.step(6, mode, tight=True) for p in pipes]
+    assert not np.array_equal(want[0].site_mean, want[1].site_mean, equal_nan=True)
+    with pytest.raises(lg.LgmiError) as e:
+        pipes[0].finish()
+    assert e.value.code == -4
+    inputs = [pb.packed2(tight=True) for pb in pbs]
+    pipes[0].begin(6, mode, inputs[0], tight=True)
+    with pytest.raises(lg.LgmiError) as e:
+        pipes[0].begin(6, mode, inputs[0], tight=True)
+    assert e.value.code == -4
+    for r in range(1, 8):                                         # begin (r), then collect (r - 1)
+        k = r & 1
+        pipes[k].begin(6, mode, inputs[k], tight=True)
+        got = pipes[k ^ 1].finish()
+        w = want[k ^ 1]
+        assert got.n_records == w.n_records
+        assert np.array_equal(got.records, w.records)
+        assert np.array_equal(got.unit_rec_off, w.unit_rec_off)
+        assert np.array_equal(got.site_mean, w.site_mean, equal_nan=True)
+    got = pipes[1].finish()
+    assert np.array_equal(got.records, want[1].records)
+    # three in flight with the downloads of the next step queued before the previous one is waited for:
+    # begin(k + 2); collect(k + 1); finish(k)
+    pbs.append(synth.make_heavy_tail(20261103, 40, s_max=120, r_max=2000)[0])
+    pipes.append(lg.Pipeline(gpu_ctx, pbs[2], 2))
+    inputs.append(pbs[2].packed2(tight=True))
+    want.append(pipes[2].step(6, mode, tight=True))
+    with pytest.raises(lg.LgmiError) as e:
+        pipes[2].collect()
+    assert e.value.code == -4
+    for k in range(9):
+        pipes[k % 3].begin(6, mode, inputs[k % 3], tight=True)
+        if k >= 1:
+            pipes[(k - 1) % 3].collect()
+            pipes[(k - 1) % 3].collect()                          # (idempotent)
+        if k >= 2:
+            got, w = pipes[(k - 2) % 3].finish(), want[(k - 2) % 3]
+            assert np.array_equal(got.records, w.records) and np.array_equal(got.unit_rec_off, w.unit_rec_off)
+            assert np.array_equal(got.site_mean, w.site_mean, equal_nan=True)
+    for k in (7, 8):
+        got, w = pipes[k % 3].finish(), want[k % 3]
+        assert np.array_equal(got.records, w.records) and np.array_equal(got.site_mean, w.site_mean, equal_nan=True)
+    # and the synchronous call still works on both afterwards
+    for p, w in zip(pipes, want):
+        assert np.array_equal(p.step(6, mode, tight=True).records, w.records)
+        p.close()
+
+
 def test_pipeline_needs_back_to_back_units(lg, gpu_ctx):
     pb = synth.make_uniform_planes(3, 4, 5, 40, 0.5)
     bad = lg.PlaneBatch(pb.units[::-1].copy(), pb.planes, pb.site_flags)

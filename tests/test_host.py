@@ -73,6 +73,18 @@ def test_version_and_pure_host_entry_points(lg):
     assert lib.lgmi_unit_cost(2000, 100000) == 1999000 * 1563
 
 
+def test_pipeline_halves_reject_a_null_handle(lg):
+    """lgmi_pipeline_begin* / lgmi_pipeline_finish without a pipeline: LGMI_ERR_ARG, no device touched."""
+    import ctypes as C
+    lib = importlib_lib().load()
+    res = importlib_lib().Result()
+    assert lib.lgmi_pipeline_begin(None, None, None, 6, 0) == -2
+    assert lib.lgmi_pipeline_begin_packed(None, None, None, 6, 0) == -2
+    assert lib.lgmi_pipeline_collect(None) == -2
+    assert lib.lgmi_pipeline_finish(None, C.byref(res)) == -2
+    assert lib.lgmi_pipeline_step_packed(None, None, None, 6, 0, C.byref(res)) == -2
+
+
 @pytest.mark.skipif(has_gpu(), reason="checks the no-device error path")
 def test_no_device_is_a_loud_error(lg):
     """No CPU fallback: creating a context without a GPU raises."""
