@@ -18,9 +18,10 @@ Prints ONE JSON line (rank 0):
   e2e           the pipelined step through the C ABI: pinned HOST planes in (packed two-plane
                 form), pinned HOST rows (MI + (i, j) arrays) + per-site means out, H2D / kernels /
                 D2H of four groups of units overlapped; measured as a stream of batches
-                (lgmi_pipeline_begin_packed of step k + 1 before lgmi_pipeline_finish of step k,
-                two pipelines) with the one-call-at-a-time figure (lgmi_pipeline_step_packed) and
-                the plain three-plane upload-run-download time reported next to it
+                (lgmi_pipeline_begin_packed / _collect / _finish over several pipelines: four steps
+                in flight, every step uploading its input and reading its rows back) with the
+                one-call-at-a-time figure (lgmi_pipeline_step_packed, four groups) and the plain
+                three-plane upload-run-download time reported next to it
   roofline      the dominant kernel (k_pairs_fast) against the measured HBM bandwidth,
                 timed live with CUDA events on the launching stream
   cpu_baseline  the unmodified reference (baseline/_ref; the oracle's port if that is
@@ -416,6 +417,29 @@ def strong_leg(lg, synth, ctx, torch, dist, rank, world, stream, steps, warmup, 
         torch.cuda.synchronize()
         return 1e3 * (time.perf_counter() - t) / steps
 
+    def timed_host_stream(pb, pins, depth=3):
+        """The same host-buffer step as a stream of batches: `depth` steps in flight over as many one-group
+        pipelines (lgmi_pipeline_begin_packed / _collect / _finish); starts idle, ends drained."""
+        pipes = [lg.Pipeline(ctx, pb, 1) for _ in range(depth)]
+        def run(n):
+            for k in range(n):
+                pipes[k % depth].begin(mc, mode | lg.MODE_COMPACT_OUTPUT, pins[0].array, pins[1].array, tight=True)
+                if k >= depth - 2:
+                    pipes[(k - depth + 2) % depth].collect()
+                if k >= depth - 1:
+                    pipes[(k - depth + 1) % depth].finish(copy=False)
+            for k in range(max(0, n - depth + 1), n):
+                pipes[k % depth].finish(copy=False)
+        run(max(depth, warmup))
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        run(steps)
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t) / steps
+        for q in pipes:
+            q.close()
+        return ms
+
     def timed_device(pb):
         batch = lg.Batch(ctx, pb)
         batch.upload()
@@ -445,6 +469,8 @@ def strong_leg(lg, synth, ctx, torch, dist, rank, world, stream, steps, warmup, 
     step, pipe, pins, chunks, h2d = host_api(mine)
     barrier()
     host_ms = all_ranks(timed_host(step))                    # upload + kernels + download of this rank's shard
+    barrier()
+    stream_ms = all_ranks(timed_host_stream(mine, pins))     # ... with three steps in flight
     barrier()
     dev_ms = all_ranks(timed_device(mine))                   # the same shard resident in HBM, ALL_PAIRS, CUDA events
     barrier()
@@ -485,6 +511,10 @@ def strong_leg(lg, synth, ctx, torch, dist, rank, world, stream, steps, warmup, 
             "what": "per rank: lgmi_pipeline_step_packed over pinned host buffers (H2D + kernels + D2H, HET_ONLY rows + "
                     "per-site means; tight two-plane input, compact rows), wall clock, max over ranks",
             "rank_ms": host_ms, "n1_ms_per_step": t1_host, "efficiency_vs_n1": t1_host / (world * max(host_ms)),
+            "streamed": {"what": "the same host-buffer step as a stream of batches: three steps in flight per rank "
+                                 "(lgmi_pipeline_begin_packed / _collect / _finish, one group per step), wall clock over "
+                                 "the steps from idle to drained, max over ranks",
+                         "ms_per_step": max(stream_ms), "value": pairs_total / (max(stream_ms) * 1e-3), "rank_ms": stream_ms},
             "device_resident": {"what": "the shard resident in HBM, ALL_PAIRS, launch chain as one CUDA graph, CUDA events, max over ranks",
                                 "ms_per_step": max(dev_ms), "value": pairs_total / (max(dev_ms) * 1e-3),
                                 "rank_ms": dev_ms, "n1_ms_per_step": t1_dev,
@@ -804,9 +834,10 @@ def run_gpu(args):
     # the same step as a stream of batches: a second pipeline, and step k + 1 begun (lgmi_pipeline_begin_packed)
     # before step k is collected (lgmi_pipeline_finish) -- every step still uploads its input and reads its rows
     depth = max(2, args.e2e_depth)                           # steps in flight = pipelines
-    more = [] if args.no_e2e else [lg.Pipeline(ctx, pb, args.e2e_chunks) for _ in range(depth - 1)]
+    # (with several steps in flight a step need not be cut into groups: one group per step by default)
+    more = [] if args.no_e2e else [lg.Pipeline(ctx, pb, args.e2e_stream_chunks) for _ in range(depth)]
     def e2e_stream(n):
-        pipes = [pipe] + more
+        pipes = more
         res = None
         for k in range(n):                                   # begin(k); collect(k - depth + 2); finish(k - depth + 1)
             pipes[k % depth].begin(mc, mode_e2e | lg.MODE_COMPACT_OUTPUT, pin_packed.array, pin_flags.array, tight=True)
@@ -821,8 +852,8 @@ def run_gpu(args):
     for _ in range(args.warmup if e2e_steps else 1):
         out = e2e_step()
     h2d = packed.nbytes + pb.site_flags.nbytes
-    d2h = out.n_records * (8 + out.rec_ij.dtype.itemsize) + pb.n_sites * 8 + (pb.n_units + args.e2e_chunks) * 8 + \
-        16 * args.e2e_chunks
+    groups_e2e = args.e2e_stream_chunks                      # (of the streamed measurement, which `value` reports)
+    d2h = out.n_records * (8 + out.rec_ij.dtype.itemsize) + pb.n_sites * 8 + (pb.n_units + groups_e2e) * 8 + 16 * groups_e2e
     launches_e2e0 = ctx.launch_count
     barrier()
     t0 = time.perf_counter()
@@ -933,11 +964,12 @@ def run_gpu(args):
                 "api": "lgmi_pipeline_begin_packed / _collect / _finish on %d pipelines, step k + %d begun before step k "
                        "is finished (a stream of batches; every step uploads its input from pinned host memory and reads "
                        "its rows back; the timed region starts idle and ends drained); tight two-plane input, MI + 2-byte "
-                       "(i, j) rows, no per-site count, %d groups of units on their own streams, each group's kernels one "
-                       "CUDA graph" % (depth, depth - 1, args.e2e_chunks),
+                       "(i, j) rows, no per-site count, %d group(s) of units per step, each group's kernels one "
+                       "CUDA graph" % (depth, depth - 1, args.e2e_stream_chunks),
                 "steps_in_flight": depth,
                 "one_step_at_a_time": {"ms_per_step": e2e_sync_ms, "value": e2e_sync_value, "unit": UNIT,
-                                       "api": "lgmi_pipeline_step_packed, each call returning before the next starts"},
+                                       "api": "lgmi_pipeline_step_packed, each call returning before the next starts; "
+                                              "%d groups of units on their own streams" % args.e2e_chunks},
                 "serial_upload_run_download_ms": serial_ms, "link_probe": link, "gpu_launches": launches_e2e * world,
                 "host_affinity": numa_note},
         "gpu_launches": launches * world,
@@ -973,7 +1005,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="groups of units of the pipelined end-to-end step")
-    ap.add_argument("--e2e-depth", type=int, default=3, help="steps in flight of the streamed end-to-end measurement")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="steps in flight of the streamed end-to-end measurement")
+    ap.add_argument("--e2e-stream-chunks", type=int, default=1, help="groups of units per step of the streamed measurement")
     ap.add_argument("--e2e-collect", type=int, default=1, help="0: no lgmi_pipeline_collect ahead of the finish")
     ap.add_argument("--no-dense", action="store_true", help="skip the cfg3 deep-unit (tensor-core) leg")
     ap.add_argument("--dense-only", action="store_true", help="profiling runs: only the cfg3 deep-unit leg")
