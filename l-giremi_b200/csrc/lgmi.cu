@@ -222,6 +222,8 @@ struct lgmi_batch {
   uint2* d_tile_cnt = nullptr;         // its output: 24 bytes of counts per pair slot
   uint32_t* d_tile_next = nullptr;     // its work counter
   uint32_t n_tiled_work_items = 0;     // work items (Item) of the tiled and of the deep units: k_pairs_generic<1>'s and <2>'s
+  TiledDesc* d_tiled_desc = nullptr;   // k_pairs_generic<1>'s items, one self-contained record each
+  uint32_t n_tiled_desc = 0;
   uint32_t* d_tile_counts = nullptr;  // EMIT_COUNTS only, allocated on first use
   uint64_t n_tiled_slots = 0;
   // host (pinned) mirrors
@@ -526,6 +528,7 @@ extern "C" void lgmi_batch_destroy(lgmi_batch_t* b) {
   ctx->dev_pool.release(b->d_tiles);
   ctx->dev_pool.release(b->d_tile_items);
   ctx->dev_pool.release(b->d_gram_tiles);
+  ctx->dev_pool.release(b->d_tiled_desc);
   ctx->dev_pool.release(b->d_tile_cnt);
   ctx->dev_pool.release(b->d_tile_next);
   ctx->dev_pool.release(b->d_tile_counts);
@@ -559,6 +562,7 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   std::vector<MeanItem> mean_items;
   std::vector<DenseTile> dense_tiles;
   std::vector<TileItem> tile_items;
+  std::vector<TiledDesc> tiled_desc;  // k_pairs_generic<1>'s items
   std::vector<TgTile> gram_tiles;
   std::vector<uint32_t> tile_words, gram_words_of;  // W of each tile's unit (launch order: longest first)
   bool any_gram_tiled = false;
@@ -701,6 +705,13 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
       it.flags = (t == 0 ? ITEM_FIRST : 0u) | (nit == 1 ? ITEM_SINGLE : 0u) | (d.tiled ? ITEM_TILED : 0u) |
                  (d.tiled == 2 ? ITEM_TILED_GRAM : 0u) | (d.gram_off != kNoGram ? ITEM_GRAM : 0u);
       if (d.tiled || d.gram_off != kNoGram) ++b->n_tiled_work_items;  // (not k_pairs_generic<0>'s)
+      if (d.tiled) {
+        TiledDesc td{};
+        td.item_idx = (uint32_t)b->h_items.size();
+        td.unit = k, td.pair_begin = it.pair_begin, td.pair_cnt = it.pair_cnt, td.flags = it.flags;
+        td.S = u.n_sites, td.site_off = u.site_off, td.dense_off = d.dense_off;
+        tiled_desc.push_back(td);
+      }
       if (nit == 1 && np >= 1 && d.gram_off == kNoGram && u.n_sites <= (uint32_t)kFastMaxS && u.n_reads <= (uint32_t)kFastMaxR) {
         it.flags |= ITEM_FAST;  // (a unit sent to the tensor-core path by a lowered threshold is not also k_pairs_fast's)
         FastItem f;
@@ -801,6 +812,12 @@ extern "C" int lgmi_batch_create(lgmi_t* ctx, const lgmi_unit_desc* units, uint3
   if (!gram_tiles.empty()) {
     BCU(pool_malloc(ctx, &b->d_gram_tiles, gram_tiles.size() * sizeof(TgTile)));
     BCU(cudaMemcpyAsync(b->d_gram_tiles, gram_tiles.data(), gram_tiles.size() * sizeof(TgTile), cudaMemcpyHostToDevice,
+                        bstream(b)));
+  }
+  b->n_tiled_desc = (uint32_t)tiled_desc.size();
+  if (!tiled_desc.empty()) {
+    BCU(pool_malloc(ctx, &b->d_tiled_desc, tiled_desc.size() * sizeof(TiledDesc)));
+    BCU(cudaMemcpyAsync(b->d_tiled_desc, tiled_desc.data(), tiled_desc.size() * sizeof(TiledDesc), cudaMemcpyHostToDevice,
                         bstream(b)));
   }
   if (any_gram_tiled) BCU(pool_malloc(ctx, &b->d_tile_cnt, std::max<uint64_t>(1, dense) * 3ull * sizeof(uint2)));
@@ -956,6 +973,8 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
   P.units = b->d_units;
   P.items = b->d_items;
   P.n_items = b->n_items;
+  P.tiled_desc = b->d_tiled_desc;
+  P.n_tiled_desc = b->n_tiled_desc;
   P.n_units = b->n_units;
   P.planes = b->d_planes;
   P.site_flags = b->d_flags;
@@ -1187,8 +1206,8 @@ static int run_chain(lgmi_batch* b, int min_common, uint32_t mode, bool timing) 
   if (forked) CU(ctx, cudaEventRecord(b->side_ev[3], small));
   if (b->n_items) {
     // everything the small-unit kernel does not take
-    if (b->n_tile_items || b->n_gram_tiles) {  // ordering + emission of what k_tile_mi / k_tile_finish computed
-      const unsigned grid = (unsigned)std::min<uint64_t>(b->n_items, (uint64_t)ctx->num_sms * 4u);
+    if (b->n_tiled_desc) {  // ordering + emission of what k_tile_mi / k_tile_finish computed
+      const unsigned grid = (unsigned)std::min<uint64_t>(b->n_tiled_desc, (uint64_t)ctx->num_sms * 4u);
       k_pairs_generic<1><<<grid, kThreads, 0, bstream(b)>>>(P);
       ++ctx->launches;
     }

@@ -52,6 +52,16 @@ struct Item {
   uint32_t flags;
 };
 
+// Everything k_pairs_generic<1> needs of a work item of a mid-depth (tiled) unit, in one 48-byte record built on
+// the host: the kernel requests the next record (cp.async) while it works on the current item, instead of the
+// chain items[] -> units[] at the head of every item.
+struct __align__(16) TiledDesc {
+  uint32_t item_idx, unit, pair_begin, pair_cnt;
+  uint32_t flags, S, site_off, pad;
+  uint64_t dense_off, pad2;
+};
+static_assert(sizeof(TiledDesc) == 48, "three 16-byte copies per record");
+
 struct Header {
   unsigned long long n_records;
   unsigned long long pad;
@@ -76,6 +86,8 @@ struct RunParams {
   const uint32_t* unit_mode;           // per unit, tensor-core path: 0 four Gram blocks + "other" cells, else nine blocks
   uint32_t* tile_counts;               // EMIT_COUNTS: 3x3 tables of the k_tile_mi units, 9 per dense slot
   uint32_t unit_base;                  // added to the unit field of every record
+  const TiledDesc* tiled_desc;         // k_pairs_generic<1>: its items, in item order
+  uint32_t n_tiled_desc;
   Header* header;
   lgmi_pair_rec* records;
   uint32_t* counts;
@@ -223,16 +235,44 @@ __global__ void __launch_bounds__(kThreads, kKind == 1 ? 4 : (kKind == 2 ? 3 : 2
   const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
   if (kKind == 0 && *P.n_generic == 0u) return;  // every item was a small unit taken by k_pairs_fast
 
-  for (uint32_t item_idx = blockIdx.x; item_idx < P.n_items; item_idx += gridDim.x) {
-    const Item it = P.items[item_idx];
-    if (kTiled != ((it.flags & ITEM_TILED) != 0u)) continue;          // another instantiation's
-    if ((kKind == 2) != ((it.flags & ITEM_GRAM) != 0u)) continue;
-    if ((it.flags & ITEM_FAST) && !P.item_dense[item_idx]) continue;  // k_pairs_fast's
-    const DevUnit u = P.units[it.unit];
+  // kTiled: the kernel walks its own list of item records, the next record in flight while the current item is worked on
+  __shared__ TiledDesc s_desc[kTiled ? 2 : 1];
+  const uint32_t n_loop = kTiled ? P.n_tiled_desc : P.n_items;
+  uint32_t buf = 0u;
+  if constexpr (kTiled) {
+    if (tid < 3u && blockIdx.x < n_loop)
+      cp_async16(reinterpret_cast<char*>(&s_desc[0]) + 16u * tid, reinterpret_cast<const char*>(P.tiled_desc + blockIdx.x) + 16u * tid, true);
+    cp_async_commit();
+  }
+  for (uint32_t q = blockIdx.x; q < n_loop; q += gridDim.x) {
+    uint32_t item_idx = q;
+    Item it;
+    DevUnit u;
+    if constexpr (kTiled) {
+      cp_async_wait<0>();
+      __syncthreads();  // the record has landed; previous item fully consumed
+      const TiledDesc d = s_desc[buf];
+      item_idx = d.item_idx;
+      it.unit = d.unit, it.pair_begin = d.pair_begin, it.pair_cnt = d.pair_cnt, it.flags = d.flags;
+      u = DevUnit{};
+      u.S = d.S, u.site_off = d.site_off, u.dense_off = d.dense_off, u.tiled = 1u;
+      buf ^= 1u;
+      if (tid < 3u && q + gridDim.x < n_loop)  // (its last readers passed the barrier above an item ago)
+        cp_async16(reinterpret_cast<char*>(&s_desc[buf]) + 16u * tid,
+                   reinterpret_cast<const char*>(P.tiled_desc + q + gridDim.x) + 16u * tid, true);
+      cp_async_commit();
+    } else {
+      it = P.items[item_idx];
+      if (it.flags & ITEM_TILED) continue;                              // another instantiation's
+      if ((kKind == 2) != ((it.flags & ITEM_GRAM) != 0u)) continue;
+      if ((it.flags & ITEM_FAST) && !P.item_dense[item_idx]) continue;  // k_pairs_fast's
+      u = P.units[it.unit];
+      __syncthreads();  // previous item fully consumed
+    }
+    const unsigned long long item_out = P.item_off[item_idx];  // (needed after the counting pass: requested here)
     const uint32_t W4 = u.W >> 2;
     const uint4* __restrict__ base = reinterpret_cast<const uint4*>(P.planes + u.plane_off);
     const uint8_t* __restrict__ flags = P.site_flags + u.site_off;
-    __syncthreads();  // previous item fully consumed
 
     // ---- counts + MI for every candidate pair of the item
     uint32_t i = 0, j = 0;
@@ -359,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, kKind == 1 ? 4 : (kKind == 2 ? 3 : 2
     }
     if (lane == 0) s_warp[warp] = mine;
     __syncthreads();
-    unsigned long long out = P.item_off[item_idx];
+    unsigned long long out = item_out;
     if (tid == 0 && (it.flags & ITEM_FIRST)) P.unit_rec_off[it.unit] = out;
     for (uint32_t w = 0; w < warp; ++w) out += s_warp[w];
     for (uint32_t pl = p_begin + lane; pl < p_begin + per_warp; pl += 32) {
