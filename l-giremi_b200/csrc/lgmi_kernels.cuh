@@ -224,7 +224,7 @@ __device__ __forceinline__ void gram_table_2x2(const uint32_t* __restrict__ g, u
 template <int kKind>
 __global__ void __launch_bounds__(kThreads, kKind == 1 ? 4 : (kKind == 2 ? 3 : 2)) k_pairs_generic(const RunParams P) {
   constexpr bool kTiled = kKind == 1;
-  __shared__ double s_mi[kPairsMax];    // MI of each pair of the item, NaN = no MI
+  __shared__ double s_mi_all[(kKind == 1 ? 2 : 1) * kPairsMax];  // MI of each pair of the item, NaN = no MI (kKind 1: and of the next item)
   __shared__ uint32_t s_ij[kPairsMax];  // (i << 16) | j
   __shared__ uint32_t s_warp[kThreads / 32];
   __shared__ uint16_t s_list[kKind == 2 ? kPairsMax : 1];  // kKind 2: pairs with a 2x2 table from the front, the others from the back
@@ -236,30 +236,46 @@ __global__ void __launch_bounds__(kThreads, kKind == 1 ? 4 : (kKind == 2 ? 3 : 2
   if (kKind == 0 && *P.n_generic == 0u) return;  // every item was a small unit taken by k_pairs_fast
 
   // kTiled: the kernel walks its own list of item records, the next record in flight while the current item is worked on
-  __shared__ TiledDesc s_desc[kTiled ? 2 : 1];
+  // and requests, a whole item ahead, the record after the next and the MI values of the next item (k_tile_finish's
+  // output, 8 bytes per pair) by cp.async: nothing of an item's input is waited for at its head.
+  __shared__ TiledDesc s_desc[kTiled ? 3 : 1];
   const uint32_t n_loop = kTiled ? P.n_tiled_desc : P.n_items;
-  uint32_t buf = 0u;
+  uint32_t n_it = 0u;  // items this CTA has started
+  auto request_desc = [&](uint32_t slot, uint32_t q) {
+    if (tid < 3u && q < n_loop)
+      cp_async16(reinterpret_cast<char*>(&s_desc[slot]) + 16u * tid, reinterpret_cast<const char*>(P.tiled_desc + q) + 16u * tid, true);
+  };
+  auto request_mi = [&](uint32_t slot, uint32_t half) {  // (the record in `slot` has landed)
+    const TiledDesc& d = s_desc[slot];
+    const double* src = P.dense + d.dense_off + d.pair_begin;
+    double* dst = s_mi_all + half * kPairsMax;
+    for (uint32_t pl = tid; pl < d.pair_cnt; pl += kThreads) cp_async8(dst + pl, src + pl);
+  };
   if constexpr (kTiled) {
-    if (tid < 3u && blockIdx.x < n_loop)
-      cp_async16(reinterpret_cast<char*>(&s_desc[0]) + 16u * tid, reinterpret_cast<const char*>(P.tiled_desc + blockIdx.x) + 16u * tid, true);
+    request_desc(0u, blockIdx.x);
+    request_desc(1u, blockIdx.x + gridDim.x);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (blockIdx.x < n_loop) request_mi(0u, 0u);
     cp_async_commit();
   }
-  for (uint32_t q = blockIdx.x; q < n_loop; q += gridDim.x) {
+  for (uint32_t q = blockIdx.x; q < n_loop; q += gridDim.x, ++n_it) {
     uint32_t item_idx = q;
     Item it;
     DevUnit u;
+    double* const s_mi = s_mi_all + (kTiled ? (n_it & 1u) * kPairsMax : 0u);
     if constexpr (kTiled) {
       cp_async_wait<0>();
-      __syncthreads();  // the record has landed; previous item fully consumed
-      const TiledDesc d = s_desc[buf];
+      __syncthreads();  // this item's record and MI values and the next record have landed; previous item fully consumed
+      const TiledDesc d = s_desc[n_it % 3u];
       item_idx = d.item_idx;
       it.unit = d.unit, it.pair_begin = d.pair_begin, it.pair_cnt = d.pair_cnt, it.flags = d.flags;
       u = DevUnit{};
       u.S = d.S, u.site_off = d.site_off, u.dense_off = d.dense_off, u.tiled = 1u;
-      buf ^= 1u;
-      if (tid < 3u && q + gridDim.x < n_loop)  // (its last readers passed the barrier above an item ago)
-        cp_async16(reinterpret_cast<char*>(&s_desc[buf]) + 16u * tid,
-                   reinterpret_cast<const char*>(P.tiled_desc + q + gridDim.x) + 16u * tid, true);
+      // (the buffers written now were last read an item ago, before the barrier above)
+      if (q + gridDim.x < n_loop) request_mi((n_it + 1u) % 3u, (n_it + 1u) & 1u);
+      request_desc((n_it + 2u) % 3u, q + 2u * gridDim.x);
       cp_async_commit();
     } else {
       it = P.items[item_idx];
@@ -269,7 +285,8 @@ __global__ void __launch_bounds__(kThreads, kKind == 1 ? 4 : (kKind == 2 ? 3 : 2
       u = P.units[it.unit];
       __syncthreads();  // previous item fully consumed
     }
-    const unsigned long long item_out = P.item_off[item_idx];  // (needed after the counting pass: requested here)
+    unsigned long long item_out = 0ull;
+    if constexpr (kTiled) item_out = P.item_off[item_idx];  // (needed after the counting pass: requested here)
     const uint32_t W4 = u.W >> 2;
     const uint4* __restrict__ base = reinterpret_cast<const uint4*>(P.planes + u.plane_off);
     const uint8_t* __restrict__ flags = P.site_flags + u.site_off;
@@ -278,10 +295,7 @@ __global__ void __launch_bounds__(kThreads, kKind == 1 ? 4 : (kKind == 2 ? 3 : 2
     uint32_t i = 0, j = 0;
     if (tid < it.pair_cnt) lg_pair_ij(it.pair_begin + tid, u.S, i, j);  // one square root per thread, then steps
     if constexpr (kTiled) {
-      // k_tile_mi has been here (NaN: dropped / not evaluated): the loads first, all in flight together
-      const double* __restrict__ src = P.dense + u.dense_off + it.pair_begin;
-#pragma unroll 8
-      for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) s_mi[pl] = src[pl];
+      // k_tile_mi / k_tile_finish have been here (NaN: dropped / not evaluated) and the values are in s_mi already
       for (uint32_t pl = tid; pl < it.pair_cnt; pl += kThreads) {
         if (pl != tid) lg_pair_advance(i, j, u.S, kThreads);
         s_ij[pl] = (i << 16) | j;
@@ -399,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, kKind == 1 ? 4 : (kKind == 2 ? 3 : 2
     }
     if (lane == 0) s_warp[warp] = mine;
     __syncthreads();
-    unsigned long long out = item_out;
+    unsigned long long out = kTiled ? item_out : P.item_off[item_idx];
     if (tid == 0 && (it.flags & ITEM_FIRST)) P.unit_rec_off[it.unit] = out;
     for (uint32_t w = 0; w < warp; ++w) out += s_warp[w];
     for (uint32_t pl = p_begin + lane; pl < p_begin + per_warp; pl += 32) {

@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU round AO of r2: k_pairs_generic<1> over its own list of self-contained item records, next record in flight
+# GPU round AO of r2: k_pairs_generic<1> over its own list of item records; record and MI values of the next item requested a whole item ahead
 O=gpurun_out
 mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_all_paths_agree.py -x -q -m gpu -k "heavy_tail or many_sites or mid_units or cfg4 or all_paths or pipelined or counts" > $O/rao_tests.log 2>&1
