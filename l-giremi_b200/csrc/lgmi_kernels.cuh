@@ -235,9 +235,9 @@ __global__ void __launch_bounds__(kThreads, kKind == 1 ? 4 : (kKind == 2 ? 3 : 2
   const bool skip_nonhet = het_only && (P.mode & LGMI_MODE_SKIP_NONHET) != 0u;
   if (kKind == 0 && *P.n_generic == 0u) return;  // every item was a small unit taken by k_pairs_fast
 
-  // kTiled: the kernel walks its own list of item records, the next record in flight while the current item is worked on
-  // and requests, a whole item ahead, the record after the next and the MI values of the next item (k_tile_finish's
-  // output, 8 bytes per pair) by cp.async: nothing of an item's input is waited for at its head.
+  // kTiled: the kernel walks its own list of item records (TiledDesc) and requests, a whole item ahead, the record
+  // after the next and the MI values of the next item (k_tile_finish's output, 8 bytes per pair) by cp.async:
+  // nothing of an item's input is waited for at its head.
   __shared__ TiledDesc s_desc[kTiled ? 3 : 1];
   const uint32_t n_loop = kTiled ? P.n_tiled_desc : P.n_items;
   uint32_t n_it = 0u;  // items this CTA has started
