@@ -422,14 +422,9 @@ def strong_leg(lg, synth, ctx, torch, dist, rank, world, stream, steps, warmup, 
         pipelines (lgmi_pipeline_begin_packed / _collect / _finish); starts idle, ends drained."""
         pipes = [lg.Pipeline(ctx, pb, 1) for _ in range(depth)]
         def run(n):
-            for k in range(n):
-                pipes[k % depth].begin(mc, mode | lg.MODE_COMPACT_OUTPUT, pins[0].array, pins[1].array, tight=True)
-                if k >= depth - 2:
-                    pipes[(k - depth + 2) % depth].collect()
-                if k >= depth - 1:
-                    pipes[(k - depth + 1) % depth].finish(copy=False)
-            for k in range(max(0, n - depth + 1), n):
-                pipes[k % depth].finish(copy=False)
+            feed = ((pins[0].array, pins[1].array) for _ in range(n))
+            for _k, _res in lg.stream_steps(pipes, feed, mc, mode | lg.MODE_COMPACT_OUTPUT, copy=False, tight=True):
+                pass
         run(max(depth, warmup))
         torch.cuda.synchronize()
         t = time.perf_counter()
@@ -836,17 +831,12 @@ def run_gpu(args):
     depth = max(2, args.e2e_depth)                           # steps in flight = pipelines
     # (with several steps in flight a step need not be cut into groups: one group per step by default)
     more = [] if args.no_e2e else [lg.Pipeline(ctx, pb, args.e2e_stream_chunks) for _ in range(depth)]
-    def e2e_stream(n):
-        pipes = more
+    def e2e_stream(n):                                       # begin(k); collect(k - depth + 2); finish(k - depth + 1)
         res = None
-        for k in range(n):                                   # begin(k); collect(k - depth + 2); finish(k - depth + 1)
-            pipes[k % depth].begin(mc, mode_e2e | lg.MODE_COMPACT_OUTPUT, pin_packed.array, pin_flags.array, tight=True)
-            if args.e2e_collect and depth > 2 and k >= depth - 2:
-                pipes[(k - depth + 2) % depth].collect()
-            if k >= depth - 1:
-                res = pipes[(k - depth + 1) % depth].finish(copy=False)
-        for k in range(max(0, n - depth + 1), n):
-            res = pipes[k % depth].finish(copy=False)
+        feed = ((pin_packed.array, pin_flags.array) for _ in range(n))
+        for _k, res in lg.stream_steps(more, feed, mc, mode_e2e | lg.MODE_COMPACT_OUTPUT, copy=False, tight=True,
+                                       collect=bool(args.e2e_collect)):
+            pass
         return res
     e2e_steps = 0 if args.no_e2e else args.steps
     for _ in range(args.warmup if e2e_steps else 1):

@@ -16,7 +16,7 @@ from ._lib import (DENSE_DEFAULT, LIB_PATH, MODE_ALL_PAIRS, MODE_COMPACT_OUTPUT,
                    PAIR_REC, SITE_HET_SNP, SITE_MISMATCH, SITE_SNP, UNIT_DESC, LgmiError)
 from .api import (Batch, Context, Pipeline, StepResult, default_device, device_count, ecdf, get_context,
                   mean_mismatch_pair_mutual_info, mi_step_batched, mip_and_calls, mismatch_pair_mutual_info,
-                  partition_lpt, site_splice_mutual_info, unit_costs)
+                  partition_lpt, site_splice_mutual_info, stream_schedule, stream_steps, unit_costs)
 from .encode import (EncodedUnit, PlaneBatch, concat_plane_batches, cs_read_mismatches, encode_batch, encode_mismatches,
                      encode_mismatches_native, pack_units)
 from .batched import (analyse_extracted, extract_footprints, extract_region, footprint_bulk_calculation,

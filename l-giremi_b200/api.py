@@ -337,6 +337,49 @@ class Pipeline:
             pass
 
 
+def stream_schedule(n_steps, depth, collect=True):
+    """The order of calls that keeps `depth` steps in flight over `depth` pipelines (step k on pipeline
+    k % depth): yields ('begin', k), ('collect', k), ('finish', k).  After begin(k) the downloads of step
+    k - depth + 2 are queued (collect) and step k - depth + 1 is waited for (finish), so that both directions
+    of the host link always have work queued; the tail finishes what is left, in order."""
+    depth = max(1, int(depth))
+    for k in range(n_steps):
+        yield 'begin', k
+        if collect and depth > 2 and k >= depth - 2:
+            yield 'collect', k - depth + 2
+        if k >= depth - 1:
+            yield 'finish', k - depth + 1
+    for k in range(max(0, n_steps - depth + 1), n_steps):
+        yield 'finish', k
+
+
+def stream_steps(pipes, inputs, min_common, mode=MODE_HET_ONLY, copy=True, packed=False, tight=False, collect=True):
+    """Batch after batch through the pipelined step with len(pipes) steps in flight (stream_schedule): `pipes`
+    are Pipeline objects built for the same unit table, `inputs` an iterable of (planes, site_flags) host arrays
+    (pinned for the copies to be asynchronous; they must stay untouched until their step has been yielded).
+    Yields (k, StepResult) in input order; each result is the synchronous step's, bit for bit.  With copy=False
+    a result's arrays are only valid until the generator is advanced again."""
+    depth = len(pipes)
+    held = {}                                                # step -> its input arrays, alive until finished
+    it = iter(inputs)
+    k = 0
+    for planes, site_flags in it:
+        held[k] = (planes, site_flags)
+        pipes[k % depth].begin(min_common, mode, planes, site_flags, packed=packed, tight=tight)
+        if collect and depth > 2 and k >= depth - 2:
+            pipes[(k - depth + 2) % depth].collect()
+        if k >= depth - 1:
+            j = k - depth + 1
+            res = pipes[j % depth].finish(copy=copy)
+            del held[j]
+            yield j, res
+        k += 1
+    for j in range(max(0, k - depth + 1), k):
+        res = pipes[j % depth].finish(copy=copy)
+        del held[j]
+        yield j, res
+
+
 PIPELINE_MIN_CANDIDATES = 2_000_000   # below this one submit is as fast as a pipelined one
 
 

@@ -591,6 +591,16 @@ def test_two_pipelines_with_steps_in_flight(lg, gpu_ctx):
     for k in (7, 8):
         got, w = pipes[k % 3].finish(), want[k % 3]
         assert np.array_equal(got.records, w.records) and np.array_equal(got.site_mean, w.site_mean, equal_nan=True)
+    # the same through the host helper: lg.stream_steps over three pipelines of one shape
+    same = [lg.Pipeline(gpu_ctx, pbs[2], 1) for _ in range(3)]
+    feed = ((inputs[2], pbs[2].site_flags) for _ in range(7))
+    seen = []
+    for k, got in lg.stream_steps(same, feed, 6, mode, tight=True):
+        seen.append(k)
+        assert np.array_equal(got.records, want[2].records) and np.array_equal(got.site_mean, want[2].site_mean, equal_nan=True)
+    assert seen == list(range(7))
+    for p in same:
+        p.close()
     # and the synchronous call still works on both afterwards
     for p, w in zip(pipes, want):
         assert np.array_equal(p.step(6, mode, tight=True).records, w.records)

@@ -285,3 +285,54 @@ def test_tight_two_plane_form_is_the_padded_form_without_the_padding(lg):
         assert np.array_equal(a[:, 0] & ~a[:, 1], M) and np.array_equal(a[:, 1] & ~a[:, 0], m)
         assert np.array_equal(a[:, 0] | a[:, 1], C)
     assert off == tight.size
+
+
+class _FakePipeline:
+    """Records the calls stream_steps makes and enforces the library's state rules (one step in flight per
+    pipeline: a second begin, or a collect / finish without a begin, is an error)."""
+
+    def __init__(self, log, name):
+        self.log, self.name, self.step, self.collected = log, name, None, False
+
+    def begin(self, min_common, mode, planes, site_flags, packed=False, tight=False):
+        assert self.step is None, "begin on a pipeline whose step has not been finished"
+        self.step, self.collected = int(planes[0]), False
+        self.log.append(('begin', self.step, self.name))
+
+    def collect(self):
+        assert self.step is not None and not self.collected
+        self.collected = True
+        self.log.append(('collect', self.step, self.name))
+
+    def finish(self, copy=True):
+        assert self.step is not None
+        k, self.step = self.step, None
+        self.log.append(('finish', k, self.name))
+        return k
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4, 6])
+def test_stream_steps_keeps_depth_steps_in_flight(lg, depth):
+    """stream_steps / stream_schedule: every step begun, (collected,) finished once and yielded in input order,
+    never more than `depth` in flight, the downloads of the next step queued before the previous one is waited
+    for (depth >= 3), and the calls are exactly stream_schedule's."""
+    for n in (0, 1, 2, 3, 5, 11):
+        log = []
+        pipes = [_FakePipeline(log, q) for q in range(depth)]
+        inputs = ((np.array([k], np.uint32), np.zeros(1, np.uint8)) for k in range(n))
+        out = list(lg.stream_steps(pipes, inputs, 6))
+        assert out == [(k, k) for k in range(n)]
+        assert [(op, k) for op, k, _q in log] == list(lg.stream_schedule(n, depth))
+        assert all(q == k % depth for _op, k, q in log)
+        in_flight = 0
+        for op, k, _q in log:
+            in_flight += (op == 'begin') - (op == 'finish')
+            assert 0 <= in_flight <= depth
+        for op in ('begin', 'finish'):
+            assert [k for o, k, _q in log if o == op] == list(range(n))
+        if depth >= 3:
+            pos = {(op, k): t for t, (op, k, _q) in enumerate(log)}
+            for k in range(n - 1):
+                if ('collect', k + 1) in pos:                # queued before the host waits for step k
+                    assert pos[('collect', k + 1)] < pos[('finish', k)]
+            assert sum(1 for o, _k, _q in log if o == 'collect') == max(0, n - (depth - 2)) if n else True
